@@ -1,0 +1,264 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json metric on its config 2 workload.
+
+A "step" is one whole pass of the hot path over one batch: reset 65,536 deterministic-MADN games per GPU from
+device-resident seeds, then play every game to termination with the reference's random legal policy
+(MuZero_det_MADN/evaluate_agent.py:733-930 do_random: valid_action -> categorical -> env_step / no_step, cap 2000).
+`value` = env steps/s (active (game, iteration) pairs) summed over all GPUs / max-over-ranks device time.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--games G] [--impl reference]
+N > 1 is launched by torchrun (one rank per GPU); games are sharded with no data-path collective (weak scaling).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RULES = dict(enable_teams=True, enable_initial_free_pin=True, enable_circular_board=False, enable_friendly_fire=False,
+             enable_start_blocking=False, enable_jump_in_goal_area=True, enable_start_on_1=True,
+             enable_bonus_turn_on_6=True, must_traverse_start=False)  # MuZero_det_MADN/game_agent.py:12-22
+BYTES_PER_STEP = 226  # SURVEY.md 8(d) cfg 2: 99 B state read + 99 B written + action 2 + mask 24 + reward/done 2
+MAX_STEPS = 2000      # evaluate_agent.py:918
+METRIC = "env steps/s (deterministic MADN, random legal policy to termination)"
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_baseline(games, nthreads, key, seeds_np):
+    """the oracle port on the host cores: same workload, bounded sample of `games` games"""
+    import oracle as O
+    from exploring_muzero_on_dog_b200 import rules as R
+    cfg = O.MadnCfg(4, 0xF, 10, R.to_mask(RULES))
+    t0 = time.perf_counter()
+    s = O.madn_reset(cfg, seeds_np[:games], 0)
+    _, total, _ = O.madn_det_play_random(s, key, MAX_STEPS, nthreads=nthreads)
+    dt = time.perf_counter() - t0
+    return total, dt
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path.  JAX is not installable here (no wheels,
+    no network), so this times the oracle port of MADN/deterministic_madn.py with every host thread."""
+    if rank != 0:
+        return
+    import numpy as np
+    import oracle as O
+    from exploring_muzero_on_dog_b200 import jaxrand
+    cores = os.cpu_count() or 1
+    key = jaxrand.split_host(jaxrand.PRNGKey(0))[1]
+    sample = min(args.games, 4096)
+    seeds = O.randint(key, sample, 0, 1_000_000)
+    for _ in range(min(args.warmup, 1)):
+        cpu_baseline(min(sample, 512), cores, key, seeds)
+    tot, dt = 0, 0.0
+    for _ in range(args.steps):
+        a, b = cpu_baseline(sample, cores, key, seeds)
+        tot += a
+        dt += b
+    v = tot / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "env_steps/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int8", "data": "synthetic",
+            "config": {"workload": "cfg2: deterministic MADN 4 players, random legal policy to termination",
+                       "games_per_step": sample, "max_steps": MAX_STEPS, "rules": "MuZero_det_MADN/game_agent.py:12-22"},
+            "cpu_baseline": {"value": v, "unit": "env_steps/s", "cores": cores, "kind": "port",
+                             "sample": f"{sample} of {args.games} games per step, played to termination, {args.steps} steps"},
+            "e2e": {"value": v, "unit": "env_steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--games", type=int, default=65536, help="lockstep games per GPU")
+    ap.add_argument("--impl", default="dogstep", choices=["dogstep", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from exploring_muzero_on_dog_b200 import jaxrand
+    from exploring_muzero_on_dog_b200.MADN import deterministic_madn as dm
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.games
+    offset = rank * n                                    # rank r owns global games [r*n, (r+1)*n)
+    key = jaxrand.split_host(jaxrand.PRNGKey(0))[1]      # subkey = split(PRNGKey(0))[1]  (game_agent.py:187)
+    all_seeds = jaxrand.randint(key, n * world, 0, 1_000_000, device=dev)  # seeds = randint(subkey,(N,),0,1e6) (:188)
+    seeds = all_seeds[offset:offset + n].contiguous()
+    seeds_host = seeds.cpu().pin_memory()
+    total = torch.zeros(1, dtype=torch.int64, device=dev)
+    glen = torch.empty(n, dtype=torch.int32, device=dev)
+    env = dm.env_reset(0, seed=seeds, **RULES, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def one_step(seed_t):
+        e = dm.env_reset(0, seed=seed_t, **RULES, device=dev)
+        dm.play_random(e, key, max_steps=MAX_STEPS, game_offset=offset, game_len=glen, total_steps=total)
+        return e
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        one_step(seeds)
+    barrier()
+
+    # ---- timed region 1: inputs resident in HBM; L2 flushed between steps; per-kernel events for the roofline
+    total.zero_()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    clocks = ClockSampler(local)
+    clocks.start()
+    barrier()
+    for s in range(args.steps):
+        flush.fill_(s & 0xFF)
+        ev[s][0].record()
+        e = dm.env_reset(0, seed=seeds, **RULES, device=dev)
+        ev[s][1].record()
+        dm.play_random(e, key, max_steps=MAX_STEPS, game_offset=offset, game_len=glen, total_steps=total)
+        ev[s][2].record()
+    barrier()
+    clk = clocks.stop()
+    step_ms = [ev[s][0].elapsed_time(ev[s][2]) for s in range(args.steps)]
+    play_ms = [ev[s][1].elapsed_time(ev[s][2]) for s in range(args.steps)]
+    my_ms = sum(step_ms)
+    my_steps = int(total.item())
+
+    # ---- timed region 2 (e2e): host seeds in pinned memory -> H2D -> public API -> D2H of the results
+    res_host = {k: torch.empty(s, dtype=d).pin_memory() for k, (s, d) in
+                {"game_len": ((n,), torch.int32), "reward": ((n,), torch.int8), "done": ((n,), torch.bool),
+                 "pins": ((n, 4, 4), torch.int8)}.items()}
+    seeds_dev = torch.empty_like(seeds)
+    total.zero_()
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for s in range(args.steps):
+        seeds_dev.copy_(seeds_host, non_blocking=True)
+        e = one_step(seeds_dev)
+        res_host["game_len"].copy_(glen, non_blocking=True)
+        res_host["reward"].copy_(e.raw("reward"), non_blocking=True)
+        res_host["done"].copy_(e.raw("done"), non_blocking=True)
+        res_host["pins"].copy_(e.raw("pins"), non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the caller consumes the results every step
+    t1.record()
+    barrier()
+    e2e_ms = t0.elapsed_time(t1)
+    e2e_steps = int(total.item())
+    assert bool(res_host["done"].all()), "games did not terminate"
+    h2d = seeds_host.numel() * 4
+    d2h = sum(t.numel() * t.element_size() for t in res_host.values())
+
+    if world > 1:
+        t = torch.tensor([my_ms, e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        c = torch.tensor([my_steps, e2e_steps], dtype=torch.int64, device=dev)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        max_ms, e2e_max_ms = t.tolist()
+        all_steps, all_e2e_steps = c.tolist()
+    else:
+        max_ms, e2e_max_ms, all_steps, all_e2e_steps = my_ms, e2e_ms, my_steps, e2e_steps
+
+    if rank == 0:
+        peak, peak_src = _peaks()
+        play_s = sum(play_ms) / 1e3
+        achieved = my_steps * BYTES_PER_STEP / play_s / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+                traffic = json.load(f).get("k_madn_det_play_random_dram_bytes_per_launch")
+        except Exception:
+            pass
+        line = {
+            "metric": METRIC, "value": all_steps / (max_ms / 1e3), "unit": "env_steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": max_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
+            "config": {"workload": "cfg2: deterministic MADN 4 players, 65,536 lockstep games per GPU, random legal policy to termination",
+                       "games_per_gpu": n, "max_steps": MAX_STEPS, "rules": "MuZero_det_MADN/game_agent.py:12-22",
+                       "env_steps_per_pass_per_gpu": my_steps // args.steps, "l2": "flushed between timed steps (256 MiB write)",
+                       "parallelism": f"games sharded x{world}, no collective on the stepping path"},
+            "e2e": {"value": all_e2e_steps / (e2e_max_ms / 1e3), "unit": "env_steps/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_max_ms / args.steps},
+            "gpu_launches": 2 * args.steps,
+            "roofline": {"bound": "hbm", "kernel": "k_madn_det_play_random", "achieved": achieved, "peak": peak,
+                         "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "algorithmic_bytes_per_env_step": BYTES_PER_STEP, "kernel_ms_per_launch": sum(play_ms) / args.steps,
+                         "note": "algorithmic bytes of the per-step reference dataflow; the persistent kernel keeps a game in registers, so it is integer-ALU bound, not HBM bound"},
+            "clocks": clk,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            seeds_np = seeds.cpu().numpy()
+            est_steps, est_dt = cpu_baseline(256, cores, key, seeds_np)
+            rate = est_steps / est_dt
+            sample = int(min(n, max(256, (12.0 * rate) / (est_steps / 256))))
+            tot, dt = cpu_baseline(sample, cores, key, seeds_np)
+            line["cpu_baseline"] = {"value": tot / dt, "unit": "env_steps/s", "cores": cores, "kind": "port",
+                                    "sample": f"first {sample} of the {n} games, played to termination once ({tot} env steps, {dt:.1f} s)"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,201 @@
+"""Host mirror of the reference's MADN/deterministic_madn.py for the self-play hot path.
+
+Same function names, argument order and return tuples as the reference
+(/root/reference/MADN/deterministic_madn.py): env_reset :42, env_step :170, set_pins_on_board :259,
+no_step :283, valid_action :299, encode_board :395, map_action :469 — but every function is
+already "vmapped": it takes the batched env (leaves with a leading game axis, CUDA tensors) and runs
+one libdogstep.so kernel over all games.  An env built from a scalar seed behaves like the
+reference's single env.  Functions are pure by default (the input env is left intact, as in JAX);
+pass `inplace=True` on the hot path to update the leaves in place (what jax.ffi does with
+input_output_aliases).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .. import _lib, rules as _rules
+from ._state import BatchedEnv, to_dev
+
+RULE_KEYS = ("enable_teams", "enable_initial_free_pin", "enable_circular_board", "enable_start_blocking",
+             "enable_jump_in_goal_area", "enable_friendly_fire", "enable_start_on_1", "enable_bonus_turn_on_6",
+             "must_traverse_start")
+
+
+def _layout_mask(layout):
+    if layout is None:
+        return 0xF
+    a = np.asarray(layout.cpu() if isinstance(layout, torch.Tensor) else layout).astype(bool).ravel()
+    return int(sum(1 << i for i in range(min(4, a.size)) if a[i]))
+
+
+def _geometry(num_players, layout_mask, distance):
+    """start / target / goal rows exactly as env_reset builds them (:70-78)."""
+    cnt = bin(layout_mask).count("1")
+    if cnt != num_players or (layout_mask == 0xF and num_players < 4):
+        layout_mask = (1 << num_players) - 1
+    seats = [i for i in range(4) if (layout_mask >> i) & 1]
+    bs = 4 * distance
+    start = np.array([i * distance for i in seats], np.int8)
+    target = ((start.astype(np.int32) - 1) % bs).astype(np.int8)
+    goal = np.array([[bs + 4 * i + k for k in range(4)] for i in seats], np.int8)
+    return start, target, goal
+
+
+class deterministic_MADN(BatchedEnv):
+    """Batched leaves of the reference dataclass (:24-40)."""
+
+    LEAVES = {
+        "board": (torch.int8, lambda s: (s["total_board_size"],)),
+        "current_player": (torch.int8, lambda s: ()),
+        "pins": (torch.int8, lambda s: (s["num_players"], 4)),
+        "reward": (torch.int8, lambda s: ()),
+        "done": (torch.bool, lambda s: ()),
+        "action_set": (torch.int8, lambda s: (s["num_players"], 6)),
+        "key": (torch.uint32, lambda s: (2,)),
+    }
+
+    # start / target / goal are per-env leaves in the reference; they are constants of the cfg here
+    def _const(self, name):
+        a = torch.as_tensor(self.static["_" + name], device=self.device)
+        return a.expand((self.n,) + tuple(a.shape)) if self.batched else a
+
+    @property
+    def start(self):
+        return self._const("start")
+
+    @property
+    def target(self):
+        return self._const("target")
+
+    @property
+    def goal(self):
+        return self._const("goal")
+
+    def cfg(self):
+        s = self.static
+        return _lib.MadnCfg(s["num_players"], s["layout_mask"], s["board_size"] // 4, _rules.to_mask(s["rules"]))
+
+    def cstate(self):
+        t = self._t
+        return _lib.MadnDetState(*[C.c_void_p(t[k].data_ptr()) for k in
+                                   ("board", "current_player", "pins", "reward", "done", "action_set", "key")])
+
+
+def env_reset(_, num_players=4, layout=None, distance=10, starting_player=0, seed=42, enable_teams=False,
+              enable_initial_free_pin=False, enable_circular_board=True, enable_start_blocking=False,
+              enable_jump_in_goal_area=True, enable_friendly_fire=False, enable_start_on_1=True,
+              enable_bonus_turn_on_6=True, must_traverse_start=False, device="cuda"):
+    """env_reset (:42-120).  `seed` may be a scalar (single env) or an int array [n] (what
+    jax.vmap(env_reset_batched) receives, game_agent.py:24-44)."""
+    num_players, distance = int(num_players), int(distance)
+    batched = np.ndim(seed.cpu() if isinstance(seed, torch.Tensor) else seed) > 0
+    seeds = to_dev(np.atleast_1d(seed.cpu().numpy() if isinstance(seed, torch.Tensor) else np.asarray(seed)),
+                   torch.int32, device)
+    lm = _layout_mask(layout)
+    start, target, goal = _geometry(num_players, lm, distance)
+    rules = dict(enable_teams=bool(enable_teams) and num_players == 4,
+                 enable_initial_free_pin=bool(enable_initial_free_pin),
+                 enable_circular_board=bool(enable_circular_board), enable_start_blocking=bool(enable_start_blocking),
+                 enable_jump_in_goal_area=bool(enable_jump_in_goal_area), enable_friendly_fire=bool(enable_friendly_fire),
+                 enable_start_on_1=bool(enable_start_on_1), enable_bonus_turn_on_6=bool(enable_bonus_turn_on_6),
+                 must_traverse_start=bool(must_traverse_start))
+    static = dict(num_players=num_players, board_size=4 * distance, total_board_size=4 * distance + 16, rules=rules,
+                  layout_mask=lm, _start=start, _target=target, _goal=goal)
+    env = deterministic_MADN(int(seeds.numel()), static, torch.device(device), batched)
+    env.alloc()
+    cfg, st = env.cfg(), env.cstate()
+    _lib.check(_lib.lib().dogstep_madn_det_reset(C.byref(st), C.c_int64(env.n), C.byref(cfg), _lib.ptr(seeds),
+                                                C.c_int32(int(starting_player)), _lib.stream()), "madn_det_reset")
+    return env
+
+
+def _out(env, t):
+    return t if env.batched else t[0]
+
+
+def valid_action(env):
+    """valid_action (:299-393) -> bool [n, 4, 6] (or [4, 6] for a single env)."""
+    mask = torch.empty((env.n, 4, 6), dtype=torch.uint8, device=env.device)
+    cfg, st = env.cfg(), env.cstate()
+    _lib.check(_lib.lib().dogstep_madn_det_valid_action(C.byref(st), C.c_int64(env.n), C.byref(cfg), _lib.ptr(mask),
+                                                       _lib.stream()), "madn_det_valid_action")
+    return _out(env, mask.view(torch.bool))
+
+
+def env_step(env, action, inplace=False):
+    """env_step (:170-257).  action = [pin, move] per game -> (env, reward int8, done bool)."""
+    if not inplace:
+        env = env.clone()
+    act = to_dev(action, torch.int8, env.device).reshape(env.n, 2)
+    reward = torch.empty(env.n, dtype=torch.int8, device=env.device)
+    done = torch.empty(env.n, dtype=torch.bool, device=env.device)
+    cfg, st = env.cfg(), env.cstate()
+    _lib.check(_lib.lib().dogstep_madn_det_step(C.byref(st), C.c_int64(env.n), C.byref(cfg), _lib.ptr(act), _lib.ptr(reward),
+                                               _lib.ptr(done), _lib.stream()), "madn_det_step")
+    return env, _out(env, reward), _out(env, done)
+
+
+def no_step(env, inplace=False):
+    """no_step (:283-297) -> (env, 0, env.done)."""
+    if not inplace:
+        env = env.clone()
+    reward = torch.empty(env.n, dtype=torch.int8, device=env.device)
+    done = torch.empty(env.n, dtype=torch.bool, device=env.device)
+    cfg, st = env.cfg(), env.cstate()
+    _lib.check(_lib.lib().dogstep_madn_det_no_step(C.byref(st), C.c_int64(env.n), C.byref(cfg), _lib.ptr(reward),
+                                                  _lib.ptr(done), _lib.stream()), "madn_det_no_step")
+    return env, _out(env, reward), _out(env, done)
+
+
+def set_pins_on_board(board, pins, distance=None):
+    """set_pins_on_board (:259-271): board int8[..., total], pins int8[..., P, 4] -> new board."""
+    dev = board.device if isinstance(board, torch.Tensor) and board.is_cuda else torch.device("cuda")
+    board = to_dev(board, torch.int8, dev)
+    pins = to_dev(pins, torch.int8, dev)
+    total, P = board.shape[-1], pins.shape[-2]
+    n = pins.numel() // (P * 4)
+    out = torch.empty((n, total), dtype=torch.int8, device=dev)
+    cfg = _lib.MadnCfg(P, (1 << P) - 1, (total - 16) // 4, 0)
+    _lib.check(_lib.lib().dogstep_madn_set_pins_on_board(_lib.ptr(pins.reshape(n, P, 4).contiguous()), _lib.ptr(out),
+                                                        C.c_int64(n), C.byref(cfg), _lib.stream()), "set_pins_on_board")
+    return out.reshape(board.shape)
+
+
+def encode_board(env, dtype=torch.int8):
+    """encode_board (:395-438) -> [n, 8*P+2, total].  The reference's result is int32 by NumPy
+    promotion; values are identical, int8 is the compact device layout (pass dtype to widen)."""
+    P, T = env.static["num_players"], env.static["total_board_size"]
+    obs = torch.empty((env.n, 8 * P + 2, T), dtype=torch.int8, device=env.device)
+    cfg, st = env.cfg(), env.cstate()
+    _lib.check(_lib.lib().dogstep_madn_det_encode_board(C.byref(st), C.c_int64(env.n), C.byref(cfg), _lib.ptr(obs),
+                                                       _lib.stream()), "madn_det_encode_board")
+    return _out(env, obs if dtype == torch.int8 else obs.to(dtype))
+
+
+def map_action(action_index):
+    """map_action (:469-479): idx -> [idx // 6, idx % 6 + 1] as int8."""
+    a = action_index if isinstance(action_index, torch.Tensor) else torch.as_tensor(action_index)
+    return torch.stack([(a // 6).to(torch.int8), (a % 6 + 1).to(torch.int8)], dim=-1)
+
+
+def random_step(env, rng_key, game_offset=0, active_count=None):
+    """One fused lockstep iteration of the random-legal-policy driver
+    (MuZero_det_MADN/evaluate_agent.py:733-930, do_random), in place."""
+    cfg, st = env.cfg(), env.cstate()
+    _lib.check(_lib.lib().dogstep_madn_det_random_step(C.byref(st), C.c_int64(env.n), C.byref(cfg), _lib.host_key(rng_key),
+                                                      C.c_int64(game_offset), _lib.ptr(active_count), _lib.stream()),
+               "madn_det_random_step")
+    return env
+
+
+def play_random(env, rng_key, max_steps=2000, game_offset=0, game_len=None, total_steps=None):
+    """The whole random-policy while_loop (evaluate_agent.py:733-930, cap :918) as one persistent
+    kernel, in place.  Returns (env, game_len int32[n])."""
+    if game_len is None:
+        game_len = torch.empty(env.n, dtype=torch.int32, device=env.device)
+    cfg, st = env.cfg(), env.cstate()
+    _lib.check(_lib.lib().dogstep_madn_det_play_random(C.byref(st), C.c_int64(env.n), C.byref(cfg), _lib.host_key(rng_key),
+                                                      C.c_int64(game_offset), C.c_int32(max_steps), _lib.ptr(game_len),
+                                                      _lib.ptr(total_steps), _lib.stream()), "madn_det_play_random")
+    return env, game_len

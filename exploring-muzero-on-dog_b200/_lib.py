@@ -1,0 +1,73 @@
+"""ctypes binding of libdogstep.so (the C-ABI declared in include/dogstep.h).
+
+There is deliberately no fallback: if the CUDA library is missing or a call fails, this module
+raises.  PyTorch is used only as the owner of device memory and streams.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdogstep.so")
+_lib = None
+
+ERRORS = {-1: "invalid argument", -2: "unsupported configuration", -3: "CUDA failure"}
+
+
+class DogstepError(RuntimeError):
+    pass
+
+
+class MadnCfg(C.Structure):
+    _fields_ = [("num_players", C.c_int32), ("layout_mask", C.c_int32), ("distance", C.c_int32), ("rules", C.c_uint32)]
+
+
+class MadnDetState(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("board", "current_player", "pins", "reward", "done", "action_set", "key")]
+
+
+class MadnClsState(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("board", "current_player", "pins", "reward", "done", "die", "key")]
+
+
+def lib():
+    """Load libdogstep.so; raise loudly when it has not been built (python __graft_entry__.py build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise DogstepError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). There is no CPU fallback.")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.dogstep_last_error.restype = C.c_char_p
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().dogstep_last_error().decode() if rc == -3 else ""
+        raise DogstepError(f"{what} failed: {ERRORS.get(rc, rc)} {msg}")
+
+
+def ptr(t):
+    """device pointer of a CUDA tensor (None -> NULL)"""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise DogstepError("dogstep kernels need CUDA tensors; there is no CPU path")
+    if not t.is_contiguous():
+        raise DogstepError("dogstep kernels need contiguous tensors")
+    return C.c_void_p(t.data_ptr())
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def host_key(key):
+    """uint32[2] host array from a tensor / ndarray / sequence"""
+    if isinstance(key, torch.Tensor):
+        key = key.detach().cpu().tolist()
+    k = [int(x) & 0xFFFFFFFF for x in list(key)]
+    return (C.c_uint32 * 2)(k[0], k[1])

@@ -1,0 +1,112 @@
+// jaxrand.cuh — on-device restatement of jax.random (jax 0.8.1, threefry2x32, partitionable
+// mode) as the reference's hot path uses it:
+//   MADN/deterministic_madn.py:60-62, MADN/classic_madn.py:70-72,238-240, DOG/dog.py:102-104,246-247,
+//   MuZero_det_MADN/game_agent.py:60,187-188, MuZero_det_MADN/evaluate_agent.py:337,741.
+// Algorithms: Random123 Threefry-2x32-20; jax/_src/prng.py (_threefry_split_foldlike,
+// _threefry_random_bits_partitionable); jax/_src/random.py (uniform, randint, choice, gumbel).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace dogstep {
+
+struct Key2 {
+  uint32_t a, b;
+};
+
+__host__ __device__ __forceinline__ uint32_t rotl32(uint32_t x, int r) {
+#ifdef __CUDA_ARCH__
+  return __funnelshift_l(x, x, r);
+#else
+  return (x << r) | (x >> (32 - r));
+#endif
+}
+
+// Threefry-2x32, 20 rounds.  Fully unrolled: 20 x (IADD, SHF, LOP) + 5 key injections.
+__host__ __device__ __forceinline__ Key2 threefry2x32(Key2 k, uint32_t c0, uint32_t c1) {
+  const uint32_t ks0 = k.a, ks1 = k.b, ks2 = k.a ^ k.b ^ 0x1BD11BDAu;
+  uint32_t x0 = c0 + ks0, x1 = c1 + ks1;
+#define DOGSTEP_TF_ROUND(r) \
+  x0 += x1;                 \
+  x1 = rotl32(x1, r);       \
+  x1 ^= x0;
+  DOGSTEP_TF_ROUND(13) DOGSTEP_TF_ROUND(15) DOGSTEP_TF_ROUND(26) DOGSTEP_TF_ROUND(6)
+  x0 += ks1; x1 += ks2 + 1u;
+  DOGSTEP_TF_ROUND(17) DOGSTEP_TF_ROUND(29) DOGSTEP_TF_ROUND(16) DOGSTEP_TF_ROUND(24)
+  x0 += ks2; x1 += ks0 + 2u;
+  DOGSTEP_TF_ROUND(13) DOGSTEP_TF_ROUND(15) DOGSTEP_TF_ROUND(26) DOGSTEP_TF_ROUND(6)
+  x0 += ks0; x1 += ks1 + 3u;
+  DOGSTEP_TF_ROUND(17) DOGSTEP_TF_ROUND(29) DOGSTEP_TF_ROUND(16) DOGSTEP_TF_ROUND(24)
+  x0 += ks1; x1 += ks2 + 4u;
+  DOGSTEP_TF_ROUND(13) DOGSTEP_TF_ROUND(15) DOGSTEP_TF_ROUND(26) DOGSTEP_TF_ROUND(6)
+  x0 += ks2; x1 += ks0 + 5u;
+#undef DOGSTEP_TF_ROUND
+  return Key2{x0, x1};
+}
+
+// jax.random.PRNGKey(int32 seed) -> raw key [0, seed]
+__host__ __device__ __forceinline__ Key2 prng_key(int32_t seed) { return Key2{0u, (uint32_t)seed}; }
+
+// jax.random.split(key, n)[i]
+__host__ __device__ __forceinline__ Key2 split_i(Key2 k, uint32_t i) { return threefry2x32(k, 0u, i); }
+
+// jax.random.bits(key, (n,), uint32)[i]
+__host__ __device__ __forceinline__ uint32_t bits_i(Key2 k, uint32_t i) {
+  Key2 o = threefry2x32(k, 0u, i);
+  return o.a ^ o.b;
+}
+
+__host__ __device__ __forceinline__ float bits_to_unit_float(uint32_t bits) {
+  uint32_t u = (bits >> 9) | 0x3F800000u;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(u) - 1.0f;
+#else
+  float f;
+  memcpy(&f, &u, 4);
+  return f - 1.0f;
+#endif
+}
+
+// jax.random.uniform(key, shape, f32, minval, maxval)[i]; explicit mul/add so no FMA contraction
+__device__ __forceinline__ float uniform_i(Key2 k, uint32_t i, float minval, float maxval) {
+  float f = bits_to_unit_float(bits_i(k, i));
+  float v = __fadd_rn(__fmul_rn(f, __fsub_rn(maxval, minval)), minval);
+  return fmaxf(minval, v);
+}
+
+// jax.random.randint(key, shape, lo, hi)[i] (uint32 arithmetic with wraparound)
+__host__ __device__ __forceinline__ int32_t randint_i(Key2 k, uint32_t i, int32_t lo, int32_t hi) {
+  Key2 k1 = split_i(k, 0), k2 = split_i(k, 1);
+  uint32_t hb = bits_i(k1, i), lb = bits_i(k2, i);
+  uint32_t span = (hi <= lo) ? 1u : (uint32_t)(hi - lo);
+  uint32_t mult = 65536u % span;
+  mult = (mult * mult) % span;
+  uint32_t off = ((hb % span) * mult + (lb % span)) % span;
+  return (int32_t)((uint32_t)lo + off);
+}
+
+// jax.random.gumbel "low" mode sample i.  logf is CUDA's (<= 1 ulp); see DESIGN.md on float parity.
+__device__ __forceinline__ float gumbel_i(Key2 k, uint32_t i) {
+  float u = uniform_i(k, i, 1.17549435e-38f, 1.0f);
+  return -logf(-logf(u));
+}
+
+// jax.random.choice(key, 6 items, p) -> index; cumsum uses XLA:CPU's association for n = 6.
+__device__ __forceinline__ int choice6(Key2 k, const float p[6]) {
+  float s01 = __fadd_rn(p[0], p[1]), s23 = __fadd_rn(p[2], p[3]), s45 = __fadd_rn(p[4], p[5]);
+  float c[6];
+  c[0] = p[0];
+  c[1] = s01;
+  c[2] = __fadd_rn(s01, p[2]);
+  c[3] = __fadd_rn(s01, s23);
+  c[4] = __fadd_rn(c[3], p[4]);
+  c[5] = __fadd_rn(c[3], s45);
+  float u = uniform_i(k, 0, 0.0f, 1.0f);
+  float r = __fmul_rn(c[5], __fsub_rn(1.0f, u));
+  int idx = 0;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) idx += (c[j] < r);
+  return idx > 5 ? 5 : idx;
+}
+
+}  // namespace dogstep

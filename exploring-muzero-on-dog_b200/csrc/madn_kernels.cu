@@ -1,0 +1,596 @@
+// madn_kernels.cu — CUDA kernels (sm_100a) + C-ABI for deterministic and classic MADN.
+//
+// Layout in HBM = the batched leaves of the reference pytrees (structure of arrays, game axis
+// leading): board int8[n,56], current_player int8[n], pins int8[n,4,4], reward int8[n],
+// done u8[n], action_set int8[n,4,6] / die int8[n], key u32[n,2].  One game per thread; a thread
+// pulls its game into registers (bitboards + packed bytes, madn_core.cuh), applies the rules and
+// writes the leaves back.  Kernels are HBM/launch bound (99 mutable bytes per game and step); the
+// persistent play_random kernel keeps the game in registers across all lockstep iterations.
+#include <cstdint>
+#include <cstdio>
+#include <cuda_runtime.h>
+#include "../../include/dogstep.h"
+#include "common.cuh"
+#include "jaxrand.cuh"
+#include "madn_core.cuh"
+
+namespace dogstep {
+
+constexpr int kThreads = 128;
+
+struct MadnPtrs {
+  int8_t* board;
+  int8_t* cur;
+  int8_t* pins;
+  int8_t* reward;
+  uint8_t* done;
+  int8_t* aset;  // det only
+  int8_t* die;   // classic only
+  uint32_t* key;
+};
+
+// ---- board bytes <-> bitboards ---------------------------------------------------------------
+__device__ __forceinline__ void board_word_to_occ(uint32_t w, int c, uint64_t occ[4]) {
+  const uint32_t L = 0x01010101u;
+  uint32_t occm = (~w >> 7) & L, b0 = w & L, b1 = (w >> 1) & L;
+  uint32_t e0 = occm & ~b0 & ~b1, e1 = occm & b0 & ~b1, e2 = occm & ~b0 & b1, e3 = occm & b0 & b1;
+  occ[0] |= (uint64_t)((e0 * 0x01020408u) >> 24) << c;
+  occ[1] |= (uint64_t)((e1 * 0x01020408u) >> 24) << c;
+  occ[2] |= (uint64_t)((e2 * 0x01020408u) >> 24) << c;
+  occ[3] |= (uint64_t)((e3 * 0x01020408u) >> 24) << c;
+}
+
+__device__ __forceinline__ uint32_t occ_to_board_word(const uint64_t occ[4], int c) {
+  const uint32_t L = 0x01010101u, S = 0x00204081u;
+  uint32_t e0 = (((uint32_t)(occ[0] >> c) & 0xFu) * S) & L;
+  uint32_t e1 = (((uint32_t)(occ[1] >> c) & 0xFu) * S) & L;
+  uint32_t e2 = (((uint32_t)(occ[2] >> c) & 0xFu) * S) & L;
+  uint32_t e3 = (((uint32_t)(occ[3] >> c) & 0xFu) * S) & L;
+  uint32_t any = e0 | e1 | e2 | e3;
+  uint32_t val = (e1 | e3) | ((e2 | e3) << 1);
+  return val | ((any ^ L) * 0xFFu);
+}
+
+template <bool DET>
+__device__ __forceinline__ void load_state(const MadnGeom& g, const MadnPtrs& p, int64_t i, MadnRegs& s) {
+  const uint32_t* bw = reinterpret_cast<const uint32_t*>(p.board + i * g.total);
+  s.occ[0] = s.occ[1] = s.occ[2] = s.occ[3] = 0ull;
+  const int nw = g.total >> 2;
+  for (int w = 0; w < nw; ++w) board_word_to_occ(__ldg(bw + w), 4 * w, s.occ);
+  if (g.n == 4) {
+    uint4 v = __ldg(reinterpret_cast<const uint4*>(p.pins) + i);
+    s.pins[0] = v.x; s.pins[1] = v.y; s.pins[2] = v.z; s.pins[3] = v.w;
+  } else {
+    const uint32_t* pw = reinterpret_cast<const uint32_t*>(p.pins) + i * g.n;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) s.pins[q] = (q < g.n) ? __ldg(pw + q) : 0xFFFFFFFFu;
+  }
+  if (DET) {
+    if (g.n == 4) {
+      const uint64_t* aw = reinterpret_cast<const uint64_t*>(p.aset) + i * 3;
+      uint64_t q0 = __ldg(aw), q1 = __ldg(aw + 1), q2 = __ldg(aw + 2);
+      const uint64_t M = 0xFFFFFFFFFFFFull;
+      s.as[0] = q0 & M;
+      s.as[1] = ((q0 >> 48) | (q1 << 16)) & M;
+      s.as[2] = ((q1 >> 32) | (q2 << 32)) & M;
+      s.as[3] = q2 >> 16;
+    } else {
+      const uint16_t* aw = reinterpret_cast<const uint16_t*>(p.aset) + i * g.n * 3;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint64_t v = 0;
+        if (q < g.n) v = (uint64_t)__ldg(aw + q * 3) | ((uint64_t)__ldg(aw + q * 3 + 1) << 16) | ((uint64_t)__ldg(aw + q * 3 + 2) << 32);
+        s.as[q] = v;
+      }
+    }
+    s.die = 0;
+  } else {
+    s.as[0] = s.as[1] = s.as[2] = s.as[3] = 0ull;
+    s.die = (int)p.die[i];
+  }
+  s.cur = (int)p.cur[i];
+  s.done = p.done[i] != 0;
+  s.reward = (int)p.reward[i];
+}
+
+__device__ __forceinline__ void store_board(const MadnGeom& g, int8_t* board, int64_t i, const MadnRegs& s) {
+  uint32_t* bw = reinterpret_cast<uint32_t*>(board + i * g.total);
+  const int nw = g.total >> 2;
+  for (int w = 0; w < nw; ++w) bw[w] = occ_to_board_word(s.occ, 4 * w);
+}
+
+__device__ __forceinline__ void store_pins(const MadnGeom& g, int8_t* pins, int64_t i, const MadnRegs& s) {
+  if (g.n == 4) {
+    reinterpret_cast<uint4*>(pins)[i] = make_uint4(s.pins[0], s.pins[1], s.pins[2], s.pins[3]);
+  } else {
+    uint32_t* pw = reinterpret_cast<uint32_t*>(pins) + i * g.n;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (q < g.n) pw[q] = s.pins[q];
+  }
+}
+
+__device__ __forceinline__ void store_aset(const MadnGeom& g, int8_t* aset, int64_t i, const MadnRegs& s) {
+  if (g.n == 4) {
+    uint64_t* aw = reinterpret_cast<uint64_t*>(aset) + i * 3;
+    aw[0] = s.as[0] | (s.as[1] << 48);
+    aw[1] = (s.as[1] >> 16) | (s.as[2] << 32);
+    aw[2] = (s.as[2] >> 32) | (s.as[3] << 16);
+  } else {
+    uint16_t* aw = reinterpret_cast<uint16_t*>(aset) + i * g.n * 3;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (q < g.n) {
+        aw[q * 3] = (uint16_t)s.as[q];
+        aw[q * 3 + 1] = (uint16_t)(s.as[q] >> 16);
+        aw[q * 3 + 2] = (uint16_t)(s.as[q] >> 32);
+      }
+  }
+}
+
+// ---- kernels ----------------------------------------------------------------------------------
+template <bool DET>
+__global__ void __launch_bounds__(kThreads) k_madn_reset(const __grid_constant__ MadnGeom g, MadnPtrs p, int64_t n,
+                                                         const int32_t* __restrict__ seeds, int starting_player) {
+  int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n) return;
+  Key2 k0 = prng_key(seeds[i]);
+  Key2 knew = split_i(k0, 0), sub = split_i(k0, 1);
+  int sp = starting_player;
+  if (sp < 0 || sp >= g.n) sp = randint_i(sub, 0, 0, g.n);
+  MadnRegs s;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint32_t w = 0xFFFFFFFFu;
+    if (q < g.n && DS_RULE(g, DOGSTEP_RULE_INITIAL_FREE_PIN)) w = 0xFFFFFF00u | (uint32_t)g.start[q];
+    s.pins[q] = w;
+    s.as[q] = 0x040404040404ull;
+  }
+  rebuild_occ(g, s);
+  store_board(g, p.board, i, s);
+  store_pins(g, p.pins, i, s);
+  if (DET) store_aset(g, p.aset, i, s);
+  else p.die[i] = 0;
+  p.cur[i] = (int8_t)sp;
+  p.reward[i] = 0;
+  p.done[i] = 0;
+  p.key[2 * i] = knew.a;
+  p.key[2 * i + 1] = knew.b;
+}
+
+__global__ void __launch_bounds__(kThreads) k_madn_set_pins_on_board(const __grid_constant__ MadnGeom g,
+                                                                     const int8_t* __restrict__ pins,
+                                                                     int8_t* __restrict__ board, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n) return;
+  MadnRegs s;
+  const uint32_t* pw = reinterpret_cast<const uint32_t*>(pins) + i * g.n;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) s.pins[q] = (q < g.n) ? __ldg(pw + q) : 0xFFFFFFFFu;
+  rebuild_occ(g, s);
+  store_board(g, board, i, s);
+}
+
+template <bool DET>
+__global__ void __launch_bounds__(kThreads) k_madn_valid_action(const __grid_constant__ MadnGeom g, MadnPtrs p, int64_t n,
+                                                                uint8_t* __restrict__ mask) {
+  int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n) return;
+  MadnRegs s;
+  load_state<DET>(g, p, i, s);
+  if (DET) {
+    uint32_t m = madn_det_valid_mask(g, s);
+    uint64_t* out = reinterpret_cast<uint64_t*>(mask) + i * 3;  // 24 bytes, 8-aligned
+#pragma unroll
+    for (int w = 0; w < 3; ++w) {
+      uint32_t bits = (m >> (8 * w)) & 0xFFu;
+      // spread 8 bits to 8 bytes
+      uint64_t lo = ((bits & 0xFu) * 0x00204081u) & 0x01010101u;
+      uint64_t hi = (((bits >> 4) & 0xFu) * 0x00204081u) & 0x01010101u;
+      out[w] = lo | (hi << 32);
+    }
+  } else {
+    uint32_t m = madn_cls_valid_mask(g, s);
+    reinterpret_cast<uint32_t*>(mask)[i] = ((m & 0xFu) * 0x00204081u) & 0x01010101u;
+  }
+}
+
+template <bool DET>
+__global__ void __launch_bounds__(kThreads) k_madn_step(const __grid_constant__ MadnGeom g, MadnPtrs p, int64_t n,
+                                                        const int8_t* __restrict__ action, int8_t* __restrict__ reward,
+                                                        uint8_t* __restrict__ done) {
+  int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n) return;
+  MadnRegs s;
+  load_state<DET>(g, p, i, s);
+  if (DET) {
+    uint32_t m = madn_det_valid_mask(g, s);
+    madn_det_step(g, s, (int)action[2 * i], (int)action[2 * i + 1], m);
+    store_aset(g, p.aset, i, s);
+  } else {
+    uint32_t m = madn_cls_valid_mask(g, s);
+    madn_cls_step(g, s, (int)action[i], m);
+  }
+  store_board(g, p.board, i, s);
+  store_pins(g, p.pins, i, s);
+  p.cur[i] = (int8_t)s.cur;
+  p.reward[i] = (int8_t)s.reward;
+  p.done[i] = (uint8_t)s.done;
+  if (reward) reward[i] = (int8_t)s.reward;
+  if (done) done[i] = (uint8_t)s.done;
+}
+
+template <bool DET>
+__global__ void __launch_bounds__(kThreads) k_madn_no_step(const __grid_constant__ MadnGeom g, MadnPtrs p, int64_t n,
+                                                           int8_t* __restrict__ reward, uint8_t* __restrict__ done) {
+  int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n) return;
+  int pid = (int)p.cur[i];
+  if (DET && pid >= -g.n && pid < g.n) {
+    int row = gidx(pid, g.n);
+    uint16_t* aw = reinterpret_cast<uint16_t*>(p.aset) + (i * g.n + row) * 3;
+    aw[0] = aw[1] = aw[2] = 0x0404u;
+  }
+  p.cur[i] = (int8_t)floormod(pid + 1, g.n);
+  if (reward) reward[i] = 0;
+  if (done) done[i] = p.done[i];
+}
+
+// encode_board: one thread per 4 output cells.
+template <bool DET>
+__global__ void __launch_bounds__(256) k_madn_encode_board(const __grid_constant__ MadnGeom g, MadnPtrs p, int64_t n,
+                                                           int8_t* __restrict__ obs) {
+  const int C = DET ? 8 * g.n + 2 : 2 * g.n + 3;
+  const int wpr = g.total >> 2;  // words per channel row
+  const int64_t wpg = (int64_t)C * wpr;
+  int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (e >= n * wpg) return;
+  int64_t i = e / wpg;
+  int r = (int)(e - i * wpg);
+  int c = r / wpr, k0 = (r - c * wpr) * 4;
+  const int8_t* board = p.board + i * g.total;
+  const int cur = (int)p.cur[i];
+  uint32_t out = 0;
+  if (c < g.n + 2) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int k = k0 + j;
+      int src = (k < g.bs) ? floormod(k + g.d * cur, g.bs) : g.bs + floormod(k - g.bs + 4 * cur, 16);
+      int v = (int)board[src];
+      int rel = (v < 0) ? -1 : floormod(v - cur, g.n);  // channel index of the owner in the mover's frame
+      int val;
+      if (c < g.n) val = rel == c;
+      else if (DS_RULE(g, DOGSTEP_RULE_TEAMS)) val = (c == g.n) ? (rel >= 0 && (rel & 1) == 0) : (rel >= 0 && (rel & 1) == 1);
+      else val = (c == g.n) ? (rel == 0) : (rel >= 1);
+      out |= (uint32_t)val << (8 * j);
+    }
+  } else if (c < 2 * g.n + 2) {
+    int src = floormod(c - g.n - 2 + cur, g.n);
+    uint32_t pw = reinterpret_cast<const uint32_t*>(p.pins)[i * g.n + src];
+    int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) cnt += (byte_s(pw, j) == -1);
+    out = (uint32_t)cnt * 0x01010101u;
+  } else if (DET) {
+    int a = c - 2 * g.n - 2;
+    int src = floormod(a / 6 + cur, g.n);
+    int v = (int)p.aset[(i * g.n + src) * 6 + a % 6];
+    out = (uint32_t)(v & 0xFF) * 0x01010101u;
+  } else {
+    out = (uint32_t)((int)p.die[i] & 0xFF) * 0x01010101u;
+  }
+  reinterpret_cast<uint32_t*>(obs)[e] = out;
+}
+
+// categorical(key, where(mask, 0, -1e9)) == first valid action with the largest 23-bit uniform
+// mantissa (gumbel = -log(-log(u)) is strictly increasing in u; see DESIGN.md "random policy").
+__device__ __forceinline__ int categorical_masked(Key2 key, uint32_t mask) {
+  int best = -1;
+  uint32_t bm = 0;
+  for (uint32_t m = mask; m; m &= m - 1) {
+    int a = __ffs(m) - 1;
+    uint32_t mant = bits_i(key, (uint32_t)a) >> 9;
+    if (best < 0 || mant > bm) { best = a; bm = mant; }
+  }
+  return best;
+}
+
+__device__ __forceinline__ void madn_det_random_turn(const MadnGeom& g, MadnRegs& s, Key2 key) {
+  uint32_t m = madn_det_valid_mask(g, s);
+  if (m) {
+    int a = categorical_masked(key, m);
+    madn_det_step(g, s, a / 6, a % 6 + 1, m);  // map_action (deterministic_madn.py:469-479)
+  } else {
+    madn_det_no_step(g, s);
+  }
+}
+
+__device__ __forceinline__ void store_det_all(const MadnGeom& g, const MadnPtrs& p, int64_t i, const MadnRegs& s) {
+  store_board(g, p.board, i, s);
+  store_pins(g, p.pins, i, s);
+  store_aset(g, p.aset, i, s);
+  p.cur[i] = (int8_t)s.cur;
+  p.reward[i] = (int8_t)s.reward;
+  p.done[i] = (uint8_t)s.done;
+}
+
+__global__ void __launch_bounds__(kThreads) k_madn_det_random_step(const __grid_constant__ MadnGeom g, MadnPtrs p, int64_t n,
+                                                                   Key2 rng, int64_t game_offset,
+                                                                   unsigned long long* __restrict__ active_count) {
+  int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  int active = 0;
+  if (i < n && p.done[i] == 0) {
+    MadnRegs s;
+    load_state<true>(g, p, i, s);
+    madn_det_random_turn(g, s, split_i(rng, (uint32_t)(game_offset + i + 1)));
+    store_det_all(g, p, i, s);
+    active = 1;
+  }
+  if (active_count) {
+    unsigned b = __ballot_sync(0xFFFFFFFFu, active);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(active_count, (unsigned long long)__popc(b));
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_madn_det_play_random(const __grid_constant__ MadnGeom g, MadnPtrs p, int64_t n,
+                                                                   Key2 rng0, int64_t game_offset, int max_steps,
+                                                                   int32_t* __restrict__ game_len,
+                                                                   unsigned long long* __restrict__ total_steps) {
+  int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  int len = 0;
+  if (i < n) {
+    MadnRegs s;
+    load_state<true>(g, p, i, s);
+    Key2 rng = rng0;
+    const uint32_t my = (uint32_t)(game_offset + i + 1);
+    while (!s.done && len < max_steps) {
+      Key2 key = split_i(rng, my);
+      rng = split_i(rng, 0u);
+      madn_det_random_turn(g, s, key);
+      ++len;
+    }
+    store_det_all(g, p, i, s);
+    if (game_len) game_len[i] = len;
+  }
+  if (total_steps) {
+    unsigned v = (unsigned)len;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(total_steps, (unsigned long long)v);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_madn_cls_throw_die(const __grid_constant__ MadnGeom g, MadnPtrs p, int64_t n,
+                                                                 float* __restrict__ probs, int write_die) {
+  int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n) return;
+  MadnRegs s;
+  load_state<false>(g, p, i, s);
+  // dice_probabilities (classic_madn.py:14-18,208-228): float32 literals rounded from doubles
+  float pr[6];
+  const int locked = madn_soft_locked(g, s) && DS_RULE(g, DOGSTEP_RULE_DICE_RETHROW);
+  if (locked && DS_RULE(g, DOGSTEP_RULE_START_ON_1)) {
+    pr[0] = pr[5] = (float)(76.0 / 216);
+    pr[1] = pr[2] = pr[3] = pr[4] = (float)(16.0 / 216);
+  } else if (locked) {
+    pr[0] = pr[1] = pr[2] = pr[3] = pr[4] = (float)(25.0 / 216);
+    pr[5] = (float)(91.0 / 216);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) pr[k] = (float)(1.0 / 6);
+  }
+  if (probs) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) probs[i * 6 + k] = pr[k];
+  }
+  if (write_die) {
+    Key2 key{p.key[2 * i], p.key[2 * i + 1]};
+    Key2 knew = split_i(key, 0), sub = split_i(key, 1);
+    p.die[i] = (int8_t)(choice6(sub, pr) + 1);
+    p.key[2 * i] = knew.a;
+    p.key[2 * i + 1] = knew.b;
+  }
+}
+
+// ---- jax.random helpers -------------------------------------------------------------------------
+__global__ void k_random_split(Key2 key, int64_t n, uint32_t* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Key2 k = split_i(key, (uint32_t)i);
+  reinterpret_cast<uint2*>(out)[i] = make_uint2(k.a, k.b);
+}
+__global__ void k_random_randint(Key2 key, int64_t n, int32_t lo, int32_t hi, int32_t* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = randint_i(key, (uint32_t)i, lo, hi);
+}
+__global__ void k_random_uniform(Key2 key, int64_t n, float lo, float hi, float* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = uniform_i(key, (uint32_t)i, lo, hi);
+}
+__global__ void k_random_bits(Key2 key, int64_t n, uint32_t* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = bits_i(key, (uint32_t)i);
+}
+
+// ---- host-side argument plumbing -------------------------------------------------------------
+static inline unsigned blocks_for(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+static int det_ptrs(const dogstep_madn_det_state* s, MadnPtrs* p) {
+  if (!s || !s->board || !s->current_player || !s->pins || !s->reward || !s->done || !s->action_set)
+    return DOGSTEP_ERR_INVALID_ARG;
+  *p = MadnPtrs{s->board, s->current_player, s->pins, s->reward, s->done, s->action_set, nullptr, s->key};
+  return DOGSTEP_OK;
+}
+static int cls_ptrs(const dogstep_madn_cls_state* s, MadnPtrs* p) {
+  if (!s || !s->board || !s->current_player || !s->pins || !s->reward || !s->done || !s->die)
+    return DOGSTEP_ERR_INVALID_ARG;
+  *p = MadnPtrs{s->board, s->current_player, s->pins, s->reward, s->done, nullptr, s->die, s->key};
+  return DOGSTEP_OK;
+}
+
+#define DS_PROLOGUE(PTRFN)                                   \
+  MadnGeom g;                                                \
+  MadnPtrs p;                                                \
+  if (n < 0) return DOGSTEP_ERR_INVALID_ARG;                 \
+  if (int rc = madn_make_geom(cfg, &g)) return rc;           \
+  if (int rc = PTRFN(s, &p)) return rc;                      \
+  if (n == 0) return DOGSTEP_OK;                             \
+  cudaStream_t st = (cudaStream_t)stream;
+
+}  // namespace dogstep
+
+using namespace dogstep;
+
+extern "C" {
+
+int dogstep_madn_det_reset(const dogstep_madn_det_state* s, int64_t n, const dogstep_madn_cfg* cfg, const int32_t* seeds,
+                           int32_t starting_player, void* stream) {
+  DS_PROLOGUE(det_ptrs)
+  if (!seeds || !p.key) return DOGSTEP_ERR_INVALID_ARG;
+  k_madn_reset<true><<<blocks_for(n, kThreads), kThreads, 0, st>>>(g, p, n, seeds, starting_player);
+  return check_launch();
+}
+
+int dogstep_madn_cls_reset(const dogstep_madn_cls_state* s, int64_t n, const dogstep_madn_cfg* cfg, const int32_t* seeds,
+                           int32_t starting_player, void* stream) {
+  DS_PROLOGUE(cls_ptrs)
+  if (!seeds || !p.key) return DOGSTEP_ERR_INVALID_ARG;
+  k_madn_reset<false><<<blocks_for(n, kThreads), kThreads, 0, st>>>(g, p, n, seeds, starting_player);
+  return check_launch();
+}
+
+int dogstep_madn_set_pins_on_board(const int8_t* pins, int8_t* board, int64_t n, const dogstep_madn_cfg* cfg, void* stream) {
+  MadnGeom g;
+  if (n < 0 || !pins || !board) return DOGSTEP_ERR_INVALID_ARG;
+  if (int rc = madn_make_geom(cfg, &g)) return rc;
+  if (n == 0) return DOGSTEP_OK;
+  k_madn_set_pins_on_board<<<blocks_for(n, kThreads), kThreads, 0, (cudaStream_t)stream>>>(g, pins, board, n);
+  return check_launch();
+}
+
+int dogstep_madn_det_valid_action(const dogstep_madn_det_state* s, int64_t n, const dogstep_madn_cfg* cfg, uint8_t* mask,
+                                  void* stream) {
+  DS_PROLOGUE(det_ptrs)
+  if (!mask) return DOGSTEP_ERR_INVALID_ARG;
+  k_madn_valid_action<true><<<blocks_for(n, kThreads), kThreads, 0, st>>>(g, p, n, mask);
+  return check_launch();
+}
+
+int dogstep_madn_cls_valid_action(const dogstep_madn_cls_state* s, int64_t n, const dogstep_madn_cfg* cfg, uint8_t* mask,
+                                  void* stream) {
+  DS_PROLOGUE(cls_ptrs)
+  if (!mask) return DOGSTEP_ERR_INVALID_ARG;
+  k_madn_valid_action<false><<<blocks_for(n, kThreads), kThreads, 0, st>>>(g, p, n, mask);
+  return check_launch();
+}
+
+int dogstep_madn_det_step(const dogstep_madn_det_state* s, int64_t n, const dogstep_madn_cfg* cfg, const int8_t* action,
+                          int8_t* reward, uint8_t* done, void* stream) {
+  DS_PROLOGUE(det_ptrs)
+  if (!action) return DOGSTEP_ERR_INVALID_ARG;
+  k_madn_step<true><<<blocks_for(n, kThreads), kThreads, 0, st>>>(g, p, n, action, reward, done);
+  return check_launch();
+}
+
+int dogstep_madn_cls_step(const dogstep_madn_cls_state* s, int64_t n, const dogstep_madn_cfg* cfg, const int8_t* action,
+                          int8_t* reward, uint8_t* done, void* stream) {
+  DS_PROLOGUE(cls_ptrs)
+  if (!action) return DOGSTEP_ERR_INVALID_ARG;
+  k_madn_step<false><<<blocks_for(n, kThreads), kThreads, 0, st>>>(g, p, n, action, reward, done);
+  return check_launch();
+}
+
+int dogstep_madn_det_no_step(const dogstep_madn_det_state* s, int64_t n, const dogstep_madn_cfg* cfg, int8_t* reward,
+                             uint8_t* done, void* stream) {
+  DS_PROLOGUE(det_ptrs)
+  k_madn_no_step<true><<<blocks_for(n, kThreads), kThreads, 0, st>>>(g, p, n, reward, done);
+  return check_launch();
+}
+
+int dogstep_madn_cls_no_step(const dogstep_madn_cls_state* s, int64_t n, const dogstep_madn_cfg* cfg, int8_t* reward,
+                             uint8_t* done, void* stream) {
+  DS_PROLOGUE(cls_ptrs)
+  k_madn_no_step<false><<<blocks_for(n, kThreads), kThreads, 0, st>>>(g, p, n, reward, done);
+  return check_launch();
+}
+
+int dogstep_madn_det_encode_board(const dogstep_madn_det_state* s, int64_t n, const dogstep_madn_cfg* cfg, int8_t* obs,
+                                  void* stream) {
+  DS_PROLOGUE(det_ptrs)
+  if (!obs) return DOGSTEP_ERR_INVALID_ARG;
+  int64_t words = n * (8 * g.n + 2) * (g.total >> 2);
+  k_madn_encode_board<true><<<blocks_for(words, 256), 256, 0, st>>>(g, p, n, obs);
+  return check_launch();
+}
+
+int dogstep_madn_cls_encode_board(const dogstep_madn_cls_state* s, int64_t n, const dogstep_madn_cfg* cfg, int8_t* obs,
+                                  void* stream) {
+  DS_PROLOGUE(cls_ptrs)
+  if (!obs) return DOGSTEP_ERR_INVALID_ARG;
+  int64_t words = n * (2 * g.n + 3) * (g.total >> 2);
+  k_madn_encode_board<false><<<blocks_for(words, 256), 256, 0, st>>>(g, p, n, obs);
+  return check_launch();
+}
+
+int dogstep_madn_det_random_step(const dogstep_madn_det_state* s, int64_t n, const dogstep_madn_cfg* cfg,
+                                 const uint32_t* host_rng_key, int64_t game_offset, unsigned long long* active_count,
+                                 void* stream) {
+  DS_PROLOGUE(det_ptrs)
+  if (!host_rng_key) return DOGSTEP_ERR_INVALID_ARG;
+  Key2 rng{host_rng_key[0], host_rng_key[1]};
+  k_madn_det_random_step<<<blocks_for(n, kThreads), kThreads, 0, st>>>(g, p, n, rng, game_offset, active_count);
+  return check_launch();
+}
+
+int dogstep_madn_det_play_random(const dogstep_madn_det_state* s, int64_t n, const dogstep_madn_cfg* cfg,
+                                 const uint32_t* host_rng_key, int64_t game_offset, int32_t max_steps, int32_t* game_len,
+                                 unsigned long long* total_steps, void* stream) {
+  DS_PROLOGUE(det_ptrs)
+  if (!host_rng_key || max_steps < 0) return DOGSTEP_ERR_INVALID_ARG;
+  Key2 rng{host_rng_key[0], host_rng_key[1]};
+  k_madn_det_play_random<<<blocks_for(n, kThreads), kThreads, 0, st>>>(g, p, n, rng, game_offset, max_steps, game_len,
+                                                                       total_steps);
+  return check_launch();
+}
+
+int dogstep_madn_cls_throw_die(const dogstep_madn_cls_state* s, int64_t n, const dogstep_madn_cfg* cfg, void* stream) {
+  DS_PROLOGUE(cls_ptrs)
+  if (!p.key) return DOGSTEP_ERR_INVALID_ARG;
+  k_madn_cls_throw_die<<<blocks_for(n, kThreads), kThreads, 0, st>>>(g, p, n, nullptr, 1);
+  return check_launch();
+}
+
+int dogstep_madn_cls_dice_probabilities(const dogstep_madn_cls_state* s, int64_t n, const dogstep_madn_cfg* cfg, float* probs,
+                                        void* stream) {
+  DS_PROLOGUE(cls_ptrs)
+  if (!probs) return DOGSTEP_ERR_INVALID_ARG;
+  k_madn_cls_throw_die<<<blocks_for(n, kThreads), kThreads, 0, st>>>(g, p, n, probs, 0);
+  return check_launch();
+}
+
+int dogstep_random_split(const uint32_t* host_key, int64_t n, uint32_t* out, void* stream) {
+  if (!host_key || !out || n < 0) return DOGSTEP_ERR_INVALID_ARG;
+  if (n == 0) return DOGSTEP_OK;
+  k_random_split<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(Key2{host_key[0], host_key[1]}, n, out);
+  return check_launch();
+}
+int dogstep_random_randint(const uint32_t* host_key, int64_t n, int32_t lo, int32_t hi, int32_t* out, void* stream) {
+  if (!host_key || !out || n < 0) return DOGSTEP_ERR_INVALID_ARG;
+  if (n == 0) return DOGSTEP_OK;
+  k_random_randint<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(Key2{host_key[0], host_key[1]}, n, lo, hi, out);
+  return check_launch();
+}
+int dogstep_random_uniform(const uint32_t* host_key, int64_t n, float lo, float hi, float* out, void* stream) {
+  if (!host_key || !out || n < 0) return DOGSTEP_ERR_INVALID_ARG;
+  if (n == 0) return DOGSTEP_OK;
+  k_random_uniform<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(Key2{host_key[0], host_key[1]}, n, lo, hi, out);
+  return check_launch();
+}
+int dogstep_random_bits(const uint32_t* host_key, int64_t n, uint32_t* out, void* stream) {
+  if (!host_key || !out || n < 0) return DOGSTEP_ERR_INVALID_ARG;
+  if (n == 0) return DOGSTEP_OK;
+  k_random_bits<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(Key2{host_key[0], host_key[1]}, n, out);
+  return check_launch();
+}
+
+}  // extern "C"

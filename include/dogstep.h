@@ -1,0 +1,149 @@
+/* dogstep.h — C ABI of libdogstep.so: the B200-native self-play hot path behind the
+ * Exploring-MuZero-on-DOG Python API.
+ *
+ * The reference has no FFI of its own: its boundary is a set of pure Python/JAX functions on
+ * flax.struct pytrees that are vmapped over games.  Each entry point
+ * below replaces one of those functions *after vmap*, i.e. it sees the batched leaves of the
+ * pytree as structure-of-arrays device buffers with a leading game axis `n`.  Every entry point
+ * cites the reference function it stands in for.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name says `host_`; the caller owns and
+ *     pre-allocates every buffer; state is updated in place (jax.ffi: input_output_aliases)
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued, never synchronised
+ *   - return 0 on success, DOGSTEP_ERR_* otherwise; an invalid *game* action is not an error
+ *     (the reference answers reward -1 and still passes the turn)
+ *   - rule dicts become one uint32 bitmask (dogstep_rules.h)
+ *   - re-entrant, no global mutable state
+ */
+#ifndef DOGSTEP_H
+#define DOGSTEP_H
+#include <stdint.h>
+#include "dogstep_rules.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int dogstep_version(void);
+/* last CUDA error string seen by this thread ("" if none) */
+const char* dogstep_last_error(void);
+
+/* ---------------------------------------------------------------- board geometry / rule set
+ * Static (pytree_node=False) fields of the reference envs: num_players, board_size, rules
+ * (MADN/deterministic_madn.py:32,38-40), plus the `layout` argument of env_reset (:45,70-78).
+ * board_size = 4*distance, total_board_size = board_size + 16. */
+typedef struct {
+  int32_t num_players; /* 2..4 */
+  int32_t layout_mask; /* bit i = seat i present; replaced by the first n seats exactly like :70-74 */
+  int32_t distance;    /* cells between two starts; 1..12 (total_board_size <= 64) */
+  uint32_t rules;      /* DOGSTEP_RULE_* */
+} dogstep_madn_cfg;
+
+/* ---------------------------------------------------------------- deterministic MADN state
+ * Batched leaves of `deterministic_MADN` (MADN/deterministic_madn.py:24-40).
+ * start/target/goal are pure functions of the cfg and are not stored per game. */
+typedef struct {
+  int8_t* board;          /* [n, total_board_size]  -1 empty, else owning player */
+  int8_t* current_player; /* [n] */
+  int8_t* pins;           /* [n, num_players, 4]    -1 home, 0..bs-1 ring, bs.. goal lanes */
+  int8_t* reward;         /* [n] */
+  uint8_t* done;          /* [n] bool */
+  int8_t* action_set;     /* [n, num_players, 6]    remaining copies of move cards 1..6 */
+  uint32_t* key;          /* [n, 2] raw threefry key */
+} dogstep_madn_det_state;
+
+/* env_reset vmapped over seeds — MADN/deterministic_madn.py:42-120 (game_agent.py:24-44).
+ * starting_player outside [0, num_players) draws randint(subkey, (), 0, num_players) (:62). */
+int dogstep_madn_det_reset(const dogstep_madn_det_state* s, int64_t n, const dogstep_madn_cfg* cfg,
+                           const int32_t* seeds /*[n]*/, int32_t starting_player, void* stream);
+
+/* valid_action — MADN/deterministic_madn.py:299-393.  mask: uint8 [n, 4, 6] (0/1). */
+int dogstep_madn_det_valid_action(const dogstep_madn_det_state* s, int64_t n, const dogstep_madn_cfg* cfg,
+                                  uint8_t* mask, void* stream);
+
+/* env_step — MADN/deterministic_madn.py:170-257.  action: int8 [n, 2] = [pin, move].
+ * reward/done outputs may be NULL (they are also written into the state leaves). */
+int dogstep_madn_det_step(const dogstep_madn_det_state* s, int64_t n, const dogstep_madn_cfg* cfg,
+                          const int8_t* action, int8_t* reward, uint8_t* done, void* stream);
+
+/* no_step — MADN/deterministic_madn.py:283-297 (returned reward is the constant 0). */
+int dogstep_madn_det_no_step(const dogstep_madn_det_state* s, int64_t n, const dogstep_madn_cfg* cfg,
+                             int8_t* reward, uint8_t* done, void* stream);
+
+/* set_pins_on_board — MADN/deterministic_madn.py:259-271.  pins [n, P, 4] -> board [n, total]. */
+int dogstep_madn_set_pins_on_board(const int8_t* pins, int8_t* board, int64_t n, const dogstep_madn_cfg* cfg,
+                                   void* stream);
+
+/* encode_board — MADN/deterministic_madn.py:395-438.  obs: int8 [n, 8*P+2, total]. */
+int dogstep_madn_det_encode_board(const dogstep_madn_det_state* s, int64_t n, const dogstep_madn_cfg* cfg,
+                                  int8_t* obs, void* stream);
+
+/* One lockstep iteration of the random-legal-policy driver, fused:
+ * MuZero_det_MADN/evaluate_agent.py:733-930 with do_random (:772-776):
+ *   game j not done: mask = valid_action; any(mask) ? env_step(map_action(categorical(key_j, where(mask,0,-1e9))))
+ *                                                  : no_step
+ *   key_j = split(rng, N+1)[game_offset + j + 1]  (:741);  the carried key is split(rng, N+1)[0].
+ * host_rng_key: uint32[2] on the HOST (the loop-carried key); active_count (device int64, may be
+ * NULL) is incremented by the number of games that were not done. */
+int dogstep_madn_det_random_step(const dogstep_madn_det_state* s, int64_t n, const dogstep_madn_cfg* cfg,
+                                 const uint32_t* host_rng_key, int64_t game_offset,
+                                 unsigned long long* active_count, void* stream);
+
+/* The whole while_loop of that driver as ONE persistent launch: every game is advanced until it is
+ * done or `max_steps` lockstep iterations have passed (cap 2000 at evaluate_agent.py:918).
+ * game_len: int32 [n] iterations in which game j was still active (may be NULL);
+ * total_steps: device int64 accumulator, += sum(game_len) (may be NULL). */
+int dogstep_madn_det_play_random(const dogstep_madn_det_state* s, int64_t n, const dogstep_madn_cfg* cfg,
+                                 const uint32_t* host_rng_key, int64_t game_offset, int32_t max_steps,
+                                 int32_t* game_len, unsigned long long* total_steps, void* stream);
+
+/* ---------------------------------------------------------------- classic (dice) MADN state
+ * Batched leaves of `classic_MADN` (MADN/classic_madn.py:33-49). */
+typedef struct {
+  int8_t* board;          /* [n, total_board_size] */
+  int8_t* current_player; /* [n] */
+  int8_t* pins;           /* [n, num_players, 4] */
+  int8_t* reward;         /* [n] */
+  uint8_t* done;          /* [n] */
+  int8_t* die;            /* [n] */
+  uint32_t* key;          /* [n, 2] */
+} dogstep_madn_cls_state;
+
+/* env_reset — MADN/classic_madn.py:51-131 */
+int dogstep_madn_cls_reset(const dogstep_madn_cls_state* s, int64_t n, const dogstep_madn_cfg* cfg,
+                           const int32_t* seeds, int32_t starting_player, void* stream);
+/* throw_die — MADN/classic_madn.py:230-242 (split env.key, choice with dice_probabilities) */
+int dogstep_madn_cls_throw_die(const dogstep_madn_cls_state* s, int64_t n, const dogstep_madn_cfg* cfg, void* stream);
+/* dice_probabilities — MADN/classic_madn.py:208-228.  p: float32 [n, 6] */
+int dogstep_madn_cls_dice_probabilities(const dogstep_madn_cls_state* s, int64_t n, const dogstep_madn_cfg* cfg,
+                                        float* p, void* stream);
+/* valid_action — MADN/classic_madn.py:367-461.  mask: uint8 [n, 4] */
+int dogstep_madn_cls_valid_action(const dogstep_madn_cls_state* s, int64_t n, const dogstep_madn_cfg* cfg,
+                                  uint8_t* mask, void* stream);
+/* env_step — MADN/classic_madn.py:257-337.  action: int8 [n] pin index */
+int dogstep_madn_cls_step(const dogstep_madn_cls_state* s, int64_t n, const dogstep_madn_cfg* cfg,
+                          const int8_t* action, int8_t* reward, uint8_t* done, void* stream);
+/* no_step — MADN/classic_madn.py:353-365 */
+int dogstep_madn_cls_no_step(const dogstep_madn_cls_state* s, int64_t n, const dogstep_madn_cfg* cfg,
+                             int8_t* reward, uint8_t* done, void* stream);
+/* encode_board — MADN/classic_madn.py:463-497.  obs: int8 [n, 2*P+3, total] */
+int dogstep_madn_cls_encode_board(const dogstep_madn_cls_state* s, int64_t n, const dogstep_madn_cfg* cfg,
+                                  int8_t* obs, void* stream);
+
+/* ---------------------------------------------------------------- jax.random on device
+ * Stand-ins for the jax.random calls the self-play drivers make around the env functions
+ * (game_agent.py:60,187-188).  keys are raw uint32[2]. */
+/* jax.random.split(key, n) -> out [n, 2] */
+int dogstep_random_split(const uint32_t* host_key, int64_t n, uint32_t* out, void* stream);
+/* jax.random.randint(key, (n,), lo, hi) int32 */
+int dogstep_random_randint(const uint32_t* host_key, int64_t n, int32_t lo, int32_t hi, int32_t* out, void* stream);
+/* jax.random.uniform(key, (n,), float32, lo, hi) */
+int dogstep_random_uniform(const uint32_t* host_key, int64_t n, float lo, float hi, float* out, void* stream);
+/* jax.random.bits(key, (n,), uint32) */
+int dogstep_random_bits(const uint32_t* host_key, int64_t n, uint32_t* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DOGSTEP_H */

@@ -1,0 +1,254 @@
+"""CPU oracle — TEST INFRASTRUCTURE ONLY.
+
+A plain-C restatement of the reference's hot path (see the headers of the *_oracle.c files for
+the reference lines each function follows), loaded through ctypes with NumPy arrays.  Only
+`tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference` leg may
+import this package; the product package never does (tests/test_no_oracle_in_product.py).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
+_lib = None
+
+
+def build(force=False):
+    """Compile oracle/*_oracle.c into oracle/_build/liboracle.so with gcc."""
+    srcs = sorted(f for f in os.listdir(_HERE) if f.endswith("_oracle.c"))
+    newest = max(os.path.getmtime(os.path.join(_HERE, f)) for f in os.listdir(_HERE) if f.endswith((".c", ".h")))
+    if not force and os.path.exists(_LIB_PATH) and os.path.getmtime(_LIB_PATH) >= newest:
+        return _LIB_PATH
+    os.makedirs(os.path.dirname(_LIB_PATH), exist_ok=True)
+    cmd = ["gcc", "-O2", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-shared", "-o", _LIB_PATH]
+    cmd += [os.path.join(_HERE, s) for s in srcs] + ["-lm", "-lpthread"]
+    subprocess.run(cmd, check=True, cwd=_HERE)
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB_PATH)
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _c(a, dt):
+    a = np.ascontiguousarray(a, dtype=dt)
+    return a
+
+
+# --------------------------------------------------------------------------- jax.random restatement
+def threefry2x32(k0, k1, c0, c1):
+    c0 = _c(c0, np.uint32).ravel()
+    c1 = _c(c1, np.uint32).ravel()
+    o0 = np.empty_like(c0)
+    o1 = np.empty_like(c1)
+    lib().orc_threefry2x32_v(C.c_uint32(k0), C.c_uint32(k1), C.c_int64(c0.size), _p(c0), _p(c1), _p(o0), _p(o1))
+    return o0, o1
+
+
+def prng_key(seed):
+    return np.array([0, np.uint32(np.int64(seed) & 0xFFFFFFFF)], dtype=np.uint32)
+
+
+def split(key, n=2):
+    key = _c(key, np.uint32)
+    out = np.empty((n, 2), np.uint32)
+    lib().orc_split(_p(key), C.c_int64(n), _p(out))
+    return out
+
+
+def random_bits(key, n):
+    key = _c(key, np.uint32)
+    out = np.empty(n, np.uint32)
+    lib().orc_random_bits(_p(key), C.c_int64(n), _p(out))
+    return out
+
+
+def uniform(key, n, minval=0.0, maxval=1.0):
+    key = _c(key, np.uint32)
+    out = np.empty(n, np.float32)
+    lib().orc_uniform(_p(key), C.c_int64(n), C.c_float(minval), C.c_float(maxval), _p(out))
+    return out
+
+
+def randint(key, n, lo, hi):
+    key = _c(key, np.uint32)
+    out = np.empty(n, np.int32)
+    lib().orc_randint(_p(key), C.c_int64(n), C.c_int32(lo), C.c_int32(hi), _p(out))
+    return out
+
+
+def gumbel(key, n):
+    key = _c(key, np.uint32)
+    out = np.empty(n, np.float32)
+    lib().orc_gumbel(_p(key), C.c_int64(n), _p(out))
+    return out
+
+
+def choice6(key, p):
+    key = _c(key, np.uint32)
+    p = _c(p, np.float32)
+    return int(lib().orc_choice6_v(_p(key), _p(p)))
+
+
+def categorical_masked(key, mask, float_gumbel=False):
+    key = _c(key, np.uint32)
+    mask = _c(mask, np.uint8)
+    return int(lib().orc_categorical(_p(key), _p(mask), C.c_int(mask.size), C.c_int(int(float_gumbel))))
+
+
+# --------------------------------------------------------------------------- MADN
+class MadnCfg:
+    """(num_players, layout, distance, rules bitmask) exactly as handed to the C-ABI."""
+
+    def __init__(self, num_players=4, layout_mask=0xF, distance=10, rules=0):
+        self.num_players, self.layout_mask, self.distance, self.rules = num_players, layout_mask, distance, rules
+        self.total = 4 * distance + 16
+
+    @property
+    def args(self):
+        return (C.c_int(self.num_players), C.c_int(self.layout_mask), C.c_int(self.distance), C.c_uint32(self.rules))
+
+    def geometry(self):
+        n = self.num_players
+        s = np.zeros(n, np.int32)
+        t = np.zeros(n, np.int32)
+        g = np.zeros((n, 4), np.int32)
+        assert lib().orc_madn_geometry(*self.args, _p(s), _p(t), _p(g)) == 0
+        return s, t, g
+
+
+class MadnState:
+    """SoA leaves of a batch of deterministic/classic MADN games (NumPy, host)."""
+
+    def __init__(self, cfg, n, det=True):
+        P = cfg.num_players
+        self.cfg, self.n, self.det = cfg, n, det
+        self.board = np.full((n, cfg.total), -1, np.int8)
+        self.current_player = np.zeros(n, np.int8)
+        self.pins = np.full((n, P, 4), -1, np.int8)
+        self.reward = np.zeros(n, np.int8)
+        self.done = np.zeros(n, np.uint8)
+        self.action_set = np.full((n, P, 6), 4, np.int8) if det else None
+        self.die = None if det else np.zeros(n, np.int8)
+        self.key = np.zeros((n, 2), np.uint32)
+
+    def copy(self):
+        o = MadnState.__new__(MadnState)
+        o.cfg, o.n, o.det = self.cfg, self.n, self.det
+        for f in ("board", "current_player", "pins", "reward", "done", "action_set", "die", "key"):
+            v = getattr(self, f)
+            setattr(o, f, None if v is None else v.copy())
+        return o
+
+    def fields(self):
+        names = ["board", "current_player", "pins", "reward", "done", "key"] + (["action_set"] if self.det else ["die"])
+        return {k: getattr(self, k) for k in names}
+
+
+def madn_reset(cfg, seeds, starting_player=0, det=True):
+    seeds = _c(seeds, np.int32)
+    s = MadnState(cfg, seeds.size, det)
+    rc = lib().orc_madn_reset(*cfg.args, C.c_int64(s.n), _p(seeds), C.c_int(starting_player), _p(s.board),
+                              _p(s.current_player), _p(s.pins), _p(s.reward), _p(s.done), _p(s.action_set),
+                              _p(s.die), _p(s.key))
+    assert rc == 0
+    return s
+
+
+def madn_set_pins_on_board(cfg, pins):
+    pins = _c(pins, np.int8)
+    n = pins.shape[0]
+    board = np.empty((n, cfg.total), np.int8)
+    assert lib().orc_madn_set_pins_on_board(*cfg.args, C.c_int64(n), _p(pins), _p(board)) == 0
+    return board
+
+
+def madn_det_valid_action(s):
+    mask = np.empty((s.n, 4, 6), np.uint8)
+    assert lib().orc_madn_det_valid_action(*s.cfg.args, C.c_int64(s.n), _p(s.board), _p(s.current_player), _p(s.pins),
+                                           _p(s.action_set), _p(mask)) == 0
+    return mask.astype(bool)
+
+
+def madn_det_step(s, action):
+    """in place; returns (reward, done)"""
+    action = _c(action, np.int8).reshape(s.n, 2)
+    assert lib().orc_madn_det_step(*s.cfg.args, C.c_int64(s.n), _p(s.board), _p(s.current_player), _p(s.pins),
+                                   _p(s.reward), _p(s.done), _p(s.action_set), _p(action)) == 0
+    return s.reward.copy(), s.done.astype(bool)
+
+
+def madn_det_no_step(s):
+    assert lib().orc_madn_det_no_step(*s.cfg.args, C.c_int64(s.n), _p(s.current_player), _p(s.reward), _p(s.done),
+                                      _p(s.action_set)) == 0
+    return np.zeros(s.n, np.int8), s.done.astype(bool)
+
+
+def madn_det_encode_board(s):
+    obs = np.empty((s.n, 8 * s.cfg.num_players + 2, s.cfg.total), np.int8)
+    assert lib().orc_madn_det_encode_board(*s.cfg.args, C.c_int64(s.n), _p(s.board), _p(s.current_player), _p(s.pins),
+                                           _p(s.action_set), _p(obs)) == 0
+    return obs
+
+
+def madn_cls_valid_action(s):
+    mask = np.empty((s.n, 4), np.uint8)
+    assert lib().orc_madn_cls_valid_action(*s.cfg.args, C.c_int64(s.n), _p(s.board), _p(s.current_player), _p(s.pins),
+                                           _p(s.die), _p(mask)) == 0
+    return mask.astype(bool)
+
+
+def madn_cls_step(s, pin):
+    pin = _c(pin, np.int8).reshape(s.n)
+    assert lib().orc_madn_cls_step(*s.cfg.args, C.c_int64(s.n), _p(s.board), _p(s.current_player), _p(s.pins),
+                                   _p(s.reward), _p(s.done), _p(s.die), _p(pin)) == 0
+    return s.reward.copy(), s.done.astype(bool)
+
+
+def madn_cls_no_step(s):
+    assert lib().orc_madn_cls_no_step(*s.cfg.args, C.c_int64(s.n), _p(s.current_player)) == 0
+    return np.zeros(s.n, np.int8), s.done.astype(bool)
+
+
+def madn_cls_throw_die(s):
+    assert lib().orc_madn_cls_throw_die(*s.cfg.args, C.c_int64(s.n), _p(s.board), _p(s.current_player), _p(s.pins),
+                                        _p(s.key), _p(s.die)) == 0
+    return s.die.copy()
+
+
+def madn_cls_dice_probabilities(s):
+    p = np.empty((s.n, 6), np.float32)
+    assert lib().orc_madn_cls_dice_probabilities(*s.cfg.args, C.c_int64(s.n), _p(s.board), _p(s.current_player),
+                                                 _p(s.pins), _p(p)) == 0
+    return p
+
+
+def madn_cls_encode_board(s):
+    obs = np.empty((s.n, 2 * s.cfg.num_players + 3, s.cfg.total), np.int8)
+    assert lib().orc_madn_cls_encode_board(*s.cfg.args, C.c_int64(s.n), _p(s.board), _p(s.current_player), _p(s.pins),
+                                           _p(s.die), _p(obs)) == 0
+    return obs
+
+
+def madn_det_play_random(s, rng_key, max_steps=2000, game_offset=0, float_gumbel=False, nthreads=1):
+    """Lockstep random-legal-policy play to termination, in place.  Returns (game_len, total_steps, rng_key_out)."""
+    key = _c(rng_key, np.uint32).copy()
+    game_len = np.zeros(s.n, np.int32)
+    total = C.c_int64(0)
+    rc = lib().orc_madn_det_play_random(*s.cfg.args, C.c_int64(s.n), C.c_int64(game_offset), _p(s.board),
+                                        _p(s.current_player), _p(s.pins), _p(s.reward), _p(s.done), _p(s.action_set),
+                                        _p(key), C.c_int(max_steps), C.c_int(int(float_gumbel)), C.c_int(nthreads),
+                                        _p(game_len), C.byref(total))
+    assert rc == 0
+    return game_len, int(total.value), key
