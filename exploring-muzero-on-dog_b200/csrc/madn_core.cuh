@@ -164,6 +164,42 @@ __device__ __forceinline__ int move_ok(const MadnGeom& g, uint64_t own, uint32_t
   return result;
 }
 
+// Bit-parallel form of move_ok for the six moves m = 1..6 of one pin (bit m-1), valid when
+// start blocking is off (then x is never overridden and the start lookups drop out).  Same
+// reference lines as move_ok; cross-checked against it over random rule sets in tests/.
+__device__ __forceinline__ uint32_t move_row_fast(const MadnGeom& g, uint64_t own, int cp, int pos) {
+  const int mts = DS_RULE(g, DOGSTEP_RULE_MUST_TRAVERSE_START);
+  const int circ = DS_RULE(g, DOGSTEP_RULE_CIRCULAR_BOARD);
+  const int jump = DS_RULE(g, DOGSTEP_RULE_JUMP_IN_GOAL);
+  const int target = g.target[cp], goal0 = g.goal0[cp];
+  const uint32_t lane = (uint32_t)(own >> goal0) & 0xFu;
+  if (pos >= goal0 && pos <= goal0 + 3) {  // pin in its goal lane (:376-381)
+    const int k0 = pos - goal0;
+    const uint32_t above = lane >> (k0 + 1);                        // bit m-1 = own pin on lane cell k0+m
+    const uint32_t clear = above ? ((above & (0u - above)) - 1u) : 0xFu;  // cells below the first own pin
+    return (jump ? ~above : clear) & ((1u << (3 - k0)) - 1u);
+  }
+  const uint64_t ring = own & ((1ull << g.bs) - 1ull);
+  const uint32_t landing_own = (uint32_t)(((ring | (ring << g.bs)) >> (pos + 1)) & 0x3Full);
+  uint32_t row = DS_RULE(g, DOGSTEP_RULE_FRIENDLY_FIRE) ? 0x3Fu : (~landing_own & 0x3Fu);
+  if (pos <= target) {
+    const int t = target + mts - pos;  // x = m - t, t >= 0 here
+    if (!circ) {
+      // (:349-357) x > 4  <=>  m > t + 4 ;  x == 0 && mts  <=>  m == t
+      const uint32_t beyond = (t + 4 < 6) ? (0x3Fu & ~((1u << (t + 4)) - 1u)) : 0u;
+      const uint32_t at_target = (mts && t >= 1 && t <= 6) ? (1u << (t - 1)) : 0u;
+      row &= ~(beyond | at_target);
+    }
+    if (t < 6) {  // goal entry window 1 <= x <= 4  <=>  t+1 <= m <= t+4  (:360-372)
+      const uint32_t clear = lane ? ((lane & (0u - lane)) - 1u) : 0xFu;  // bit x-1: lane cells 0..x-1 free of own pins
+      const uint32_t goal_ok = (jump ? ~lane : clear) & 0xFu;            // B & C indexed by x-1
+      const uint32_t win = (0xFu << t) & 0x3Fu;
+      row = (row & ~win) | (win & ((circ ? row : 0u) | (goal_ok << t)));
+    }
+  }
+  return row;
+}
+
 // valid_action, deterministic variant -> 24-bit mask, bit pin*6 + (move-1)
 __device__ __forceinline__ uint32_t madn_det_valid_mask(const MadnGeom& g, const MadnRegs& s) {
   const int pid = s.cur;
@@ -179,15 +215,19 @@ __device__ __forceinline__ uint32_t madn_det_valid_mask(const MadnGeom& g, const
   for (int m = 1; m <= 6; ++m) avail |= (byte_s64(asr, m - 1) > 0) ? (1u << (m - 1)) : 0u;
   const uint32_t home_moves = DS_RULE(g, DOGSTEP_RULE_START_ON_1) ? 0x21u : 0x20u;
   uint32_t mask = 0;
-#pragma unroll
+#pragma unroll 1
   for (int i = 0; i < 4; ++i) {
     int pos = byte_s(pw, i);
     uint32_t row = 0;
     if (pos == -1) {
       row = start_free ? home_moves : 0u;
     } else {
+      if (!DS_RULE(g, DOGSTEP_RULE_START_BLOCKING)) {
+        row = move_row_fast(g, own, cp, pos);
+      } else {
 #pragma unroll
-      for (int m = 1; m <= 6; ++m) row |= move_ok(g, own, posmask, cp, pos, m) ? (1u << (m - 1)) : 0u;
+        for (int m = 1; m <= 6; ++m) row |= move_ok(g, own, posmask, cp, pos, m) ? (1u << (m - 1)) : 0u;
+      }
     }
     mask |= (row & avail) << (6 * i);
   }

@@ -332,31 +332,86 @@ __global__ void __launch_bounds__(kThreads) k_madn_det_random_step(const __grid_
   }
 }
 
+// Persistent lockstep loop.  One game per lane, but the expensive part of a turn — one
+// Threefry-2x32-20 per LEGAL action for the categorical draw — is pooled per warp: the (game, action)
+// pairs of all 32 games are compacted into a shared list and dealt out evenly to the lanes, so a game
+// with 14 legal actions does not stall 31 lanes that have 3.  Results come back through a
+// [32 games x 24 actions] mantissa table in shared memory.
+constexpr int kPlayWarps = kThreads / 32;
+
 __global__ void __launch_bounds__(kThreads) k_madn_det_play_random(const __grid_constant__ MadnGeom g, MadnPtrs p, int64_t n,
                                                                    Key2 rng0, int64_t game_offset, int max_steps,
                                                                    int32_t* __restrict__ game_len,
                                                                    unsigned long long* __restrict__ total_steps) {
+  __shared__ uint16_t s_items[kPlayWarps][32 * 24];
+  __shared__ uint32_t s_mant[kPlayWarps][32 * 24];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t FULL = 0xFFFFFFFFu;
   int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   int len = 0;
+  MadnRegs s;
+  bool alive = false;
   if (i < n) {
-    MadnRegs s;
     load_state<true>(g, p, i, s);
-    Key2 rng = rng0;
-    const uint32_t my = (uint32_t)(game_offset + i + 1);
-    while (!s.done && len < max_steps) {
-      Key2 key = split_i(rng, my);
-      rng = split_i(rng, 0u);
-      madn_det_random_turn(g, s, key);
-      ++len;
+    alive = !s.done;
+  }
+  Key2 rng = rng0;
+  const uint32_t my = (uint32_t)(game_offset + i + 1);
+  uint16_t* items = s_items[warp];
+  uint32_t* mant = s_mant[warp];
+  for (int t = 0; t < max_steps; ++t) {
+    if (!__any_sync(FULL, alive)) break;
+    const Key2 key = split_i(rng, my);  // split(rng, N+1)[j+1]
+    rng = split_i(rng, 0u);             // split(rng, N+1)[0]
+    const uint32_t m = alive ? madn_det_valid_mask(g, s) : 0u;
+    // warp-wide compaction of (lane, action) pairs
+    const int cnt = __popc(m);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int v = __shfl_up_sync(FULL, incl, o);
+      if (lane >= o) incl += v;
     }
+    const int total = __shfl_sync(FULL, incl, 31);
+    int off = incl - cnt;
+    for (uint32_t mm = m; mm; mm &= mm - 1) items[off++] = (uint16_t)((lane << 8) | (__ffs(mm) - 1));
+    __syncwarp();
+    for (int base = 0; base < total; base += 32) {
+      const int j = base + lane;
+      const int it = (j < total) ? (int)items[j] : 0;
+      const int o = it >> 8, a = it & 0xFF;
+      Key2 k{__shfl_sync(FULL, key.a, o), __shfl_sync(FULL, key.b, o)};
+      const uint32_t v = bits_i(k, (uint32_t)a) >> 9;
+      if (j < total) mant[o * 24 + a] = v;
+    }
+    __syncwarp();
+    if (alive) {
+      if (m) {
+        int best = -1;
+        uint32_t bm = 0;
+        for (uint32_t mm = m; mm; mm &= mm - 1) {
+          const int a = __ffs(mm) - 1;
+          const uint32_t v = mant[lane * 24 + a];
+          if (best < 0 || v > bm) { best = a; bm = v; }
+        }
+        madn_det_step(g, s, best / 6, best % 6 + 1, m);  // map_action (deterministic_madn.py:469-479)
+      } else {
+        madn_det_no_step(g, s);
+      }
+      ++len;
+      alive = !s.done;
+    }
+    __syncwarp();
+  }
+  if (i < n) {
     store_det_all(g, p, i, s);
     if (game_len) game_len[i] = len;
   }
   if (total_steps) {
     unsigned v = (unsigned)len;
 #pragma unroll
-    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-    if ((threadIdx.x & 31) == 0 && v) atomicAdd(total_steps, (unsigned long long)v);
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    if (lane == 0 && v) atomicAdd(total_steps, (unsigned long long)v);
   }
 }
 
