@@ -1,0 +1,118 @@
+"""`jax.numpy` stand-in: NumPy functions with JAX's default 32-bit dtypes, returning `Arr`."""
+import builtins
+
+import numpy as _np
+
+from ._core import Arr, wrap, _narrow
+
+ndarray = Arr
+int8, int16, int32, int64 = _np.int8, _np.int16, _np.int32, _np.int32
+uint8, uint16, uint32, uint64 = _np.uint8, _np.uint16, _np.uint32, _np.uint32
+float16, float32, float64 = _np.float16, _np.float32, _np.float32
+bool_ = _np.bool_
+inf, pi, nan, newaxis = _np.inf, _np.pi, _np.nan, None
+
+
+def _u(x):
+    if isinstance(x, Arr):
+        return _np.asarray(x)
+    if isinstance(x, (list, tuple)):
+        return type(x)(_u(v) for v in x)
+    return x
+
+
+def _default(dtype, x=None):
+    return dtype
+
+
+def array(x, dtype=None, copy=True):
+    a = _np.array(_u(x), dtype=dtype)
+    return wrap(a)
+
+
+asarray = array
+
+
+def arange(*a, dtype=None):
+    r = _np.arange(*[_u(v) for v in a], dtype=dtype)
+    return wrap(r)
+
+
+def zeros(shape, dtype=None):
+    return wrap(_np.zeros(_u(shape), dtype=dtype or _np.float32))
+
+
+def ones(shape, dtype=None):
+    return wrap(_np.ones(_u(shape), dtype=dtype or _np.float32))
+
+
+def full(shape, fill_value, dtype=None):
+    return wrap(_np.full(_u(shape), _u(fill_value), dtype=dtype))
+
+
+def zeros_like(x, dtype=None):
+    return wrap(_np.zeros_like(_u(x), dtype=dtype))
+
+
+def ones_like(x, dtype=None):
+    return wrap(_np.ones_like(_u(x), dtype=dtype))
+
+
+def full_like(x, fill_value, dtype=None):
+    return wrap(_np.full_like(_u(x), _u(fill_value), dtype=dtype))
+
+
+def _wrapfn(name):
+    f = getattr(_np, name)
+
+    def g(*a, **k):
+        with _np.errstate(over="ignore", invalid="ignore", divide="ignore"):
+            r = f(*[_u(v) for v in a], **{kk: _u(vv) for kk, vv in k.items()})
+        if isinstance(r, tuple):
+            return tuple(wrap(x) for x in r)
+        if isinstance(r, list):
+            return [wrap(x) for x in r]
+        return wrap(r) if isinstance(r, (_np.ndarray, _np.generic)) else r
+
+    g.__name__ = name
+    return g
+
+
+for _n in ["where", "isin", "concatenate", "all", "any", "sum", "roll", "count_nonzero", "diag", "reshape", "sign", "max", "min",
+           "fliplr", "flipud", "unique", "tile", "logical_or", "logical_and", "logical_not", "log", "exp", "copy", "argwhere",
+           "stack", "mean", "abs", "clip", "maximum", "minimum", "cumsum", "argmin", "take", "expand_dims", "squeeze",
+           "array_equal", "array_split", "transpose", "sqrt", "prod", "floor", "ceil", "mod", "equal", "not_equal", "power",
+           "broadcast_to", "moveaxis", "swapaxes", "sort", "nonzero", "trace", "dot", "matmul", "square", "tanh", "round",
+           "std", "var", "median", "linspace", "eye", "outer", "log2", "isnan", "isinf", "isfinite", "vstack", "hstack",
+           "allclose", "cumprod", "diff", "flip", "ravel", "atleast_1d", "triu", "tril", "searchsorted", "bincount", "split"]:
+    globals()[_n] = _wrapfn(_n)
+
+
+def argmax(x, axis=None, **k):
+    return wrap(_np.asarray(_np.argmax(_u(x), axis=axis)).astype(_np.int32))
+
+
+def argsort(x, axis=-1, **k):
+    return wrap(_np.argsort(_u(x), axis=axis, kind="stable").astype(_np.int32))
+
+
+def meshgrid(*xs, indexing="xy"):
+    return [wrap(m) for m in _np.meshgrid(*[_u(x) for x in xs], indexing=indexing)]
+
+
+def repeat(a, repeats, axis=None, total_repeat_length=None):
+    r = _np.repeat(_u(a), _u(repeats), axis=axis)
+    if total_repeat_length is not None:
+        if r.shape[0] < total_repeat_length:
+            pad = _np.full((total_repeat_length - r.shape[0],) + r.shape[1:], r[-1] if r.shape[0] else 0, dtype=r.dtype)
+            r = _np.concatenate([r, pad])
+        r = r[:total_repeat_length]
+    return wrap(r)
+
+
+def iinfo(d):
+    return _np.iinfo(d)
+
+
+def finfo(d):
+    return _np.finfo(d)
