@@ -71,3 +71,8 @@ def host_key(key):
         key = key.detach().cpu().tolist()
     k = [int(x) & 0xFFFFFFFF for x in list(key)]
     return (C.c_uint32 * 2)(k[0], k[1])
+
+
+class DogState(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("board", "current_player", "pins", "reward", "done", "deck", "hands",
+                                          "swap_choices", "round_starter", "phase", "key", "hand_size")]

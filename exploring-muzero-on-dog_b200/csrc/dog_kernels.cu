@@ -1,0 +1,364 @@
+// dog_kernels.cu — CUDA kernels (sm_100a) + C-ABI for the DOG environment.  One warp per game,
+// four games per 128-thread CTA; see dog_core.cuh for the per-warp shared record and the rules.
+// HBM layout = batched leaves of the reference `DOG` pytree (DOG/dog.py:31-56), game axis leading.
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../include/dogstep.h"
+#include "common.cuh"
+#include "jaxrand.cuh"
+#include "dog_core.cuh"
+
+namespace dogstep {
+
+constexpr int kDogThreads = 128;
+constexpr int kDogWarps = kDogThreads / 32;
+
+struct DogPtrs {
+  int8_t* board;
+  int8_t* cur;
+  int32_t* pins;
+  int8_t* reward;
+  uint8_t* done;
+  int8_t* deck;
+  int8_t* hands;
+  int8_t* swap_choices;
+  int8_t* round_starter;
+  int8_t* phase;
+  uint32_t* key;
+  int8_t* hand_size;
+};
+
+__device__ __forceinline__ void dog_load(const DogGeom& g, const DogPtrs& p, int64_t i, DogS& s, int lane) {
+  for (int k = lane; k < 64; k += 32) s.board[k] = (k < g.total) ? p.board[i * g.total + k] : (int8_t)-1;
+  if (lane < 16) s.pins[lane >> 2][lane & 3] = (lane < g.n * 4) ? p.pins[i * g.n * 4 + lane] : -1;
+  for (int k = lane; k < 64; k += 32) {
+    int q = k >> 4, c = k & 15;
+    s.hands[q][c] = (q < g.n && c < kNCard) ? p.hands[(i * g.n + q) * kNCard + c] : (int8_t)0;
+  }
+  if (lane < 16) s.deck[lane] = (lane < kNCard) ? p.deck[i * kNCard + lane] : (int8_t)0;
+  if (lane < 4) s.swap_choices[lane] = p.swap_choices[i * 4 + lane];
+  if (lane < 2) s.key[lane] = p.key[i * 2 + lane];
+  if (lane == 0) {
+    s.cur = p.cur[i];
+    s.reward = p.reward[i];
+    s.done = p.done[i] != 0;
+    s.round_starter = p.round_starter[i];
+    s.phase = p.phase[i];
+    s.hand_size = p.hand_size[i];
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ void dog_store(const DogGeom& g, const DogPtrs& p, int64_t i, const DogS& s, int lane) {
+  __syncwarp();
+  for (int k = lane; k < g.total; k += 32) p.board[i * g.total + k] = s.board[k];
+  if (lane < g.n * 4) p.pins[i * g.n * 4 + lane] = s.pins[lane >> 2][lane & 3];
+  for (int k = lane; k < 64; k += 32) {
+    int q = k >> 4, c = k & 15;
+    if (q < g.n && c < kNCard) p.hands[(i * g.n + q) * kNCard + c] = s.hands[q][c];
+  }
+  if (lane < kNCard) p.deck[i * kNCard + lane] = s.deck[lane];
+  if (lane < 4) p.swap_choices[i * 4 + lane] = s.swap_choices[lane];
+  if (lane < 2) p.key[i * 2 + lane] = s.key[lane];
+  if (lane == 0) {
+    p.cur[i] = (int8_t)s.cur;
+    p.reward[i] = (int8_t)s.reward;
+    p.done[i] = (uint8_t)s.done;
+    p.round_starter[i] = (int8_t)s.round_starter;
+    p.phase[i] = (int8_t)s.phase;
+    p.hand_size[i] = (int8_t)s.hand_size;
+  }
+}
+
+// categorical(key, where(mask, 0, -1e9)) over the legal mask in s.mask: legal actions are compacted into
+// s.items, the Threefry draws are dealt evenly to the lanes, the winner is the FIRST action with the largest
+// 23-bit uniform mantissa (== argmax of logits + gumbel).  Returns -1 if nothing is legal.
+__device__ __forceinline__ int dog_categorical(const DogGeom& g, DogS& s, int lane, Key2 key) {
+  const uint32_t FULL = 0xFFFFFFFFu;
+  const int nwords = (g.num_actions + 31) >> 5;
+  uint32_t w = (lane < nwords) ? s.mask[lane] : 0u;
+  int cnt = __popc(w), incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int v = __shfl_up_sync(FULL, incl, o);
+    if (lane >= o) incl += v;
+  }
+  const int total = __shfl_sync(FULL, incl, 31);
+  if (total == 0) return -1;
+  int off = incl - cnt;
+  for (uint32_t m = w; m; m &= m - 1) s.items[off++] = (uint16_t)(lane * 32 + __ffs(m) - 1);
+  __syncwarp();
+  uint32_t best_m = 0;
+  int best_a = 0x7FFFFFFF;
+  for (int j = lane; j < total; j += 32) {
+    int a = s.items[j];
+    uint32_t m = bits_i(key, (uint32_t)a) >> 9;
+    if (best_a == 0x7FFFFFFF || m > best_m) { best_m = m; best_a = a; }  // items ascend, so ties keep the first
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    uint32_t om = __shfl_xor_sync(FULL, best_m, o);
+    int oa = __shfl_xor_sync(FULL, best_a, o);
+    bool take = (oa != 0x7FFFFFFF) && (best_a == 0x7FFFFFFF || om > best_m || (om == best_m && oa < best_a));
+    if (take) { best_m = om; best_a = oa; }
+  }
+  __syncwarp();
+  return best_a;
+}
+
+#define DOG_KERNEL_PROLOGUE                                            \
+  __shared__ DogS sh[kDogWarps];                                       \
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;          \
+  const int64_t i = (int64_t)blockIdx.x * kDogWarps + warp;            \
+  DogS& s = sh[warp];
+
+__global__ void __launch_bounds__(kDogThreads) k_dog_reset(const __grid_constant__ DogGeom g, DogPtrs p, int64_t n,
+                                                           const int32_t* __restrict__ seeds, int starting_player) {
+  DOG_KERNEL_PROLOGUE
+  if (i >= n) return;
+  if (lane == 0) {  // env_reset (dog.py:83-181)
+    Key2 k0 = prng_key(seeds[i]);
+    Key2 knew = split_i(k0, 0), sub = split_i(k0, 1);
+    int sp = starting_player;
+    if (sp < 0 || sp >= g.n) sp = randint_i(sub, 0, 0, g.n);
+    for (int q = 0; q < 4; ++q)
+      for (int k = 0; k < 4; ++k) s.pins[q][k] = -1;
+    if (DG_RULE(g, DOGSTEP_RULE_INITIAL_FREE_PIN))
+      for (int q = 0; q < g.n; ++q) s.pins[q][0] = g.start[q];
+    dog_set_pins_on_board(g, s.pins, s.board);
+    for (int q = 0; q < 4; ++q)
+      for (int k = 0; k < 16; ++k) s.hands[q][k] = 0;
+    for (int k = 0; k < 16; ++k) s.deck[k] = (k < kNCard) ? 8 : 0;
+    s.deck[0] = 6;
+    for (int q = 0; q < 4; ++q) s.swap_choices[q] = -1;
+    s.cur = sp;
+    s.reward = 0;
+    s.done = 0;
+    s.round_starter = -1;
+    s.phase = 0;
+    s.hand_size = 6;
+    s.key[0] = knew.a;
+    s.key[1] = knew.b;
+  }
+  __syncwarp();
+  dog_distribute_cards(g, s, lane);
+  dog_store(g, p, i, s, lane);
+}
+
+__global__ void __launch_bounds__(kDogThreads) k_dog_valid_actions(const __grid_constant__ DogGeom g, DogPtrs p, int64_t n,
+                                                                   uint8_t* __restrict__ mask) {
+  DOG_KERNEL_PROLOGUE
+  if (i >= n) return;
+  dog_load(g, p, i, s, lane);
+  dog_build_mask(g, s, lane);
+  uint8_t* out = mask + i * g.num_actions;
+  for (int a = lane; a < g.num_actions; a += 32) out[a] = (uint8_t)((s.mask[a >> 5] >> (a & 31)) & 1u);
+}
+
+__global__ void __launch_bounds__(kDogThreads) k_dog_step(const __grid_constant__ DogGeom g, DogPtrs p, int64_t n,
+                                                          const int32_t* __restrict__ action, int8_t* __restrict__ reward,
+                                                          uint8_t* __restrict__ done) {
+  DOG_KERNEL_PROLOGUE
+  if (i >= n) return;
+  dog_load(g, p, i, s, lane);
+  int r, d;
+  dog_env_step(g, s, lane, action[i], r, d);
+  dog_store(g, p, i, s, lane);
+  if (lane == 0) {
+    if (reward) reward[i] = (int8_t)r;
+    if (done) done[i] = (uint8_t)d;
+  }
+}
+
+__global__ void __launch_bounds__(kDogThreads) k_dog_no_step(const __grid_constant__ DogGeom g, DogPtrs p, int64_t n,
+                                                             int8_t* __restrict__ reward, uint8_t* __restrict__ done) {
+  DOG_KERNEL_PROLOGUE
+  if (i >= n) return;
+  dog_load(g, p, i, s, lane);
+  dog_no_step(g, s, lane);
+  dog_store(g, p, i, s, lane);
+  if (lane == 0) {
+    if (reward) reward[i] = 0;
+    if (done) done[i] = (uint8_t)s.done;
+  }
+}
+
+__global__ void __launch_bounds__(kDogThreads) k_dog_distribute_cards(const __grid_constant__ DogGeom g, DogPtrs p, int64_t n) {
+  DOG_KERNEL_PROLOGUE
+  if (i >= n) return;
+  dog_load(g, p, i, s, lane);
+  dog_distribute_cards(g, s, lane);
+  dog_store(g, p, i, s, lane);
+}
+
+// the reference's module-level sub-steps (dog.py:755, 790, 861, 913); env left untouched
+__global__ void __launch_bounds__(kDogThreads) k_dog_substep(const __grid_constant__ DogGeom g, DogPtrs p, int64_t n,
+                                                             const int32_t* __restrict__ kind, const int32_t* __restrict__ args,
+                                                             int8_t* __restrict__ board_out, int32_t* __restrict__ pins_out,
+                                                             int8_t* __restrict__ reward, uint8_t* __restrict__ done) {
+  DOG_KERNEL_PROLOGUE
+  if (i >= n) return;
+  dog_load(g, p, i, s, lane);
+  if (lane == 0) {
+    const int32_t* a = args + i * 4;
+    int r = 0, d = 0;
+    int k = kind[i];
+    if (k == 0) dog_step_normal(g, s, a[0], a[1], r, d);
+    else if (k == 1) dog_step_neg(g, s, a[0], a[1], r, d);
+    else if (k == 2) dog_step_swap(g, s, a[0], a[1], r, d);
+    else {
+      int dist[4] = {a[0], a[1], a[2], a[3]};
+      dog_step_hot7(g, s, dist, r, d);
+    }
+    reward[i] = (int8_t)r;
+    done[i] = (uint8_t)d;
+  }
+  __syncwarp();
+  for (int k = lane; k < g.total; k += 32) board_out[i * g.total + k] = s.board[k];
+  if (lane < g.n * 4) pins_out[i * g.n * 4 + lane] = s.pins[lane >> 2][lane & 3];
+}
+
+__device__ __forceinline__ void dog_random_turn(const DogGeom& g, DogS& s, int lane, Key2 key) {
+  dog_build_mask(g, s, lane);
+  int a = dog_categorical(g, s, lane, key);
+  if (a >= 0) {
+    int r, d;
+    dog_env_step(g, s, lane, a, r, d);
+  } else {
+    dog_no_step(g, s, lane);
+  }
+}
+
+__global__ void __launch_bounds__(kDogThreads) k_dog_random_step(const __grid_constant__ DogGeom g, DogPtrs p, int64_t n,
+                                                                 Key2 rng, int64_t game_offset,
+                                                                 unsigned long long* __restrict__ active_count) {
+  DOG_KERNEL_PROLOGUE
+  if (i >= n) return;
+  if (p.done[i] != 0) return;  // warp-uniform
+  dog_load(g, p, i, s, lane);
+  dog_random_turn(g, s, lane, split_i(rng, (uint32_t)(game_offset + i + 1)));
+  dog_store(g, p, i, s, lane);
+  if (active_count && lane == 0) atomicAdd(active_count, 1ull);
+}
+
+__global__ void __launch_bounds__(kDogThreads) k_dog_play_random(const __grid_constant__ DogGeom g, DogPtrs p, int64_t n, Key2 rng0,
+                                                                 int64_t game_offset, int max_steps,
+                                                                 int32_t* __restrict__ game_len,
+                                                                 unsigned long long* __restrict__ total_steps) {
+  DOG_KERNEL_PROLOGUE
+  if (i >= n) return;
+  dog_load(g, p, i, s, lane);
+  Key2 rng = rng0;
+  const uint32_t my = (uint32_t)(game_offset + i + 1);
+  int len = 0;
+  while (len < max_steps) {
+    __syncwarp();
+    if (s.done) break;  // shared, warp-uniform
+    Key2 key = split_i(rng, my);
+    rng = split_i(rng, 0u);
+    dog_random_turn(g, s, lane, key);
+    ++len;
+  }
+  dog_store(g, p, i, s, lane);
+  if (lane == 0) {
+    if (game_len) game_len[i] = len;
+    if (total_steps && len) atomicAdd(total_steps, (unsigned long long)len);
+  }
+}
+
+static inline unsigned dog_blocks(int64_t n) { return (unsigned)((n + kDogWarps - 1) / kDogWarps); }
+
+static int dog_ptrs(const dogstep_dog_state* s, DogPtrs* p) {
+  if (!s || !s->board || !s->current_player || !s->pins || !s->reward || !s->done || !s->deck || !s->hands ||
+      !s->swap_choices || !s->round_starter || !s->phase || !s->key || !s->hand_size)
+    return DOGSTEP_ERR_INVALID_ARG;
+  *p = DogPtrs{s->board, s->current_player, s->pins, s->reward, s->done, s->deck, s->hands, s->swap_choices,
+               s->round_starter, s->phase, s->key, s->hand_size};
+  return DOGSTEP_OK;
+}
+
+#define DOG_PROLOGUE                                 \
+  DogGeom g;                                         \
+  DogPtrs p;                                         \
+  if (n < 0) return DOGSTEP_ERR_INVALID_ARG;         \
+  if (int rc = dog_make_geom(cfg, &g)) return rc;    \
+  if (int rc = dog_ptrs(s, &p)) return rc;           \
+  if (n == 0) return DOGSTEP_OK;                     \
+  cudaStream_t st = (cudaStream_t)stream;
+
+}  // namespace dogstep
+
+using namespace dogstep;
+
+extern "C" {
+
+int dogstep_dog_num_actions(const dogstep_dog_cfg* cfg) {
+  DogGeom g;
+  if (int rc = dog_make_geom(cfg, &g)) return rc;
+  return g.num_actions;
+}
+
+int dogstep_dog_reset(const dogstep_dog_state* s, int64_t n, const dogstep_dog_cfg* cfg, const int32_t* seeds,
+                      int32_t starting_player, void* stream) {
+  DOG_PROLOGUE
+  if (!seeds) return DOGSTEP_ERR_INVALID_ARG;
+  k_dog_reset<<<dog_blocks(n), kDogThreads, 0, st>>>(g, p, n, seeds, starting_player);
+  return check_launch();
+}
+
+int dogstep_dog_valid_actions(const dogstep_dog_state* s, int64_t n, const dogstep_dog_cfg* cfg, uint8_t* mask, void* stream) {
+  DOG_PROLOGUE
+  if (!mask) return DOGSTEP_ERR_INVALID_ARG;
+  k_dog_valid_actions<<<dog_blocks(n), kDogThreads, 0, st>>>(g, p, n, mask);
+  return check_launch();
+}
+
+int dogstep_dog_step(const dogstep_dog_state* s, int64_t n, const dogstep_dog_cfg* cfg, const int32_t* action, int8_t* reward,
+                     uint8_t* done, void* stream) {
+  DOG_PROLOGUE
+  if (!action) return DOGSTEP_ERR_INVALID_ARG;
+  k_dog_step<<<dog_blocks(n), kDogThreads, 0, st>>>(g, p, n, action, reward, done);
+  return check_launch();
+}
+
+int dogstep_dog_no_step(const dogstep_dog_state* s, int64_t n, const dogstep_dog_cfg* cfg, int8_t* reward, uint8_t* done,
+                        void* stream) {
+  DOG_PROLOGUE
+  k_dog_no_step<<<dog_blocks(n), kDogThreads, 0, st>>>(g, p, n, reward, done);
+  return check_launch();
+}
+
+int dogstep_dog_distribute_cards(const dogstep_dog_state* s, int64_t n, const dogstep_dog_cfg* cfg, void* stream) {
+  DOG_PROLOGUE
+  k_dog_distribute_cards<<<dog_blocks(n), kDogThreads, 0, st>>>(g, p, n);
+  return check_launch();
+}
+
+int dogstep_dog_substep(const dogstep_dog_state* s, int64_t n, const dogstep_dog_cfg* cfg, const int32_t* kind,
+                        const int32_t* args, int8_t* board_out, int32_t* pins_out, int8_t* reward, uint8_t* done, void* stream) {
+  DOG_PROLOGUE
+  if (!kind || !args || !board_out || !pins_out || !reward || !done) return DOGSTEP_ERR_INVALID_ARG;
+  k_dog_substep<<<dog_blocks(n), kDogThreads, 0, st>>>(g, p, n, kind, args, board_out, pins_out, reward, done);
+  return check_launch();
+}
+
+int dogstep_dog_random_step(const dogstep_dog_state* s, int64_t n, const dogstep_dog_cfg* cfg, const uint32_t* host_rng_key,
+                            int64_t game_offset, unsigned long long* active_count, void* stream) {
+  DOG_PROLOGUE
+  if (!host_rng_key) return DOGSTEP_ERR_INVALID_ARG;
+  k_dog_random_step<<<dog_blocks(n), kDogThreads, 0, st>>>(g, p, n, Key2{host_rng_key[0], host_rng_key[1]}, game_offset,
+                                                           active_count);
+  return check_launch();
+}
+
+int dogstep_dog_play_random(const dogstep_dog_state* s, int64_t n, const dogstep_dog_cfg* cfg, const uint32_t* host_rng_key,
+                            int64_t game_offset, int32_t max_steps, int32_t* game_len, unsigned long long* total_steps,
+                            void* stream) {
+  DOG_PROLOGUE
+  if (!host_rng_key || max_steps < 0) return DOGSTEP_ERR_INVALID_ARG;
+  k_dog_play_random<<<dog_blocks(n), kDogThreads, 0, st>>>(g, p, n, Key2{host_rng_key[0], host_rng_key[1]}, game_offset,
+                                                           max_steps, game_len, total_steps);
+  return check_launch();
+}
+
+}  // extern "C"

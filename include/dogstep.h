@@ -131,6 +131,56 @@ int dogstep_madn_cls_no_step(const dogstep_madn_cls_state* s, int64_t n, const d
 int dogstep_madn_cls_encode_board(const dogstep_madn_cls_state* s, int64_t n, const dogstep_madn_cfg* cfg,
                                   int8_t* obs, void* stream);
 
+/* ---------------------------------------------------------------- DOG (2v2 card game)
+ * Batched leaves of the `DOG` dataclass (DOG/dog.py:31-56).  num_cards is 14: the disable_* rule bits
+ * are rejected with DOGSTEP_ERR_UNSUPPORTED (the reference itself is only self-consistent with all cards).
+ * Action space: [0,396) joker copies, [396,792) real cards, [792,806) swap-phase card choice, for
+ * total_board_size 56 (get_play_action_size, DOG/dog.py:58-59). */
+typedef dogstep_madn_cfg dogstep_dog_cfg;
+typedef struct {
+  int8_t* board;          /* [n, total_board_size] */
+  int8_t* current_player; /* [n] */
+  int32_t* pins;          /* [n, num_players, 4]  (int32 in the reference) */
+  int8_t* reward;         /* [n] */
+  uint8_t* done;          /* [n] */
+  int8_t* deck;           /* [n, 14] remaining copies per card type */
+  int8_t* hands;          /* [n, num_players, 14] */
+  int8_t* swap_choices;   /* [n, 4] */
+  int8_t* round_starter;  /* [n] */
+  int8_t* phase;          /* [n] 0 play, 1 partner card swap */
+  uint32_t* key;          /* [n, 2] */
+  int8_t* hand_size;      /* [n] size of the NEXT deal (6,5,4,3,2,6,...) */
+} dogstep_dog_state;
+
+/* get_play_action_size(env) + 14 — DOG/dog.py:58-59, 693-711 (negative = error code) */
+int dogstep_dog_num_actions(const dogstep_dog_cfg* cfg);
+/* env_reset (+ first distribute_cards) — DOG/dog.py:83-181 */
+int dogstep_dog_reset(const dogstep_dog_state* s, int64_t n, const dogstep_dog_cfg* cfg, const int32_t* seeds,
+                      int32_t starting_player, void* stream);
+/* valid_actions — DOG/dog.py:693-711 (valid_step_actions :618-691).  mask: uint8 [n, num_actions] */
+int dogstep_dog_valid_actions(const dogstep_dog_state* s, int64_t n, const dogstep_dog_cfg* cfg, uint8_t* mask, void* stream);
+/* env_step — DOG/dog.py:1117-1131.  action: int32 [n] */
+int dogstep_dog_step(const dogstep_dog_state* s, int64_t n, const dogstep_dog_cfg* cfg, const int32_t* action, int8_t* reward,
+                     uint8_t* done, void* stream);
+/* no_step — DOG/dog.py:713-752 */
+int dogstep_dog_no_step(const dogstep_dog_state* s, int64_t n, const dogstep_dog_cfg* cfg, int8_t* reward, uint8_t* done,
+                        void* stream);
+/* distribute_cards — DOG/dog.py:201-298 */
+int dogstep_dog_distribute_cards(const dogstep_dog_state* s, int64_t n, const dogstep_dog_cfg* cfg, void* stream);
+/* step_normal_move / step_neg_move / step_swap / step_hot_7 — DOG/dog.py:790, 861, 755, 913 as the reference's
+ * tests call them: kind int32[n] (0,1,2,3), args int32[n,4] = (pin, move) | (pin, move) | (pin, pos) | dist[4];
+ * returns (board int8[n,total], pins int32[n,P,4], reward, done) and leaves the env untouched. */
+int dogstep_dog_substep(const dogstep_dog_state* s, int64_t n, const dogstep_dog_cfg* cfg, const int32_t* kind,
+                        const int32_t* args, int8_t* board_out, int32_t* pins_out, int8_t* reward, uint8_t* done, void* stream);
+/* one fused lockstep iteration of the random-legal-policy driver over DOG's 806 actions (same key
+ * derivation as dogstep_madn_det_random_step) */
+int dogstep_dog_random_step(const dogstep_dog_state* s, int64_t n, const dogstep_dog_cfg* cfg, const uint32_t* host_rng_key,
+                            int64_t game_offset, unsigned long long* active_count, void* stream);
+/* the whole random-policy loop as one persistent launch (cap MuZero_DOG/evaluate_agent.py:518) */
+int dogstep_dog_play_random(const dogstep_dog_state* s, int64_t n, const dogstep_dog_cfg* cfg, const uint32_t* host_rng_key,
+                            int64_t game_offset, int32_t max_steps, int32_t* game_len, unsigned long long* total_steps,
+                            void* stream);
+
 /* ---------------------------------------------------------------- jax.random on device
  * Stand-ins for the jax.random calls the self-play drivers make around the env functions
  * (game_agent.py:60,187-188).  keys are raw uint32[2]. */

@@ -252,3 +252,119 @@ def madn_det_play_random(s, rng_key, max_steps=2000, game_offset=0, float_gumbel
                                         _p(game_len), C.byref(total))
     assert rc == 0
     return game_len, int(total.value), key
+
+
+# --------------------------------------------------------------------------- DOG
+class _DogSoa(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("board", "cur", "pins", "reward", "done", "deck", "hands", "swap_choices",
+                                          "round_starter", "phase", "key", "hand_size")]
+
+
+class DogCfg(MadnCfg):
+    @property
+    def num_actions(self):
+        return 2 * (4 * (13 + self.total) + 120) + 14
+
+
+class DogState:
+    """SoA leaves of a batch of DOG games (NumPy, host); dtypes as in the reference dataclass (DOG/dog.py:31-56)."""
+    FIELDS = ("board", "current_player", "pins", "reward", "done", "deck", "hands", "swap_choices", "round_starter",
+              "phase", "key", "hand_size")
+
+    def __init__(self, cfg, n):
+        P = cfg.num_players
+        self.cfg, self.n = cfg, n
+        self.board = np.full((n, cfg.total), -1, np.int8)
+        self.current_player = np.zeros(n, np.int8)
+        self.pins = np.full((n, P, 4), -1, np.int32)
+        self.reward = np.zeros(n, np.int8)
+        self.done = np.zeros(n, np.uint8)
+        self.deck = np.zeros((n, 14), np.int8)
+        self.hands = np.zeros((n, P, 14), np.int8)
+        self.swap_choices = np.full((n, 4), -1, np.int8)
+        self.round_starter = np.full(n, -1, np.int8)
+        self.phase = np.zeros(n, np.int8)
+        self.key = np.zeros((n, 2), np.uint32)
+        self.hand_size = np.full(n, 6, np.int8)
+
+    def soa(self):
+        return _DogSoa(*[_p(getattr(self, k)) for k in self.FIELDS])
+
+    def fields(self):
+        return {k: getattr(self, k) for k in self.FIELDS}
+
+    def copy(self):
+        o = DogState.__new__(DogState)
+        o.cfg, o.n = self.cfg, self.n
+        for k in self.FIELDS:
+            setattr(o, k, getattr(self, k).copy())
+        return o
+
+
+def dog_reset(cfg, seeds, starting_player=0):
+    seeds = _c(seeds, np.int32)
+    s = DogState(cfg, seeds.size)
+    soa = s.soa()
+    assert lib().orc_dog_reset(*cfg.args, C.c_int64(s.n), _p(seeds), C.c_int(starting_player), C.byref(soa)) == 0
+    return s
+
+
+def dog_valid_actions(s):
+    mask = np.empty((s.n, s.cfg.num_actions), np.uint8)
+    soa = s.soa()
+    assert lib().orc_dog_valid_actions(*s.cfg.args, C.c_int64(s.n), C.byref(soa), _p(mask)) == 0
+    return mask.astype(bool)
+
+
+def dog_step(s, action):
+    action = _c(action, np.int32).reshape(s.n)
+    reward = np.empty(s.n, np.int8)
+    done = np.empty(s.n, np.uint8)
+    soa = s.soa()
+    assert lib().orc_dog_step(*s.cfg.args, C.c_int64(s.n), C.byref(soa), _p(action), _p(reward), _p(done)) == 0
+    return reward, done.astype(bool)
+
+
+def dog_no_step(s):
+    reward = np.empty(s.n, np.int8)
+    done = np.empty(s.n, np.uint8)
+    soa = s.soa()
+    assert lib().orc_dog_no_step(*s.cfg.args, C.c_int64(s.n), C.byref(soa), _p(reward), _p(done)) == 0
+    return reward, done.astype(bool)
+
+
+def dog_distribute_cards(s):
+    soa = s.soa()
+    assert lib().orc_dog_distribute_cards(*s.cfg.args, C.c_int64(s.n), C.byref(soa)) == 0
+
+
+def dog_map_action_to_move(cfg, action):
+    action = _c(action, np.int32).ravel()
+    out = np.empty((action.size, 6), np.int32)
+    assert lib().orc_dog_map_action_to_move(*cfg.args, C.c_int64(action.size), _p(action), _p(out)) == 0
+    return out
+
+
+def dog_substep(s, kind, args):
+    """reference sub-steps (0 normal, 1 neg, 2 swap, 3 hot-7) -> (board, pins, reward, done); env untouched"""
+    kind = _c(kind, np.int32).reshape(s.n)
+    args = _c(args, np.int32).reshape(s.n, 4)
+    board = np.empty_like(s.board)
+    pins = np.empty_like(s.pins)
+    reward = np.empty(s.n, np.int8)
+    done = np.empty(s.n, np.uint8)
+    soa = s.soa()
+    assert lib().orc_dog_substep(*s.cfg.args, C.c_int64(s.n), C.byref(soa), _p(kind), _p(args), _p(board), _p(pins),
+                                 _p(reward), _p(done)) == 0
+    return board, pins, reward, done.astype(bool)
+
+
+def dog_play_random(s, rng_key, max_steps=2000, game_offset=0, float_gumbel=False, nthreads=1):
+    key = _c(rng_key, np.uint32).copy()
+    game_len = np.zeros(s.n, np.int32)
+    total = C.c_int64(0)
+    soa = s.soa()
+    assert lib().orc_dog_play_random(*s.cfg.args, C.c_int64(s.n), C.c_int64(game_offset), C.byref(soa), _p(key),
+                                     C.c_int(max_steps), C.c_int(int(float_gumbel)), C.c_int(nthreads), _p(game_len),
+                                     C.byref(total)) == 0
+    return game_len, int(total.value), key
