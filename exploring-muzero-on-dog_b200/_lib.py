@@ -76,3 +76,21 @@ def host_key(key):
 class DogState(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("board", "current_player", "pins", "reward", "done", "deck", "hands",
                                           "swap_choices", "round_starter", "phase", "key", "hand_size")]
+
+
+class MctsCfg(C.Structure):
+    _fields_ = [("policy", C.c_int32), ("qtransform", C.c_int32), ("num_simulations", C.c_int32), ("max_depth", C.c_int32),
+                ("num_actions", C.c_int32), ("num_chance", C.c_int32), ("embed_dim", C.c_int32),
+                ("max_num_considered_actions", C.c_int32), ("q_min", C.c_float), ("q_max", C.c_float),
+                ("value_scale", C.c_float), ("maxvisit_init", C.c_float), ("epsilon", C.c_float), ("pb_c_init", C.c_float),
+                ("pb_c_base", C.c_float), ("dirichlet_fraction", C.c_float), ("temperature", C.c_float),
+                ("gumbel_scale", C.c_float)]
+
+
+MCTS_TREE_FIELDS = ("node_visits", "raw_values", "node_values", "parents", "action_from_parent", "children_index",
+                    "children_prior_logits", "children_visits", "children_rewards", "children_discounts", "children_values",
+                    "embeddings", "is_decision", "root_invalid_actions", "root_gumbel", "search_key", "policy_key")
+
+
+class MctsTree(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in MCTS_TREE_FIELDS]

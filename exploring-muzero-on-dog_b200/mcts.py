@@ -1,0 +1,209 @@
+"""mctx-shaped search API on libdogstep.so's per-game tree kernels.
+
+Stands in for the three mctx 0.0.6 policies the reference calls (MuZero_det_MADN/muzero_deterministic_madn.py:673-684,
+MuZero_Classic_MADN/muzero_classic_madn.py:488-501, TicTacToe/mcts.py:13-22,29-37) with the same names, keyword
+arguments and PolicyOutput fields.  The networks stay the caller's: `recurrent_fn(params, rng_key, action, embedding)`
+is any callable on CUDA tensors (a Flax function behind DLPack in the reference's setting, a torch module in the
+tests) returning an object with .prior_logits/.value/.reward/.discount and the next embedding.  One simulation is
+select kernel -> recurrent_fn on [games, E] -> expand+backup kernel.
+
+Differences from mctx that are deliberate and documented: `rng_key` is a uint32 [games, 2] tensor of
+per-game keys (the reference vmaps a B=1 search per game, game_agent.py:80), and the Dirichlet root-noise SAMPLE of
+muzero_policy / stochastic_muzero_policy is an input (`dirichlet_noise`) instead of jax.random.dirichlet.
+"""
+import ctypes as C
+import functools
+from collections import namedtuple
+
+import torch
+
+from . import _lib
+
+PolicyOutput = namedtuple("PolicyOutput", ["action", "action_weights", "search_tree"])
+RootFnOutput = namedtuple("RootFnOutput", ["prior_logits", "value", "embedding"])
+RecurrentFnOutput = namedtuple("RecurrentFnOutput", ["reward", "discount", "prior_logits", "value"])
+DecisionRecurrentFnOutput = namedtuple("DecisionRecurrentFnOutput", ["chance_logits", "afterstate_value"])
+ChanceRecurrentFnOutput = namedtuple("ChanceRecurrentFnOutput", ["action_logits", "value", "reward", "discount"])
+SearchSummary = namedtuple("SearchSummary", ["visit_counts", "visit_probs", "value", "qvalues"])
+
+MUZERO, GUMBEL, STOCHASTIC = 0, 1, 2
+
+
+class _QT:
+    def __init__(self, kind, **kw):
+        self.kind, self.kw = kind, kw
+
+    def __call__(self, **kw):  # functools.partial-style refinement: qtransform_by_min_max(min_value=-1, max_value=1)
+        return _QT(self.kind, **{**self.kw, **kw})
+
+
+qtransform_by_min_max = _QT(0, min_value=0.0, max_value=1.0)
+qtransform_by_parent_and_siblings = _QT(1, epsilon=1e-8)
+qtransform_completed_by_mix_value = _QT(2, value_scale=0.1, maxvisit_init=50.0, epsilon=1e-8)
+
+
+def _resolve_qt(qt):
+    if isinstance(qt, functools.partial):
+        return qt.func(**qt.keywords)
+    return qt
+
+
+class Tree:
+    """mctx.Tree-shaped view of the device buffers ([games, nodes, actions])."""
+
+    ROOT_INDEX, NO_PARENT, UNVISITED = 0, -1, -1
+
+    def __init__(self, n, num_simulations, num_actions, num_chance, embed_dim, policy, device):
+        N, A = num_simulations + 1, num_actions + num_chance
+        i32, f32 = torch.int32, torch.float32
+        e = functools.partial(torch.empty, device=device)
+        self.node_visits, self.raw_values, self.node_values = e((n, N), dtype=i32), e((n, N), dtype=f32), e((n, N), dtype=f32)
+        self.parents, self.action_from_parent = e((n, N), dtype=i32), e((n, N), dtype=i32)
+        self.children_index, self.children_visits = e((n, N, A), dtype=i32), e((n, N, A), dtype=i32)
+        self.children_prior_logits, self.children_rewards = e((n, N, A), dtype=f32), e((n, N, A), dtype=f32)
+        self.children_discounts, self.children_values = e((n, N, A), dtype=f32), e((n, N, A), dtype=f32)
+        self.embeddings = e((n, N, embed_dim), dtype=f32)
+        self.is_decision = e((n, N), dtype=torch.uint8) if policy == STOCHASTIC else None
+        self.root_invalid_actions = e((n, A), dtype=torch.uint8)
+        self.root_gumbel = e((n, A), dtype=f32) if policy == GUMBEL else None
+        self.search_key, self.policy_key = e((n, 2), dtype=torch.uint32), e((n, 2), dtype=torch.uint32)
+        self.num_actions, self.num_chance, self.n = num_actions, num_chance, n
+
+    def cstruct(self):
+        return _lib.MctsTree(*[None if getattr(self, k) is None else C.c_void_p(getattr(self, k).data_ptr())
+                               for k in _lib.MCTS_TREE_FIELDS])
+
+    def qvalues(self, indices=0):
+        return self.children_rewards[:, indices] + self.children_discounts[:, indices] * self.children_values[:, indices]
+
+    def summary(self):
+        """mctx Tree.summary() restricted to the decision actions"""
+        A = self.num_actions
+        value = self.node_values[:, 0]
+        vc = self.children_visits[:, 0, :A].to(torch.float32)
+        tot = vc.sum(-1, keepdim=True)
+        probs = torch.where(tot > 0, vc / tot.clamp(min=1), torch.full_like(vc, 1.0 / A))
+        return SearchSummary(visit_counts=self.children_visits[:, 0, :A], visit_probs=probs, value=value,
+                             qvalues=self.qvalues(0)[:, :A])
+
+
+def _cfg(policy, qtransform, num_simulations, max_depth, A, Cn, E, **kw):
+    qt = _resolve_qt(qtransform)
+    return _lib.MctsCfg(policy=policy, qtransform=qt.kind, num_simulations=num_simulations,
+                        max_depth=num_simulations if max_depth is None else max_depth, num_actions=A, num_chance=Cn, embed_dim=E,
+                        max_num_considered_actions=kw.get("max_num_considered_actions", 16),
+                        q_min=qt.kw.get("min_value", 0.0), q_max=qt.kw.get("max_value", 1.0),
+                        value_scale=qt.kw.get("value_scale", 0.1), maxvisit_init=qt.kw.get("maxvisit_init", 50.0),
+                        epsilon=qt.kw.get("epsilon", 1e-8), pb_c_init=kw.get("pb_c_init", 1.25), pb_c_base=kw.get("pb_c_base", 19652.0),
+                        dirichlet_fraction=kw.get("dirichlet_fraction", 0.25), temperature=kw.get("temperature", 1.0),
+                        gumbel_scale=kw.get("gumbel_scale", 1.0))
+
+
+class Search:
+    """The explicit select / expand stepping API (what a jax.ffi caller drives once per simulation)."""
+
+    def __init__(self, cfg, n, device="cuda"):
+        self.cfg, self.n, self.device = cfg, n, torch.device(device)
+        self.tree = Tree(n, cfg.num_simulations, cfg.num_actions, cfg.num_chance, cfg.embed_dim, cfg.policy, self.device)
+        self._ct = self.tree.cstruct()
+        self.parent = torch.empty(n, dtype=torch.int32, device=self.device)
+        self.action = torch.empty(n, dtype=torch.int32, device=self.device)
+        self.embedding = torch.empty((n, cfg.embed_dim), dtype=torch.float32, device=self.device)
+        self.is_decision = torch.empty(n, dtype=torch.uint8, device=self.device)
+
+    def init(self, keys, root, invalid_actions=None, dirichlet_noise=None):
+        f = lambda x: None if x is None else x.contiguous()
+        inv = None if invalid_actions is None else invalid_actions.reshape(self.n, -1).to(torch.uint8).contiguous()
+        _lib.check(_lib.lib().dogstep_mcts_init(C.byref(self._ct), C.c_int64(self.n), C.byref(self.cfg), _lib.ptr(keys.contiguous()),
+                                               _lib.ptr(f(root.prior_logits.float())), _lib.ptr(f(root.value.float())),
+                                               _lib.ptr(f(root.embedding.float().reshape(self.n, -1))), _lib.ptr(inv),
+                                               _lib.ptr(f(dirichlet_noise)), _lib.stream()), "mcts_init")
+
+    def select(self, sim):
+        _lib.check(_lib.lib().dogstep_mcts_select(C.byref(self._ct), C.c_int64(self.n), C.byref(self.cfg), C.c_int32(sim),
+                                                 _lib.ptr(self.parent), _lib.ptr(self.action), _lib.ptr(self.embedding),
+                                                 _lib.ptr(self.is_decision), _lib.stream()), "mcts_select")
+        return self.parent, self.action, self.embedding, self.is_decision
+
+    def expand(self, sim, prior_logits, value, reward, discount, embedding, chance_logits=None, afterstate_value=None,
+               afterstate_embedding=None):
+        f = lambda x: None if x is None else x.float().contiguous()
+        _lib.check(_lib.lib().dogstep_mcts_expand(C.byref(self._ct), C.c_int64(self.n), C.byref(self.cfg), C.c_int32(sim),
+                                                 _lib.ptr(self.parent), _lib.ptr(self.action), _lib.ptr(f(prior_logits)),
+                                                 _lib.ptr(f(value)), _lib.ptr(f(reward)), _lib.ptr(f(discount)),
+                                                 _lib.ptr(f(embedding)), _lib.ptr(f(chance_logits)), _lib.ptr(f(afterstate_value)),
+                                                 _lib.ptr(f(afterstate_embedding)), _lib.stream()), "mcts_expand")
+
+    def policy_output(self):
+        A = self.cfg.num_actions
+        action = torch.empty(self.n, dtype=torch.int32, device=self.device)
+        weights = torch.empty((self.n, A), dtype=torch.float32, device=self.device)
+        value = torch.empty(self.n, dtype=torch.float32, device=self.device)
+        _lib.check(_lib.lib().dogstep_mcts_policy_output(C.byref(self._ct), C.c_int64(self.n), C.byref(self.cfg), _lib.ptr(action),
+                                                        _lib.ptr(weights), _lib.ptr(value), _lib.stream()), "mcts_policy_output")
+        return PolicyOutput(action=action, action_weights=weights, search_tree=self.tree), value
+
+
+def _run(search, params, root, recurrent_fn, invalid_actions, keys, dirichlet_noise=None):
+    search.init(keys, root, invalid_actions, dirichlet_noise)
+    for sim in range(search.cfg.num_simulations):
+        _, action, emb, _ = search.select(sim)
+        out, nxt = recurrent_fn(params, None, action.long(), emb)
+        search.expand(sim, out.prior_logits, out.value, out.reward, out.discount, nxt.reshape(search.n, -1))
+    return search.policy_output()[0]
+
+
+def muzero_policy(params, rng_key, root, recurrent_fn, num_simulations, invalid_actions=None, max_depth=None, *,
+                  qtransform=qtransform_by_parent_and_siblings, dirichlet_fraction=0.25, dirichlet_alpha=0.3, pb_c_init=1.25,
+                  pb_c_base=19652, temperature=1.0, dirichlet_noise=None):
+    """mctx.muzero_policy.  rng_key: uint32 [games, 2]."""
+    n, A = root.prior_logits.shape
+    E = root.embedding.reshape(n, -1).shape[1]
+    if dirichlet_noise is None and dirichlet_fraction > 0:
+        dirichlet_noise = torch.distributions.Dirichlet(torch.full((A,), float(dirichlet_alpha), device=root.value.device)).sample((n,))
+    cfg = _cfg(MUZERO, qtransform, num_simulations, max_depth, A, 0, E, pb_c_init=pb_c_init, pb_c_base=pb_c_base,
+               dirichlet_fraction=dirichlet_fraction, temperature=temperature)
+    return _run(Search(cfg, n, root.value.device), params, root, recurrent_fn, invalid_actions, rng_key,
+                dirichlet_noise if dirichlet_fraction > 0 else None)
+
+
+def gumbel_muzero_policy(params, rng_key, root, recurrent_fn, num_simulations, invalid_actions=None, max_depth=None, *,
+                         qtransform=qtransform_completed_by_mix_value, max_num_considered_actions=16, gumbel_scale=1.0):
+    """mctx.gumbel_muzero_policy.  rng_key: uint32 [games, 2]."""
+    n, A = root.prior_logits.shape
+    E = root.embedding.reshape(n, -1).shape[1]
+    cfg = _cfg(GUMBEL, qtransform, num_simulations, max_depth, A, 0, E, max_num_considered_actions=max_num_considered_actions,
+               gumbel_scale=gumbel_scale)
+    return _run(Search(cfg, n, root.value.device), params, root, recurrent_fn, invalid_actions, rng_key)
+
+
+def stochastic_muzero_policy(params, rng_key, root, decision_recurrent_fn, chance_recurrent_fn, num_simulations,
+                             invalid_actions=None, max_depth=None, *, qtransform=qtransform_by_parent_and_siblings,
+                             dirichlet_fraction=0.25, dirichlet_alpha=0.3, pb_c_init=1.25, pb_c_base=19652, temperature=1.0,
+                             dirichlet_noise=None, num_chance_outcomes=None):
+    """mctx.stochastic_muzero_policy: decision nodes (A actions) alternate with chance nodes (C outcomes).
+    Both callbacks are evaluated every simulation (as mctx does) and the kernel picks per game by node type; the stored
+    embedding is padded to the wider of the state / afterstate embeddings."""
+    n, A = root.prior_logits.shape
+    dev = root.value.device
+    state_emb = root.embedding.reshape(n, -1).float()
+    dummy_out, dummy_after = decision_recurrent_fn(params, None, torch.zeros(n, dtype=torch.long, device=dev), state_emb)
+    Cn = dummy_out.chance_logits.shape[-1] if num_chance_outcomes is None else num_chance_outcomes
+    Es, Ea = state_emb.shape[1], dummy_after.reshape(n, -1).shape[1]
+    E = max(Es, Ea)
+    pad = lambda x: torch.nn.functional.pad(x.reshape(n, -1).float(), (0, E - x.reshape(n, -1).shape[1]))
+    if dirichlet_noise is None and dirichlet_fraction > 0:
+        dirichlet_noise = torch.distributions.Dirichlet(torch.full((A,), float(dirichlet_alpha), device=dev)).sample((n,))
+    cfg = _cfg(STOCHASTIC, qtransform, num_simulations, max_depth, A, Cn, E, pb_c_init=pb_c_init, pb_c_base=pb_c_base,
+               dirichlet_fraction=dirichlet_fraction, temperature=temperature)
+    s = Search(cfg, n, dev)
+    s.init(rng_key, RootFnOutput(root.prior_logits, root.value, pad(state_emb)), invalid_actions,
+           dirichlet_noise if dirichlet_fraction > 0 else None)
+    for sim in range(num_simulations):
+        _, action, emb, is_dec = s.select(sim)
+        a = action.long()
+        dec, after = decision_recurrent_fn(params, None, a.clamp(max=A - 1), emb[:, :Es])
+        ch, nxt = chance_recurrent_fn(params, None, (a - A).clamp(min=0, max=Cn - 1), emb[:, :Ea])
+        s.expand(sim, ch.action_logits, ch.value, ch.reward, ch.discount, pad(nxt), dec.chance_logits, dec.afterstate_value,
+                 pad(after))
+    return s.policy_output()[0]

@@ -181,6 +181,82 @@ int dogstep_dog_play_random(const dogstep_dog_state* s, int64_t n, const dogstep
                             int64_t game_offset, int32_t max_steps, int32_t* game_len, unsigned long long* total_steps,
                             void* stream);
 
+/* ---------------------------------------------------------------- MCTS (mctx 0.0.6 search, per-game trees)
+ * Stand-in for the search calls the reference makes through the third-party `mctx` package:
+ *   mctx.gumbel_muzero_policy      MuZero_det_MADN/muzero_deterministic_madn.py:673-684 (run_muzero_mcts :663-704)
+ *   mctx.stochastic_muzero_policy  MuZero_Classic_MADN/muzero_classic_madn.py:488-501 (run_stochastic_muzero_mcts :464-517)
+ *   mctx.muzero_policy / gumbel    TicTacToe/mcts.py:13-22, 29-37
+ * The networks (root_fn / recurrent_fn) stay with the caller: one simulation is
+ *   dogstep_mcts_select  ->  caller evaluates recurrent_fn on the gathered parent embeddings  ->  dogstep_mcts_expand
+ * Tree buffers have mctx's `Tree` layout (batch, node, action) so `policy_output.search_tree` can alias them.
+ * Float contract: IEEE add/mul/div/sqrt without FMA contraction, exp/log correctly rounded from double, sums in the
+ * fixed order "lane l accumulates a = l, l+32, ...; then butterfly 16,8,4,2,1" (MCTS numerics). */
+#define DOGSTEP_MCTS_MUZERO      0 /* mctx.muzero_policy: PUCT + tie-break noise, sample from visit counts */
+#define DOGSTEP_MCTS_GUMBEL      1 /* mctx.gumbel_muzero_policy: sequential halving at the root */
+#define DOGSTEP_MCTS_STOCHASTIC  2 /* mctx.stochastic_muzero_policy: decision / chance levels alternate */
+#define DOGSTEP_Q_BY_MIN_MAX             0 /* qtransform_by_min_max(min_value, max_value) */
+#define DOGSTEP_Q_BY_PARENT_AND_SIBLINGS 1 /* qtransform_by_parent_and_siblings(epsilon) */
+#define DOGSTEP_Q_COMPLETED_BY_MIX_VALUE 2 /* qtransform_completed_by_mix_value(value_scale, maxvisit_init, epsilon) */
+
+typedef struct {
+  int32_t policy, qtransform;
+  int32_t num_simulations, max_depth;
+  int32_t num_actions;  /* A: decision actions */
+  int32_t num_chance;   /* C: chance outcomes (stochastic only, else 0); children arrays are A' = A + C wide */
+  int32_t embed_dim;    /* floats per stored node embedding */
+  int32_t max_num_considered_actions; /* gumbel */
+  float q_min, q_max;                 /* by_min_max */
+  float value_scale, maxvisit_init;   /* completed_by_mix_value */
+  float epsilon;                      /* 1e-8 in mctx */
+  float pb_c_init, pb_c_base;         /* 1.25, 19652 */
+  float dirichlet_fraction;           /* muzero / stochastic root noise mix; the Dirichlet SAMPLE is an input */
+  float temperature;                  /* final sampling temperature (muzero / stochastic) */
+  float gumbel_scale;                 /* gumbel */
+} dogstep_mcts_cfg;
+
+typedef struct {
+  int32_t* node_visits;           /* [n, N]      N = num_simulations + 1 */
+  float* raw_values;              /* [n, N] */
+  float* node_values;             /* [n, N] */
+  int32_t* parents;               /* [n, N]      -1 = no parent */
+  int32_t* action_from_parent;    /* [n, N] */
+  int32_t* children_index;        /* [n, N, A']  -1 = unvisited */
+  float* children_prior_logits;   /* [n, N, A'] */
+  int32_t* children_visits;       /* [n, N, A'] */
+  float* children_rewards;        /* [n, N, A'] */
+  float* children_discounts;      /* [n, N, A'] */
+  float* children_values;         /* [n, N, A'] */
+  float* embeddings;              /* [n, N, E] */
+  uint8_t* is_decision;           /* [n, N]  stochastic only (may be NULL otherwise) */
+  uint8_t* root_invalid_actions;  /* [n, A'] */
+  float* root_gumbel;             /* [n, A'] gumbel only (may be NULL otherwise) */
+  uint32_t* search_key;           /* [n, 2]  key chain of search(): rng, sim, exp = split(rng, 3) per simulation */
+  uint32_t* policy_key;           /* [n, 2]  key of the final categorical draw (muzero / stochastic) */
+} dogstep_mcts_tree;
+
+/* policy prologue + instantiate_tree_from_root.  keys: uint32 [n,2] = the rng_key each game hands to the mctx policy.
+ * root_prior_logits f32 [n,A], root_value f32 [n], root_embedding f32 [n,E], invalid_actions u8 [n,A] (NULL = none),
+ * dirichlet_noise f32 [n,A] (NULL = no root noise; ignored by gumbel). */
+int dogstep_mcts_init(const dogstep_mcts_tree* t, int64_t n, const dogstep_mcts_cfg* cfg, const uint32_t* keys,
+                      const float* root_prior_logits, const float* root_value, const float* root_embedding,
+                      const uint8_t* invalid_actions, const float* dirichlet_noise, void* stream);
+/* simulate(): descend from the root to (parent, action) for simulation `sim`; gathers the parent's embedding.
+ * parent_out i32 [n], action_out i32 [n], embedding_out f32 [n,E], is_decision_out u8 [n] (may be NULL). */
+int dogstep_mcts_select(const dogstep_mcts_tree* t, int64_t n, const dogstep_mcts_cfg* cfg, int32_t sim, int32_t* parent_out,
+                        int32_t* action_out, float* embedding_out, uint8_t* is_decision_out, void* stream);
+/* expand() + backward() with the caller's recurrent_fn outputs for the (parent, action) pairs of `sim`:
+ * prior_logits f32 [n,A], value/reward/discount f32 [n], embedding f32 [n,E].
+ * Stochastic: the same five arrays are the chance_recurrent_fn outputs (action_logits, value, reward, discount,
+ * state embedding) and chance_logits f32 [n,C], afterstate_value f32 [n], afterstate_embedding f32 [n,E] are the
+ * decision_recurrent_fn outputs; the kernel picks per game by the parent's node type like mctx's where(). */
+int dogstep_mcts_expand(const dogstep_mcts_tree* t, int64_t n, const dogstep_mcts_cfg* cfg, int32_t sim, const int32_t* parent,
+                        const int32_t* action, const float* prior_logits, const float* value, const float* reward,
+                        const float* discount, const float* embedding, const float* chance_logits,
+                        const float* afterstate_value, const float* afterstate_embedding, void* stream);
+/* policy epilogue: action i32 [n], action_weights f32 [n,A], root_value f32 [n] (= search_tree.summary().value) */
+int dogstep_mcts_policy_output(const dogstep_mcts_tree* t, int64_t n, const dogstep_mcts_cfg* cfg, int32_t* action,
+                               float* action_weights, float* root_value, void* stream);
+
 /* ---------------------------------------------------------------- jax.random on device
  * Stand-ins for the jax.random calls the self-play drivers make around the env functions
  * (game_agent.py:60,187-188).  keys are raw uint32[2]. */

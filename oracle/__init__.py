@@ -368,3 +368,81 @@ def dog_play_random(s, rng_key, max_steps=2000, game_offset=0, float_gumbel=Fals
                                      C.c_int(max_steps), C.c_int(int(float_gumbel)), C.c_int(nthreads), _p(game_len),
                                      C.byref(total)) == 0
     return game_len, int(total.value), key
+
+
+# --------------------------------------------------------------------------- MCTS (mctx restatement)
+class MctsCfg(C.Structure):
+    _fields_ = [("policy", C.c_int32), ("qtransform", C.c_int32), ("num_simulations", C.c_int32), ("max_depth", C.c_int32),
+                ("num_actions", C.c_int32), ("num_chance", C.c_int32), ("embed_dim", C.c_int32),
+                ("max_num_considered_actions", C.c_int32), ("q_min", C.c_float), ("q_max", C.c_float),
+                ("value_scale", C.c_float), ("maxvisit_init", C.c_float), ("epsilon", C.c_float), ("pb_c_init", C.c_float),
+                ("pb_c_base", C.c_float), ("dirichlet_fraction", C.c_float), ("temperature", C.c_float),
+                ("gumbel_scale", C.c_float)]
+
+
+_MCTS_FIELDS = (("node_visits", np.int32, "N"), ("raw_values", np.float32, "N"), ("node_values", np.float32, "N"),
+                ("parents", np.int32, "N"), ("action_from_parent", np.int32, "N"), ("children_index", np.int32, "NA"),
+                ("children_prior_logits", np.float32, "NA"), ("children_visits", np.int32, "NA"),
+                ("children_rewards", np.float32, "NA"), ("children_discounts", np.float32, "NA"),
+                ("children_values", np.float32, "NA"), ("embeddings", np.float32, "NE"), ("is_decision", np.uint8, "N"),
+                ("root_invalid_actions", np.uint8, "A"), ("root_gumbel", np.float32, "A"), ("search_key", np.uint32, "2"),
+                ("policy_key", np.uint32, "2"))
+
+
+class _MctsTreeC(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k, _, _ in _MCTS_FIELDS]
+
+
+class MctsTree:
+    def __init__(self, cfg, n):
+        N, A, E = cfg.num_simulations + 1, cfg.num_actions + cfg.num_chance, cfg.embed_dim
+        shp = {"N": (n, N), "NA": (n, N, A), "NE": (n, N, E), "A": (n, A), "2": (n, 2)}
+        for k, dt, s in _MCTS_FIELDS:
+            setattr(self, k, np.zeros(shp[s], dt))
+        self.cfg, self.n = cfg, n
+
+    def c(self):
+        return _MctsTreeC(*[_p(getattr(self, k)) for k, _, _ in _MCTS_FIELDS])
+
+
+def mcts_init(tree, keys, root_prior, root_value, root_emb, invalid=None, noise=None):
+    t = tree.c()
+    keys, root_prior = _c(keys, np.uint32), _c(root_prior, np.float32)
+    root_value, root_emb = _c(root_value, np.float32), _c(root_emb, np.float32)
+    invalid = None if invalid is None else _c(invalid, np.uint8)
+    noise = None if noise is None else _c(noise, np.float32)
+    assert lib().orc_mcts_init(C.byref(t), C.c_int64(tree.n), C.byref(tree.cfg), _p(keys), _p(root_prior), _p(root_value),
+                               _p(root_emb), _p(invalid), _p(noise)) == 0
+
+
+def mcts_select(tree, sim):
+    t = tree.c()
+    parent = np.empty(tree.n, np.int32)
+    action = np.empty(tree.n, np.int32)
+    emb = np.empty((tree.n, tree.cfg.embed_dim), np.float32)
+    isdec = np.empty(tree.n, np.uint8)
+    assert lib().orc_mcts_select(C.byref(t), C.c_int64(tree.n), C.byref(tree.cfg), C.c_int32(sim), _p(parent), _p(action),
+                                 _p(emb), _p(isdec)) == 0
+    return parent, action, emb, isdec
+
+
+def mcts_expand(tree, sim, parent, action, prior, value, reward, discount, emb, chance_logits=None, after_value=None, after_emb=None):
+    t = tree.c()
+    f = lambda x: None if x is None else _c(x, np.float32)
+    args = [f(prior), f(value), f(reward), f(discount), f(emb), f(chance_logits), f(after_value), f(after_emb)]
+    parent, action = _c(parent, np.int32), _c(action, np.int32)
+    assert lib().orc_mcts_expand(C.byref(t), C.c_int64(tree.n), C.byref(tree.cfg), C.c_int32(sim), _p(parent), _p(action),
+                                 *[_p(a) for a in args]) == 0
+
+
+def mcts_policy_output(tree):
+    t = tree.c()
+    action = np.empty(tree.n, np.int32)
+    weights = np.empty((tree.n, tree.cfg.num_actions), np.float32)
+    value = np.empty(tree.n, np.float32)
+    assert lib().orc_mcts_policy_output(C.byref(t), C.c_int64(tree.n), C.byref(tree.cfg), _p(action), _p(weights), _p(value)) == 0
+    return action, weights, value
+
+
+def considered_visit(m, S, i):
+    return int(lib().orc_considered_visit(C.c_int(m), C.c_int(S), C.c_int(i)))

@@ -1,0 +1,154 @@
+"""MCTS parity proper: the CUDA tree kernels (through the C-ABI) versus the CPU oracle, simulation by simulation, fed
+IDENTICAL network outputs (computed once on the GPU by a small torch stand-in for the Flax networks).  Visit counts and
+every tree array must match exactly (floats bit-for-bit, which is tighter than the 1e-5 relative bar of BASELINE)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TREE_FIELDS = ("node_visits", "raw_values", "node_values", "parents", "action_from_parent", "children_index",
+               "children_prior_logits", "children_visits", "children_rewards", "children_discounts", "children_values",
+               "embeddings", "root_invalid_actions", "search_key", "policy_key")
+
+
+def _mk_cfgs(policy, qt, S, depth, A, Cn, E, **kw):
+    from exploring_muzero_on_dog_b200 import _lib
+    d = dict(policy=policy, qtransform=qt, num_simulations=S, max_depth=depth, num_actions=A, num_chance=Cn, embed_dim=E,
+             max_num_considered_actions=16, q_min=-1.0, q_max=1.0, value_scale=0.5, maxvisit_init=50.0, epsilon=1e-8,
+             pb_c_init=1.25, pb_c_base=19652.0, dirichlet_fraction=0.25, temperature=1.0, gumbel_scale=1.0)
+    d.update(kw)
+    return _lib.MctsCfg(**d), O.MctsCfg(**d)
+
+
+class Net:
+    """deterministic stand-in for dynamics+prediction: emb' = tanh(W[a] emb), heads are linear maps of emb'"""
+
+    def __init__(self, A, Cn, E, seed):
+        g = torch.Generator(device="cuda").manual_seed(seed)
+        self.W = torch.randn(A + Cn, E, E, device="cuda", generator=g) * 0.7
+        self.P = torch.randn(E, A, device="cuda", generator=g)
+        self.Pc = torch.randn(E, max(Cn, 1), device="cuda", generator=g)
+
+    def __call__(self, action, emb):
+        nxt = torch.tanh(torch.einsum("nij,nj->ni", self.W[action], emb))
+        return dict(prior=nxt @ self.P, value=torch.tanh(nxt.sum(1)), reward=0.1 * nxt[:, 0],
+                    discount=torch.where(nxt[:, 1] > 0, 1.0, -1.0), emb=nxt, chance=nxt @ self.Pc)
+
+
+def _compare_trees(search, otree, what):
+    t = search.tree
+    for k in TREE_FIELDS + (("is_decision",) if t.is_decision is not None else ()) + (("root_gumbel",) if t.root_gumbel is not None else ()):
+        got = getattr(t, k).cpu().numpy()
+        exp = getattr(otree, k)
+        if got.dtype == np.float32:
+            same = (got.view(np.int32) == exp.view(np.int32)) | (np.isnan(got) & np.isnan(exp))
+        else:
+            same = got == exp
+        if not same.all():
+            idx = np.argwhere(~same)[0]
+            raise AssertionError(f"{what}: tree.{k}{tuple(idx)}: cuda {got[tuple(idx)]!r} oracle {exp[tuple(idx)]!r}")
+
+
+CASES = [
+    # (policy, qtransform, A, C, sims, depth)      the reference's four search configurations + DOG-sized trees
+    (0, 0, 9, 0, 50, 9),       # TicTacToe run_mcts: muzero_policy, by_min_max(-1,1), max_depth 9       (TicTacToe/mcts.py:13-22)
+    (1, 0, 9, 0, 50, 9),       # TicTacToe run_gumbel                                                   (TicTacToe/mcts.py:29-37)
+    (1, 2, 24, 0, 100, 50),    # det MADN run_muzero_mcts: gumbel, completed_by_mix_value(0.5)          (muzero_deterministic_madn.py:673-684)
+    (2, 1, 4, 6, 64, 50),      # classic MADN run_stochastic_muzero_mcts: by_parent_and_siblings        (muzero_classic_madn.py:488-501)
+    (0, 1, 24, 0, 40, 5),      # muzero_policy, depth cut revisits
+    (1, 2, 806, 0, 100, 50),   # DOG-wide action space (config 5)
+    (0, 2, 806, 0, 30, 8),
+]
+
+
+@pytest.mark.parametrize("policy,qt,A,Cn,S,depth", CASES)
+def test_cuda_search_equals_oracle(policy, qt, A, Cn, S, depth):
+    from exploring_muzero_on_dog_b200 import mcts
+    n, E = 96, 16
+    ccfg, ocfg = _mk_cfgs(policy, qt, S, depth, A, Cn, E)
+    rng = np.random.default_rng(1000 * policy + A)
+    keys = rng.integers(0, 2**32, (n, 2), dtype=np.uint64).astype(np.uint32)
+    prior = rng.standard_normal((n, A)).astype(np.float32) * 2
+    value = rng.uniform(-1, 1, n).astype(np.float32)
+    emb = rng.standard_normal((n, E)).astype(np.float32)
+    invalid = (rng.random((n, A)) < 0.4).astype(np.uint8)
+    invalid[np.arange(n), rng.integers(0, A, n)] = 0
+    invalid[:4] = 0
+    noise = rng.dirichlet(np.full(A, 0.3), n).astype(np.float32)
+    net = Net(A, Cn, E, 7)
+
+    s = mcts.Search(ccfg, n)
+    dev = lambda x: torch.as_tensor(x, device="cuda")
+    keys_t = torch.from_numpy(keys).cuda()
+    s.init(keys_t, mcts.RootFnOutput(dev(prior), dev(value), dev(emb)), dev(invalid), dev(noise))
+    otree = O.MctsTree(ocfg, n)
+    O.mcts_init(otree, keys, prior, value, emb, invalid, noise)
+    _compare_trees(s, otree, "init")
+    for sim in range(S):
+        parent, action, pemb, isdec = s.select(sim)
+        op, oa, oemb, oisdec = O.mcts_select(otree, sim)
+        assert np.array_equal(parent.cpu().numpy(), op), f"parent differs at sim {sim}"
+        assert np.array_equal(action.cpu().numpy(), oa), f"action differs at sim {sim}: {np.argwhere(action.cpu().numpy() != oa)[:3].tolist()}"
+        assert np.array_equal(pemb.cpu().numpy(), oemb)
+        o = net(action.long().clamp(0, A + Cn - 1), pemb)
+        h = {k: v.float().contiguous().cpu().numpy() for k, v in o.items()}
+        if policy == 2:
+            s.expand(sim, o["prior"], o["value"], o["reward"], o["discount"], o["emb"], o["chance"], o["value"], o["emb"])
+            O.mcts_expand(otree, sim, op, oa, h["prior"], h["value"], h["reward"], h["discount"], h["emb"], h["chance"], h["value"], h["emb"])
+        else:
+            s.expand(sim, o["prior"], o["value"], o["reward"], o["discount"], o["emb"])
+            O.mcts_expand(otree, sim, op, oa, h["prior"], h["value"], h["reward"], h["discount"], h["emb"])
+    _compare_trees(s, otree, "after search")
+    out, root_value = s.policy_output()
+    oact, ow, ov = O.mcts_policy_output(otree)
+    assert np.array_equal(out.action.cpu().numpy(), oact)
+    assert np.array_equal(out.action_weights.cpu().numpy().view(np.int32), ow.view(np.int32))
+    assert np.array_equal(root_value.cpu().numpy().view(np.int32), ov.view(np.int32))
+    vc = s.tree.children_visits[:, 0].cpu().numpy()
+    assert (vc.sum(1) == S).all() and (vc[:, :A][invalid.astype(bool)] == 0).all()
+
+
+def test_mctx_shaped_policies_run():
+    """the drop-in wrappers (same names / kwargs as mctx) on a torch recurrent_fn"""
+    import functools
+    from exploring_muzero_on_dog_b200 import mcts
+    n, A, E = 64, 24, 32
+    net = Net(A, 6, E, 3)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    root = mcts.RootFnOutput(torch.randn(n, A, device="cuda", generator=g), torch.rand(n, device="cuda", generator=g) * 2 - 1,
+                             torch.randn(n, E, device="cuda", generator=g))
+    keys = torch.randint(0, 2**31, (n, 2), device="cuda", generator=g).to(torch.uint32)
+    invalid = torch.rand(n, A, device="cuda", generator=g) < 0.5
+    invalid[:, 0] = False
+
+    def recurrent_fn(params, rng_key, action, embedding):
+        o = net(action, embedding)
+        return mcts.RecurrentFnOutput(o["reward"], o["discount"], o["prior"], o["value"]), o["emb"]
+
+    out = mcts.gumbel_muzero_policy(None, keys, root, recurrent_fn, 50, invalid_actions=invalid, max_depth=25,
+                                    qtransform=functools.partial(mcts.qtransform_completed_by_mix_value, value_scale=0.5), gumbel_scale=1.0)
+    assert out.action.shape == (n,) and not invalid[torch.arange(n), out.action.long()].any()
+    assert torch.allclose(out.action_weights.sum(1), torch.ones(n, device="cuda"), atol=1e-5)
+    assert (out.search_tree.summary().visit_counts.sum(1) == 50).all()
+    out = mcts.muzero_policy(None, keys, root, recurrent_fn, 30, invalid_actions=invalid, max_depth=9,
+                             qtransform=functools.partial(mcts.qtransform_by_min_max, min_value=-1, max_value=1), dirichlet_fraction=0.0)
+    assert (out.search_tree.summary().visit_counts.sum(1) == 30).all()
+
+    root4 = mcts.RootFnOutput(root.prior_logits[:, :4].contiguous(), root.value, root.embedding)
+    net4 = Net(4, 6, E, 5)
+
+    def dec(params, rng_key, action, embedding):
+        o = net4(action, embedding)
+        return mcts.DecisionRecurrentFnOutput(o["chance"], o["value"]), torch.cat([o["emb"], o["reward"][:, None], o["discount"][:, None]], 1)
+
+    def ch(params, rng_key, outcome, afterstate):
+        o = net4(outcome + 4, afterstate[:, :-2])
+        return mcts.ChanceRecurrentFnOutput(o["prior"], o["value"], afterstate[:, -2], afterstate[:, -1]), o["emb"]
+
+    out = mcts.stochastic_muzero_policy(None, keys, root4, dec, ch, 64, invalid_actions=invalid[:, :4].contiguous(), max_depth=50,
+                                        qtransform=mcts.qtransform_by_parent_and_siblings, temperature=1.0)
+    assert (out.search_tree.summary().visit_counts.sum(1) == 64).all()
+    assert out.search_tree.children_visits.shape[-1] == 10
