@@ -94,3 +94,15 @@ MCTS_TREE_FIELDS = ("node_visits", "raw_values", "node_values", "parents", "acti
 
 class MctsTree(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in MCTS_TREE_FIELDS]
+
+
+class ReplayArrays(C.Structure):
+    _fields_ = [("capacity", C.c_int32), ("max_episode_length", C.c_int32), ("obs_size", C.c_int32), ("action_dim", C.c_int32),
+                ("obs_is_int8", C.c_int32), ("stochastic", C.c_int32)] + \
+               [(k, C.c_void_p) for k in ("observations", "actions", "rewards", "root_values", "child_visits", "masks", "players",
+                                          "teams", "discounts", "episode_lengths", "dice_outcomes", "dice_distributions")]
+
+
+class ReplayBatch(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("observations", "actions", "rewards", "policies", "values", "masks", "target_values",
+                                          "discount_targets", "dice_outcomes", "dice_probs")]

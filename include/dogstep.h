@@ -257,6 +257,60 @@ int dogstep_mcts_expand(const dogstep_mcts_tree* t, int64_t n, const dogstep_mct
 int dogstep_mcts_policy_output(const dogstep_mcts_tree* t, int64_t n, const dogstep_mcts_cfg* cfg, int32_t* action,
                                float* action_weights, float* root_value, void* stream);
 
+/* ---------------------------------------------------------------- replay ring buffer (per-GPU shard)
+ * Stand-in for VectorizedReplayBuffer (MuZero_det_MADN/vec_replay_buffer.py:9-264) and
+ * VectorizedReplayBufferStochastic (MuZero_Classic_MADN/vec_replay_buffer_stochastic.py), whose arrays live in host
+ * NumPy in the reference; here they live in HBM next to the trajectory buffers self-play writes. */
+typedef struct {
+  int32_t capacity, max_episode_length, obs_size, action_dim;
+  int32_t obs_is_int8;   /* 0: observations float32 (reference dtype), 1: int8 (4x smaller, same values) */
+  int32_t stochastic;    /* 1: dice_outcomes / dice_distributions present, game_won = final_reward > 0 */
+  void* observations;        /* [capacity, T, obs_size] */
+  int32_t* actions;          /* [capacity, T] */
+  int32_t* rewards;          /* [capacity, T]   class index 0/1/2 */
+  float* root_values;        /* [capacity, T] */
+  float* child_visits;       /* [capacity, T, action_dim] */
+  float* masks;              /* [capacity, T] */
+  int32_t* players;          /* [capacity, T] */
+  int32_t* teams;            /* [capacity, T] */
+  int32_t* discounts;        /* [capacity, T]   class index 0/1/2 */
+  int32_t* episode_lengths;  /* [capacity] */
+  int32_t* dice_outcomes;    /* [capacity, T]    stochastic only */
+  float* dice_distributions; /* [capacity, T, 6] stochastic only */
+} dogstep_replay_arrays;
+
+/* save_games_from_buffers (:36-61): trajectories `traj` (same struct, capacity = number of games, episode_lengths = the
+ * 'idx' leaf) are copied to ring slots slot[i] (device int32 [n_games], -1 = skip: length 0); only the first
+ * length rows of a slot are overwritten, as in the reference.  The slot order is host logic (position/size). */
+int dogstep_replay_save(const dogstep_replay_arrays* buf, const dogstep_replay_arrays* traj, int64_t n_games,
+                        const int32_t* slot, void* stream);
+
+/* The random part of sample_batch (:73-97): 75 % uniform (episode, t), 25 % windows aligned so that the episode's last
+ * step falls at a random unroll position.  Drawn with threefry from host_key (the reference uses unseeded np.random,
+ * so only the distribution is defined).  Outputs int32 [batch_size] each. */
+int dogstep_replay_plan(const dogstep_replay_arrays* buf, int32_t size, int32_t batch_size, int32_t unroll_steps,
+                        float terminal_ratio, const uint32_t* host_key, int32_t* ep_indices, int32_t* t_starts, void* stream);
+
+typedef struct {
+  float* observations;       /* [B, obs_size] */
+  int32_t* actions;          /* [B, K-1] */
+  int32_t* rewards;          /* [B, K-1] */
+  float* policies;           /* [B, K, action_dim] */
+  float* values;             /* [B, K] */
+  float* masks;              /* [B, K] */
+  float* target_values;      /* [B, K] */
+  int32_t* discount_targets; /* [B, K-1] */
+  int32_t* dice_outcomes;    /* [B, K-1]    stochastic only */
+  float* dice_probs;         /* [B, K-1, 6] stochastic only */
+} dogstep_replay_batch;
+
+/* The deterministic part of sample_batch (:104-264): K = unroll_steps+1 window gathers, z / n-step bootstrap value
+ * targets with the team / player perspective flip, clip, padding.  gamma_pow: device float64 [T+1] = GAMMA ** k
+ * (host-computed so the powers are the reference's own libm values); arithmetic in float64, rounded to float32 once. */
+int dogstep_replay_gather(const dogstep_replay_arrays* buf, int32_t batch_size, int32_t unroll_steps, int32_t td_steps,
+                          int32_t bootstrap_value_target, const double* gamma_pow, const int32_t* ep_indices,
+                          const int32_t* t_starts, const dogstep_replay_batch* out, void* stream);
+
 /* ---------------------------------------------------------------- jax.random on device
  * Stand-ins for the jax.random calls the self-play drivers make around the env functions
  * (game_agent.py:60,187-188).  keys are raw uint32[2]. */
