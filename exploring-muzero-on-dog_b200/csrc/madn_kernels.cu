@@ -416,9 +416,10 @@ __global__ void __launch_bounds__(kThreads) k_madn_det_play_random(const __grid_
 }
 
 __global__ void __launch_bounds__(kThreads) k_madn_cls_throw_die(const __grid_constant__ MadnGeom g, MadnPtrs p, int64_t n,
-                                                                 float* __restrict__ probs, int write_die) {
+                                                                 float* __restrict__ probs, int write_die, int only_active) {
   int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   if (i >= n) return;
+  if (only_active && p.done[i] != 0) return;
   MadnRegs s;
   load_state<false>(g, p, i, s);
   // dice_probabilities (classic_madn.py:14-18,208-228): float32 literals rounded from doubles
@@ -445,6 +446,97 @@ __global__ void __launch_bounds__(kThreads) k_madn_cls_throw_die(const __grid_co
     p.key[2 * i] = knew.a;
     p.key[2 * i + 1] = knew.b;
   }
+}
+
+// ---- self-play bookkeeping: one lockstep iteration of play_batch_of_games_jitted after the search ---------------------
+// MuZero_det_MADN/game_agent.py:64-148 (do_active_step) and MuZero_Classic_MADN/game_agent_stochastic.py:86-204.
+// One warp per game: lane 0 applies env_step / no_step and the targets, all lanes copy the observation / policy rows.
+template <bool DET>
+__global__ void __launch_bounds__(kThreads) k_madn_agent_step(const __grid_constant__ MadnGeom g, MadnPtrs p, int64_t n,
+                                                              const int32_t* __restrict__ action, const float* __restrict__ root_value,
+                                                              const float* __restrict__ weights, const int8_t* __restrict__ obs,
+                                                              dogstep_replay_arrays tr) {
+  __shared__ int sh_row[kThreads / 32][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t i = (int64_t)blockIdx.x * (kThreads / 32) + warp;
+  if (i >= n) return;
+  if (p.done[i] != 0) return;  // do_skip_step: finished games are left untouched
+  const int A = DET ? 24 : 4;
+  int* row = sh_row[warp];
+  if (lane == 0) {
+    MadnRegs s;
+    load_state<DET>(g, p, i, s);
+    const uint32_t m = DET ? madn_det_valid_mask(g, s) : madn_cls_valid_mask(g, s);
+    const int teams = DS_RULE(g, DOGSTEP_RULE_TEAMS);
+    const int pid = s.cur;
+    const int team_before = teams ? floormod(pid, 2) : -1;
+    const int idx = tr.episode_lengths[i];
+    const int dice = s.die;
+    int has_valid = m != 0u, act = -1, rew_t = 1, disc_t = 1;
+    if (has_valid) {
+      act = action[i];
+      if (DET) madn_det_step(g, s, act / 6, act % 6 + 1, m);  // map_action
+      else madn_cls_step(g, s, act, m);
+      const int next_team = teams ? floormod(s.cur, 2) : -1;
+      rew_t = (s.done && s.reward > 0) ? 2 : ((s.done && s.reward < 0) ? 0 : 1);
+      disc_t = s.done ? 1 : (teams ? (team_before == next_team ? 2 : 0) : (pid == s.cur ? 2 : 0));
+      if (DET) store_aset(g, p.aset, i, s);
+      store_board(g, p.board, i, s);
+      store_pins(g, p.pins, i, s);
+      p.reward[i] = (int8_t)s.reward;
+      p.done[i] = (uint8_t)s.done;
+    } else {
+      if (DET) { madn_det_no_step(g, s); store_aset(g, p.aset, i, s); }
+      else s.cur = (int)(int8_t)floormod(s.cur + 1, g.n);
+    }
+    p.cur[i] = (int8_t)s.cur;
+    if (idx >= 0 && idx < tr.max_episode_length) {  // .at[idx].set drops out-of-range rows
+      const int64_t r = i * tr.max_episode_length + idx;
+      tr.actions[r] = act;
+      tr.rewards[r] = rew_t;
+      tr.root_values[r] = has_valid ? root_value[i] : 0.0f;
+      tr.masks[r] = has_valid ? 1.0f : 0.0f;
+      tr.players[r] = pid;
+      tr.teams[r] = team_before;
+      tr.discounts[r] = disc_t;
+      if (!DET) {
+        tr.dice_outcomes[r] = dice;
+        // dice_probabilities(next_env) (game_agent_stochastic.py:160)
+        const int locked = madn_soft_locked(g, s) && DS_RULE(g, DOGSTEP_RULE_DICE_RETHROW);
+        float pr[6];
+        if (locked && DS_RULE(g, DOGSTEP_RULE_START_ON_1)) { pr[0] = pr[5] = (float)(76.0 / 216); pr[1] = pr[2] = pr[3] = pr[4] = (float)(16.0 / 216); }
+        else if (locked) { pr[0] = pr[1] = pr[2] = pr[3] = pr[4] = (float)(25.0 / 216); pr[5] = (float)(91.0 / 216); }
+        else { for (int k = 0; k < 6; ++k) pr[k] = (float)(1.0 / 6); }
+        for (int k = 0; k < 6; ++k) tr.dice_distributions[r * 6 + k] = pr[k];
+      }
+    }
+    tr.episode_lengths[i] = idx + 1;
+    row[0] = idx;
+    row[1] = has_valid;
+  }
+  __syncwarp();
+  const int idx = row[0], has_valid = row[1];
+  if (idx < 0 || idx >= tr.max_episode_length) return;
+  const int64_t r = i * tr.max_episode_length + idx;
+  for (int k = lane; k < A; k += 32) tr.child_visits[r * A + k] = has_valid ? weights[i * A + k] : 0.0f;
+  const int8_t* src = obs + i * tr.obs_size;
+  if (tr.obs_is_int8) {
+    int8_t* d = (int8_t*)tr.observations + r * tr.obs_size;
+    for (int k = lane; k < tr.obs_size; k += 32) d[k] = has_valid ? src[k] : (int8_t)0;
+  } else {
+    float* d = (float*)tr.observations + r * tr.obs_size;
+    for (int k = lane; k < tr.obs_size; k += 32) d[k] = has_valid ? (float)src[k] : 0.0f;
+  }
+}
+
+// keys[i] -> split(keys[i], m)[index] for every game (game_agent.py:80 hands step_keys[i] to run_muzero_mcts, which
+// keeps split(key)[1], muzero_deterministic_madn.py:665)
+__global__ void k_random_split_each(const uint32_t* __restrict__ keys, int64_t n, uint32_t index, uint32_t* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Key2 k = split_i(Key2{keys[2 * i], keys[2 * i + 1]}, index);
+  out[2 * i] = k.a;
+  out[2 * i + 1] = k.b;
 }
 
 // ---- jax.random helpers -------------------------------------------------------------------------
@@ -611,7 +703,7 @@ int dogstep_madn_det_play_random(const dogstep_madn_det_state* s, int64_t n, con
 int dogstep_madn_cls_throw_die(const dogstep_madn_cls_state* s, int64_t n, const dogstep_madn_cfg* cfg, void* stream) {
   DS_PROLOGUE(cls_ptrs)
   if (!p.key) return DOGSTEP_ERR_INVALID_ARG;
-  k_madn_cls_throw_die<<<blocks_for(n, kThreads), kThreads, 0, st>>>(g, p, n, nullptr, 1);
+  k_madn_cls_throw_die<<<blocks_for(n, kThreads), kThreads, 0, st>>>(g, p, n, nullptr, 1, 0);
   return check_launch();
 }
 
@@ -619,7 +711,7 @@ int dogstep_madn_cls_dice_probabilities(const dogstep_madn_cls_state* s, int64_t
                                         void* stream) {
   DS_PROLOGUE(cls_ptrs)
   if (!probs) return DOGSTEP_ERR_INVALID_ARG;
-  k_madn_cls_throw_die<<<blocks_for(n, kThreads), kThreads, 0, st>>>(g, p, n, probs, 0);
+  k_madn_cls_throw_die<<<blocks_for(n, kThreads), kThreads, 0, st>>>(g, p, n, probs, 0, 0);
   return check_launch();
 }
 
@@ -645,6 +737,50 @@ int dogstep_random_bits(const uint32_t* host_key, int64_t n, uint32_t* out, void
   if (!host_key || !out || n < 0) return DOGSTEP_ERR_INVALID_ARG;
   if (n == 0) return DOGSTEP_OK;
   k_random_bits<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(Key2{host_key[0], host_key[1]}, n, out);
+  return check_launch();
+}
+
+int dogstep_madn_cls_throw_die_active(const dogstep_madn_cls_state* s, int64_t n, const dogstep_madn_cfg* cfg, void* stream) {
+  DS_PROLOGUE(cls_ptrs)
+  if (!p.key) return DOGSTEP_ERR_INVALID_ARG;
+  k_madn_cls_throw_die<<<blocks_for(n, kThreads), kThreads, 0, st>>>(g, p, n, nullptr, 1, 1);
+  return check_launch();
+}
+
+static int traj_check(const dogstep_replay_arrays* tr, int64_t n, int obs_size, int action_dim, int stochastic) {
+  if (!tr || tr->capacity < n || tr->obs_size != obs_size || tr->action_dim != action_dim || tr->stochastic != stochastic)
+    return DOGSTEP_ERR_INVALID_ARG;
+  if (!tr->observations || !tr->actions || !tr->rewards || !tr->root_values || !tr->child_visits || !tr->masks || !tr->players ||
+      !tr->teams || !tr->discounts || !tr->episode_lengths)
+    return DOGSTEP_ERR_INVALID_ARG;
+  if (stochastic && (!tr->dice_outcomes || !tr->dice_distributions)) return DOGSTEP_ERR_INVALID_ARG;
+  return DOGSTEP_OK;
+}
+
+int dogstep_madn_det_agent_step(const dogstep_madn_det_state* s, int64_t n, const dogstep_madn_cfg* cfg, const int32_t* action,
+                                const float* root_value, const float* action_weights, const int8_t* obs,
+                                const dogstep_replay_arrays* traj, void* stream) {
+  DS_PROLOGUE(det_ptrs)
+  if (!action || !root_value || !action_weights || !obs) return DOGSTEP_ERR_INVALID_ARG;
+  if (int rc = traj_check(traj, n, (8 * g.n + 2) * g.total, 24, 0)) return rc;
+  k_madn_agent_step<true><<<blocks_for(n, kThreads / 32), kThreads, 0, st>>>(g, p, n, action, root_value, action_weights, obs, *traj);
+  return check_launch();
+}
+
+int dogstep_madn_cls_agent_step(const dogstep_madn_cls_state* s, int64_t n, const dogstep_madn_cfg* cfg, const int32_t* action,
+                                const float* root_value, const float* action_weights, const int8_t* obs,
+                                const dogstep_replay_arrays* traj, void* stream) {
+  DS_PROLOGUE(cls_ptrs)
+  if (!action || !root_value || !action_weights || !obs) return DOGSTEP_ERR_INVALID_ARG;
+  if (int rc = traj_check(traj, n, (2 * g.n + 3) * g.total, 4, 1)) return rc;
+  k_madn_agent_step<false><<<blocks_for(n, kThreads / 32), kThreads, 0, st>>>(g, p, n, action, root_value, action_weights, obs, *traj);
+  return check_launch();
+}
+
+int dogstep_random_split_each(const uint32_t* keys, int64_t n, uint32_t index, uint32_t* out, void* stream) {
+  if (!keys || !out || n < 0) return DOGSTEP_ERR_INVALID_ARG;
+  if (n == 0) return DOGSTEP_OK;
+  k_random_split_each<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(keys, n, index, out);
   return check_launch();
 }
 

@@ -311,6 +311,21 @@ int dogstep_replay_gather(const dogstep_replay_arrays* buf, int32_t batch_size, 
                           int32_t bootstrap_value_target, const double* gamma_pow, const int32_t* ep_indices,
                           const int32_t* t_starts, const dogstep_replay_batch* out, void* stream);
 
+/* ---------------------------------------------------------------- self-play bookkeeping
+ * One lockstep iteration of play_batch_of_games_jitted AFTER the search (MuZero_det_MADN/game_agent.py:64-148,
+ * MuZero_Classic_MADN/game_agent_stochastic.py:86-204): for every game that is not done, env_step(map_action(action)) if a
+ * legal action exists else no_step, reward / discount class targets, and the trajectory row at traj.episode_lengths[g]
+ * ('idx'): obs, act, rew, val, pol, mask, player, team, discount (+ dice, dice_dist).  `traj` uses the replay struct with
+ * capacity = n and max_episode_length = max_steps.  obs: int8 [n, C, total] = encode_board(env) taken BEFORE the step. */
+int dogstep_madn_det_agent_step(const dogstep_madn_det_state* s, int64_t n, const dogstep_madn_cfg* cfg, const int32_t* action,
+                                const float* root_value, const float* action_weights, const int8_t* obs,
+                                const dogstep_replay_arrays* traj, void* stream);
+int dogstep_madn_cls_agent_step(const dogstep_madn_cls_state* s, int64_t n, const dogstep_madn_cfg* cfg, const int32_t* action,
+                                const float* root_value, const float* action_weights, const int8_t* obs,
+                                const dogstep_replay_arrays* traj, void* stream);
+/* throw_die for the games that are not done (game_agent_stochastic.py:90 runs inside do_active_step) */
+int dogstep_madn_cls_throw_die_active(const dogstep_madn_cls_state* s, int64_t n, const dogstep_madn_cfg* cfg, void* stream);
+
 /* ---------------------------------------------------------------- jax.random on device
  * Stand-ins for the jax.random calls the self-play drivers make around the env functions
  * (game_agent.py:60,187-188).  keys are raw uint32[2]. */
@@ -320,6 +335,8 @@ int dogstep_random_split(const uint32_t* host_key, int64_t n, uint32_t* out, voi
 int dogstep_random_randint(const uint32_t* host_key, int64_t n, int32_t lo, int32_t hi, int32_t* out, void* stream);
 /* jax.random.uniform(key, (n,), float32, lo, hi) */
 int dogstep_random_uniform(const uint32_t* host_key, int64_t n, float lo, float hi, float* out, void* stream);
+/* out[i] = jax.random.split(keys[i], m)[index] for every i: keys, out uint32 [n,2] on the device */
+int dogstep_random_split_each(const uint32_t* keys, int64_t n, uint32_t index, uint32_t* out, void* stream);
 /* jax.random.bits(key, (n,), uint32) */
 int dogstep_random_bits(const uint32_t* host_key, int64_t n, uint32_t* out, void* stream);
 

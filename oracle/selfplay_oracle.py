@@ -1,0 +1,78 @@
+"""selfplay_oracle.py — TEST INFRASTRUCTURE ONLY.
+
+NumPy restatement of the bookkeeping of play_batch_of_games_jitted (MuZero_det_MADN/game_agent.py:50-183 and
+MuZero_Classic_MADN/game_agent_stochastic.py:52-218) on top of the C env oracle: per lockstep iteration and live game,
+encode / mask / (search result supplied by the caller) / env_step or no_step / reward+discount class targets / the
+trajectory row.  The search itself is an input (`search_fn`), exactly as in the CUDA mirror.
+
+PARITY STATUS: the env functions underneath are pinned (see madn_oracle.c); the loop bookkeeping itself is pinned by no
+reference test ("parity unpinned"), it is a line-by-line restatement of the cited lines.
+"""
+import numpy as np
+
+import oracle as O
+
+
+def play_batch_of_games(state, max_steps, rng_key, search_fn, teams):
+    """state: O.MadnState (det or classic).  search_fn(step_keys [n,2], obs, invalid [n,A]) -> (action, weights, value)."""
+    n, det = state.n, state.det
+    A = 24 if det else 4
+    C_, T = (8 * state.cfg.num_players + 2, state.cfg.total) if det else (2 * state.cfg.num_players + 3, state.cfg.total)
+    buf = dict(obs=np.zeros((n, max_steps, C_, T), np.float32), act=np.zeros((n, max_steps), np.int32),
+               rew=np.zeros((n, max_steps), np.int32), val=np.zeros((n, max_steps), np.float32), pol=np.zeros((n, max_steps, A), np.float32),
+               mask=np.zeros((n, max_steps), np.float32), player=np.zeros((n, max_steps), np.int32),
+               team=np.full((n, max_steps), -1, np.int32), discount=np.zeros((n, max_steps), np.int32), idx=np.zeros(n, np.int32))
+    if not det:
+        buf["dice"] = np.zeros((n, max_steps), np.int32)
+        buf["dice_dist"] = np.zeros((n, max_steps, 6), np.float32)
+    key = np.asarray(rng_key, np.uint32)
+    step = 0
+    while step < max_steps and not state.done.all():
+        keys = O.split(key, n + 1)
+        key, step_keys = keys[0], keys[1:]
+        live = state.done == 0
+        if not det:  # throw_die only inside do_active_step
+            thrown = state.copy()
+            O.madn_cls_throw_die(thrown)
+            state.die[live] = thrown.die[live]
+            state.key[live] = thrown.key[live]
+        obs = O.madn_det_encode_board(state) if det else O.madn_cls_encode_board(state)
+        valid = (O.madn_det_valid_action(state) if det else O.madn_cls_valid_action(state)).reshape(n, -1)
+        action, weights, value = search_fn(step_keys, obs, ~valid)
+        stepped, skipped = state.copy(), state.copy()
+        if det:
+            r, d = O.madn_det_step(stepped, np.stack([action // 6, action % 6 + 1], 1).astype(np.int8))
+            O.madn_det_no_step(skipped)
+        else:
+            r, d = O.madn_cls_step(stepped, action.astype(np.int8))
+            O.madn_cls_no_step(skipped)
+        if not det:
+            dist_step, dist_skip = O.madn_cls_dice_probabilities(stepped), O.madn_cls_dice_probabilities(skipped)
+        for g in range(n):
+            if not live[g]:
+                continue
+            i = buf["idx"][g]
+            has_valid = valid[g].any()
+            pid = int(state.current_player[g])
+            team = pid % 2 if teams else -1
+            src = stepped if has_valid else skipped
+            if has_valid:
+                nxt, nd, rw = int(stepped.current_player[g]), bool(d[g]), int(r[g])
+                rew_t = 2 if (nd and rw > 0) else (0 if (nd and rw < 0) else 1)
+                same = (team == nxt % 2) if teams else (pid == nxt)
+                disc_t = 1 if nd else (2 if same else 0)
+                row = (obs[g], int(action[g]), rew_t, value[g], weights[g], 1.0, disc_t)
+            else:
+                row = (np.zeros_like(obs[g]), -1, 1, 0.0, np.zeros(A, np.float32), 0.0, 1)
+            if i < max_steps:
+                buf["obs"][g, i], buf["act"][g, i], buf["rew"][g, i], buf["val"][g, i] = row[0], row[1], row[2], row[3]
+                buf["pol"][g, i], buf["mask"][g, i], buf["discount"][g, i] = row[4], row[5], row[6]
+                buf["player"][g, i], buf["team"][g, i] = pid, team
+                if not det:
+                    buf["dice"][g, i] = state.die[g]
+                    buf["dice_dist"][g, i] = (dist_step if has_valid else dist_skip)[g]
+            buf["idx"][g] = i + 1
+            for f, v in src.fields().items():
+                getattr(state, f)[g] = v[g]
+        step += 1
+    return buf
