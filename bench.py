@@ -86,6 +86,76 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.rows), "power_w_max": max(r[3] for r in self.rows)}
 
 
+
+def measure_extras(dev, key):
+    """Side measurements on one GPU, reported under "extras" (not the headline): BASELINE config 4 (DOG, 16,384 lockstep
+    games, random legal policy over 806 actions to termination) and config 3's tree work (stochastic MuZero search,
+    4,096 games x 64 simulations, A = 4 + 6) with a minimal stand-in network, so the number is the tree kernels' rate."""
+    import torch
+    from exploring_muzero_on_dog_b200 import jaxrand, mcts
+    from exploring_muzero_on_dog_b200.DOG import dog
+    peak, _ = _peaks()
+    out = {}
+    DOG_RULES = dict(enable_teams=True, enable_initial_free_pin=False, enable_circular_board=True, enable_friendly_fire=True,
+                     enable_start_blocking=True, enable_jump_in_goal_area=False, must_traverse_start=True)  # MuZero_DOG/game_agent.py:12-23
+    n = 16384
+    seeds = jaxrand.randint(key, n, 0, 1_000_000, device=dev)
+    total = torch.zeros(1, dtype=torch.int64, device=dev)
+    for rep in range(3):
+        env = dog.env_reset(0, seed=seeds, device=dev, **DOG_RULES)
+        total.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dog.play_random(env, key, max_steps=MAX_STEPS, total_steps=total)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    steps = int(total.item())
+    out["dog_cfg4"] = {"workload": "cfg4: DOG 2v2, 16,384 lockstep games, random legal policy (806 actions) to termination",
+                       "env_steps": steps, "kernel_ms": ms, "env_steps_per_s": steps / (ms / 1e3),
+                       "roofline": {"bound": "hbm", "kernel": "k_dog_play_random", "algorithmic_bytes_per_env_step": 1228,
+                                    "achieved": steps * 1228 / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                                    "frac": steps * 1228 / (ms / 1e3) / 1e9 / peak}}
+    # config 3 tree work
+    n, S, A, Cn, E = 4096, 64, 4, 6, 258
+    g = torch.Generator(device=dev).manual_seed(0)
+    Wd = torch.randn(E, E, device=dev, generator=g) * 0.05
+    Wp, Wc = torch.randn(E, A, device=dev, generator=g), torch.randn(E, Cn, device=dev, generator=g)
+
+    def dec(params, rng, action, emb):
+        e = torch.tanh(emb @ Wd)
+        return mcts.DecisionRecurrentFnOutput(e @ Wc, torch.tanh(e[:, 0])), e
+
+    def ch(params, rng, outcome, emb):
+        e = torch.tanh(emb @ Wd)
+        return mcts.ChanceRecurrentFnOutput(e @ Wp, torch.tanh(e[:, 0]), 0.1 * e[:, 1], torch.where(e[:, 2] > 0, 1.0, -1.0)), e
+
+    root = mcts.RootFnOutput(torch.randn(n, A, device=dev, generator=g), torch.zeros(n, device=dev), torch.randn(n, E, device=dev, generator=g))
+    keys = jaxrand.split(key, n, device=dev)
+    invalid = torch.zeros(n, A, dtype=torch.bool, device=dev)
+    for rep in range(2):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        po = mcts.stochastic_muzero_policy(None, keys, root, dec, ch, S, invalid_actions=invalid, max_depth=50, dirichlet_fraction=0.0)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    t = po.search_tree
+    depth = torch.zeros_like(t.parents)
+    for node in range(1, S + 1):  # nodes are created in order, so a parent's depth is known
+        par = t.parents[:, node].long().clamp(min=0)
+        depth[:, node] = torch.where(t.parents[:, node] >= 0, depth.gather(1, par[:, None])[:, 0] + 1, 0)
+    dbar = float(depth[:, 1:].float().mean().item())
+    bytes_per_sim = 2100 + 248 * dbar  # SURVEY.md 8(d) cfg 3
+    out["mcts_cfg3"] = {"workload": "cfg3 tree work: stochastic MuZero search, 4,096 games x 64 sims, A=4+6, E=258, stand-in network",
+                        "sims": n * S, "ms": ms, "sims_per_s": n * S / (ms / 1e3), "mean_expansion_depth": dbar,
+                        "roofline": {"bound": "hbm", "kernel": "k_mcts_select + k_mcts_expand", "algorithmic_bytes_per_sim": bytes_per_sim,
+                                     "achieved": n * S * bytes_per_sim / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                                     "frac": n * S * bytes_per_sim / (ms / 1e3) / 1e9 / peak,
+                                     "note": "wall time of the whole search incl. the stand-in network and 2 launches per simulation"}}
+    return out
+
+
 def cpu_baseline(games, nthreads, key, seeds_np):
     """the oracle port on the host cores: same workload, bounded sample of `games` games"""
     import oracle as O
@@ -137,6 +207,7 @@ def main():
     ap.add_argument("--games", type=int, default=65536, help="lockstep games per GPU")
     ap.add_argument("--impl", default="dogstep", choices=["dogstep", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the DOG (cfg 4) and MCTS (cfg 3) side measurements")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -237,6 +308,10 @@ def main():
     else:
         max_ms, e2e_max_ms, all_steps, all_e2e_steps = my_ms, e2e_ms, my_steps, e2e_steps
 
+    extras = None
+    if world == 1 and not args.no_extras:
+        extras = measure_extras(dev, key)
+
     if rank == 0:
         peak, peak_src = _peaks()
         play_s = sum(play_ms) / 1e3
@@ -264,6 +339,8 @@ def main():
                          "note": "algorithmic bytes of the per-step reference dataflow; the persistent kernel keeps a game in registers, so it is integer-ALU bound, not HBM bound"},
             "clocks": clk,
         }
+        if extras:
+            line["extras"] = extras
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             seeds_np = seeds.cpu().numpy()
