@@ -1,0 +1,236 @@
+// ttt_kernels.cu — TicTacToe / TicTacToeV2 envs and their true-env mctx callbacks (root_fn, recurrent_fn with a random
+// rollout to the end of the game) for BASELINE config 1.  One game per thread; a game is 18 bytes.
+// Restates TicTacToe/TicTacToe.py:19-117 (variant 0) and TicTacToe/TicTacToeV2.py:22-140 (variant 1, including the two
+// operator-precedence quirks of env_step :66 and :70).
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../include/dogstep.h"
+#include "common.cuh"
+#include "jaxrand.cuh"
+
+namespace dogstep {
+
+struct Ttt {
+  int8_t board[9];
+  int8_t cur, reward, done;
+  int8_t memory[6];
+};
+
+__device__ __forceinline__ float t_log(float x) { return (float)log((double)x); }
+__device__ __forceinline__ int t_floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+__device__ __forceinline__ int t_mod(int a, int b) { int r = a % b; return r < 0 ? r + b : r; }
+__device__ __forceinline__ int t_wrap(int i, int n) { i = i < 0 ? i + n : i; return min(max(i, 0), n - 1); }
+
+__device__ __forceinline__ int ttt_winner(const int8_t* b) {
+  int w = 0, neg = 0;
+#define TTT_LINE(a, c, d) { int s = b[a] + b[c] + b[d]; w |= (s == 3); neg |= (s == -3); }
+  TTT_LINE(0, 1, 2) TTT_LINE(3, 4, 5) TTT_LINE(6, 7, 8) TTT_LINE(0, 3, 6) TTT_LINE(1, 4, 7) TTT_LINE(2, 5, 8) TTT_LINE(0, 4, 8) TTT_LINE(2, 4, 6)
+#undef TTT_LINE
+  return neg ? -1 : w;
+}
+
+__device__ void ttt_step(int variant, Ttt& e, int action_in) {
+  const int action = (int)(int8_t)action_in;
+  const int cell = t_wrap(t_floordiv(action, 3), 3) * 3 + t_wrap(t_mod(action, 3), 3);
+  const int invalid = e.board[cell] != 0;
+  const int keep = e.done || invalid;
+  int8_t board[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) board[k] = e.board[k];
+  if (!keep) board[cell] = e.cur;
+  if (variant == 1) {
+    int8_t* m = e.memory + 3 * (e.cur < 0);
+    const int removed = m[0];
+    // ((done | invalid) | removed_action) == -1 in int8 arithmetic (TicTacToeV2.py:66)
+    const int keep_removed = (int8_t)((int8_t)keep | (int8_t)removed) == -1;
+    const int rc = t_wrap(t_floordiv(removed, 3), 3) * 3 + t_wrap(t_mod(removed, 3), 3);
+    if (!keep_removed) board[rc] = 0;
+    if (!keep) { m[0] = m[1]; m[1] = m[2]; m[2] = (int8_t)action; }
+  }
+  const int reward = e.done ? 0 : (invalid ? -1 : ttt_winner(board) * e.cur);
+  int full = 1;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) full &= board[k] != 0;
+  int done;
+  if (variant == 1) done = (int)(int8_t)((int8_t)e.done | (int8_t)reward) != (0 | invalid | full);  // (:70)
+  else done = e.done || reward != 0 || invalid || full;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) e.board[k] = board[k];
+  e.cur = (int8_t)(done ? e.cur : -e.cur);
+  e.done = (int8_t)done;
+  e.reward = (int8_t)reward;
+}
+
+__device__ void ttt_policy(int variant, const Ttt& e, float logits[9]) {
+  for (int a = 0; a < 9; ++a) {
+    float v = (!e.done && e.board[a] == 0) ? 100.0f : 0.0f;
+    for (int side = 0; side < 2; ++side) {
+      Ttt t = e;
+      t.cur = (int8_t)(side == 0 ? -e.cur : e.cur);
+      ttt_step(variant, t, a);
+      if (t.reward == 1) v = __fadd_rn(v, side == 0 ? 200.0f : 300.0f);
+    }
+    logits[a] = v;
+  }
+}
+
+__device__ float ttt_rollout(int variant, const Ttt& e0, Key2 key) {
+  Ttt e = e0;
+  for (int it = 0; it < 100000 && !e.done; ++it) {
+    const Key2 nk = split_i(key, 0), sub = split_i(key, 1);
+    key = nk;
+    float lg[9];
+    ttt_policy(variant, e, lg);
+    int best = 0;
+    float bv = 0.f;
+    for (int a = 0; a < 9; ++a) {
+      float u = uniform_i(sub, (uint32_t)a, 1.17549435e-38f, 1.0f);
+      float v = __fadd_rn(-t_log(-t_log(u)), lg[a]);
+      if (a == 0 || v > bv) { bv = v; best = a; }
+    }
+    ttt_step(variant, e, best);
+  }
+  return (float)(int8_t)(e.reward * e.cur * e0.cur);
+}
+
+struct TttPtrs { int8_t* board; int8_t* cur; int8_t* reward; uint8_t* done; int8_t* memory; };
+
+__device__ __forceinline__ void ttt_load(const TttPtrs& p, int64_t g, Ttt& e) {
+  for (int k = 0; k < 9; ++k) e.board[k] = p.board[9 * g + k];
+  e.cur = p.cur[g]; e.reward = p.reward[g]; e.done = p.done[g] != 0;
+  for (int k = 0; k < 6; ++k) e.memory[k] = p.memory[6 * g + k];
+}
+__device__ __forceinline__ void ttt_store(const TttPtrs& p, int64_t g, const Ttt& e) {
+  for (int k = 0; k < 9; ++k) p.board[9 * g + k] = e.board[k];
+  p.cur[g] = e.cur; p.reward[g] = e.reward; p.done[g] = (uint8_t)e.done;
+  for (int k = 0; k < 6; ++k) p.memory[6 * g + k] = e.memory[k];
+}
+__device__ __forceinline__ void ttt_to_emb(const Ttt& e, float* f) {
+  for (int k = 0; k < 9; ++k) f[k] = (float)e.board[k];
+  f[9] = (float)e.cur; f[10] = (float)e.reward; f[11] = (float)e.done;
+  for (int k = 0; k < 6; ++k) f[12 + k] = (float)e.memory[k];
+}
+__device__ __forceinline__ void ttt_from_emb(Ttt& e, const float* f) {
+  for (int k = 0; k < 9; ++k) e.board[k] = (int8_t)f[k];
+  e.cur = (int8_t)f[9]; e.reward = (int8_t)f[10]; e.done = (int8_t)f[11];
+  for (int k = 0; k < 6; ++k) e.memory[k] = (int8_t)f[12 + k];
+}
+
+__global__ void k_ttt_reset(TttPtrs p, int64_t n) {
+  int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  Ttt e;
+  for (int k = 0; k < 9; ++k) e.board[k] = 0;
+  e.cur = 1; e.reward = 0; e.done = 0;
+  for (int k = 0; k < 6; ++k) e.memory[k] = -1;
+  ttt_store(p, g, e);
+}
+__global__ void k_ttt_step(TttPtrs p, int64_t n, int variant, const int8_t* __restrict__ action, int8_t* __restrict__ reward,
+                           uint8_t* __restrict__ done) {
+  int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  Ttt e;
+  ttt_load(p, g, e);
+  ttt_step(variant, e, action[g]);
+  ttt_store(p, g, e);
+  if (reward) reward[g] = e.reward;
+  if (done) done[g] = (uint8_t)e.done;
+}
+__global__ void k_ttt_policy(TttPtrs p, int64_t n, int variant, float* __restrict__ logits, uint8_t* __restrict__ valid) {
+  int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  Ttt e;
+  ttt_load(p, g, e);
+  if (logits) { float lg[9]; ttt_policy(variant, e, lg); for (int a = 0; a < 9; ++a) logits[9 * g + a] = lg[a]; }
+  if (valid) for (int a = 0; a < 9; ++a) valid[9 * g + a] = (uint8_t)(!e.done && e.board[a] == 0);  // valid_action_mask
+}
+__global__ void k_ttt_root_fn(TttPtrs p, int64_t n, int variant, const uint32_t* __restrict__ keys, float* __restrict__ prior,
+                              float* __restrict__ value, float* __restrict__ emb) {
+  int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  Ttt e;
+  ttt_load(p, g, e);
+  float lg[9];
+  ttt_policy(variant, e, lg);
+  for (int a = 0; a < 9; ++a) prior[9 * g + a] = lg[a];
+  value[g] = ttt_rollout(variant, e, Key2{keys[2 * g], keys[2 * g + 1]});
+  ttt_to_emb(e, emb + 18 * g);
+}
+__global__ void k_ttt_recurrent_fn(int64_t n, int variant, const uint32_t* __restrict__ keys, const int32_t* __restrict__ action,
+                                   const float* __restrict__ emb_in, float* __restrict__ prior, float* __restrict__ value,
+                                   float* __restrict__ reward, float* __restrict__ discount, float* __restrict__ emb_out) {
+  int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  Ttt e;
+  ttt_from_emb(e, emb_in + 18 * g);
+  ttt_step(variant, e, (int)(int8_t)action[g]);
+  reward[g] = (float)e.reward;
+  discount[g] = e.done ? 0.0f : -1.0f;
+  float lg[9];
+  ttt_policy(variant, e, lg);
+  for (int a = 0; a < 9; ++a) prior[9 * g + a] = lg[a];
+  value[g] = e.done ? 0.0f : ttt_rollout(variant, e, Key2{keys[2 * g], keys[2 * g + 1]});
+  ttt_to_emb(e, emb_out + 18 * g);
+}
+
+static int ttt_ptrs(const dogstep_ttt_state* s, TttPtrs* p) {
+  if (!s || !s->board || !s->current_player || !s->reward || !s->done || !s->memory) return DOGSTEP_ERR_INVALID_ARG;
+  *p = TttPtrs{s->board, s->current_player, s->reward, s->done, s->memory};
+  return DOGSTEP_OK;
+}
+static inline unsigned tb(int64_t n) { return (unsigned)((n + 127) / 128); }
+
+}  // namespace dogstep
+
+using namespace dogstep;
+
+extern "C" {
+
+int dogstep_ttt_reset(const dogstep_ttt_state* s, int64_t n, void* stream) {
+  TttPtrs p;
+  if (n < 0) return DOGSTEP_ERR_INVALID_ARG;
+  if (int rc = ttt_ptrs(s, &p)) return rc;
+  if (n == 0) return DOGSTEP_OK;
+  k_ttt_reset<<<tb(n), 128, 0, (cudaStream_t)stream>>>(p, n);
+  return check_launch();
+}
+int dogstep_ttt_step(const dogstep_ttt_state* s, int64_t n, int32_t variant, const int8_t* action, int8_t* reward, uint8_t* done,
+                     void* stream) {
+  TttPtrs p;
+  if (n < 0 || !action || variant < 0 || variant > 1) return DOGSTEP_ERR_INVALID_ARG;
+  if (int rc = ttt_ptrs(s, &p)) return rc;
+  if (n == 0) return DOGSTEP_OK;
+  k_ttt_step<<<tb(n), 128, 0, (cudaStream_t)stream>>>(p, n, variant, action, reward, done);
+  return check_launch();
+}
+int dogstep_ttt_policy_function(const dogstep_ttt_state* s, int64_t n, int32_t variant, float* logits, uint8_t* valid_mask,
+                                void* stream) {
+  TttPtrs p;
+  if (n < 0 || variant < 0 || variant > 1 || (!logits && !valid_mask)) return DOGSTEP_ERR_INVALID_ARG;
+  if (int rc = ttt_ptrs(s, &p)) return rc;
+  if (n == 0) return DOGSTEP_OK;
+  k_ttt_policy<<<tb(n), 128, 0, (cudaStream_t)stream>>>(p, n, variant, logits, valid_mask);
+  return check_launch();
+}
+int dogstep_ttt_root_fn(const dogstep_ttt_state* s, int64_t n, int32_t variant, const uint32_t* keys, float* prior_logits,
+                        float* value, float* embedding, void* stream) {
+  TttPtrs p;
+  if (n < 0 || variant < 0 || variant > 1 || !keys || !prior_logits || !value || !embedding) return DOGSTEP_ERR_INVALID_ARG;
+  if (int rc = ttt_ptrs(s, &p)) return rc;
+  if (n == 0) return DOGSTEP_OK;
+  k_ttt_root_fn<<<tb(n), 128, 0, (cudaStream_t)stream>>>(p, n, variant, keys, prior_logits, value, embedding);
+  return check_launch();
+}
+int dogstep_ttt_recurrent_fn(int64_t n, int32_t variant, const uint32_t* keys, const int32_t* action, const float* embedding_in,
+                             float* prior_logits, float* value, float* reward, float* discount, float* embedding_out,
+                             void* stream) {
+  if (n < 0 || variant < 0 || variant > 1 || !keys || !action || !embedding_in || !prior_logits || !value || !reward ||
+      !discount || !embedding_out)
+    return DOGSTEP_ERR_INVALID_ARG;
+  if (n == 0) return DOGSTEP_OK;
+  k_ttt_recurrent_fn<<<tb(n), 128, 0, (cudaStream_t)stream>>>(n, variant, keys, action, embedding_in, prior_logits, value, reward,
+                                                              discount, embedding_out);
+  return check_launch();
+}
+
+}  // extern "C"

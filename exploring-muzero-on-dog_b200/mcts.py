@@ -110,6 +110,7 @@ class Search:
         self.action = torch.empty(n, dtype=torch.int32, device=self.device)
         self.embedding = torch.empty((n, cfg.embed_dim), dtype=torch.float32, device=self.device)
         self.is_decision = torch.empty(n, dtype=torch.uint8, device=self.device)
+        self.expand_key = torch.empty((n, 2), dtype=torch.uint32, device=self.device)
 
     def init(self, keys, root, invalid_actions=None, dirichlet_noise=None):
         f = lambda x: None if x is None else x.contiguous()
@@ -122,7 +123,7 @@ class Search:
     def select(self, sim):
         _lib.check(_lib.lib().dogstep_mcts_select(C.byref(self._ct), C.c_int64(self.n), C.byref(self.cfg), C.c_int32(sim),
                                                  _lib.ptr(self.parent), _lib.ptr(self.action), _lib.ptr(self.embedding),
-                                                 _lib.ptr(self.is_decision), _lib.stream()), "mcts_select")
+                                                 _lib.ptr(self.is_decision), _lib.ptr(self.expand_key), _lib.stream()), "mcts_select")
         return self.parent, self.action, self.embedding, self.is_decision
 
     def expand(self, sim, prior_logits, value, reward, discount, embedding, chance_logits=None, afterstate_value=None,
@@ -148,7 +149,7 @@ def _run(search, params, root, recurrent_fn, invalid_actions, keys, dirichlet_no
     search.init(keys, root, invalid_actions, dirichlet_noise)
     for sim in range(search.cfg.num_simulations):
         _, action, emb, _ = search.select(sim)
-        out, nxt = recurrent_fn(params, None, action.long(), emb)
+        out, nxt = recurrent_fn(params, search.expand_key, action.long(), emb)
         search.expand(sim, out.prior_logits, out.value, out.reward, out.discount, nxt.reshape(search.n, -1))
     return search.policy_output()[0]
 

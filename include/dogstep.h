@@ -241,9 +241,11 @@ int dogstep_mcts_init(const dogstep_mcts_tree* t, int64_t n, const dogstep_mcts_
                       const float* root_prior_logits, const float* root_value, const float* root_embedding,
                       const uint8_t* invalid_actions, const float* dirichlet_noise, void* stream);
 /* simulate(): descend from the root to (parent, action) for simulation `sim`; gathers the parent's embedding.
- * parent_out i32 [n], action_out i32 [n], embedding_out f32 [n,E], is_decision_out u8 [n] (may be NULL). */
+ * parent_out i32 [n], action_out i32 [n], embedding_out f32 [n,E], is_decision_out u8 [n] (may be NULL),
+ * expand_key_out u32 [n,2] (may be NULL): the `expand_key` mctx hands to recurrent_fn for this simulation. */
 int dogstep_mcts_select(const dogstep_mcts_tree* t, int64_t n, const dogstep_mcts_cfg* cfg, int32_t sim, int32_t* parent_out,
-                        int32_t* action_out, float* embedding_out, uint8_t* is_decision_out, void* stream);
+                        int32_t* action_out, float* embedding_out, uint8_t* is_decision_out, uint32_t* expand_key_out,
+                        void* stream);
 /* expand() + backward() with the caller's recurrent_fn outputs for the (parent, action) pairs of `sim`:
  * prior_logits f32 [n,A], value/reward/discount f32 [n], embedding f32 [n,E].
  * Stochastic: the same five arrays are the chance_recurrent_fn outputs (action_logits, value, reward, discount,
@@ -325,6 +327,33 @@ int dogstep_madn_cls_agent_step(const dogstep_madn_cls_state* s, int64_t n, cons
                                 const dogstep_replay_arrays* traj, void* stream);
 /* throw_die for the games that are not done (game_agent_stochastic.py:90 runs inside do_active_step) */
 int dogstep_madn_cls_throw_die_active(const dogstep_madn_cls_state* s, int64_t n, const dogstep_madn_cfg* cfg, void* stream);
+
+/* ---------------------------------------------------------------- TicTacToe (BASELINE config 1)
+ * Batched leaves of `TicTacToe` / `TicTacToeV2` (TicTacToe/TicTacToe.py:12-17, TicTacToeV2.py:14-20).
+ * variant 0 = TicTacToe.py, 1 = TicTacToeV2.py (last three moves per player persist; `memory`). */
+typedef struct {
+  int8_t* board;          /* [n, 3, 3]  0 empty, +1 / -1 */
+  int8_t* current_player; /* [n]  +1 / -1 */
+  int8_t* reward;         /* [n] */
+  uint8_t* done;          /* [n] */
+  int8_t* memory;         /* [n, 2, 3]  V2 only (still required; -1 filled) */
+} dogstep_ttt_state;
+/* env_reset — TicTacToeV2.py:38-45 */
+int dogstep_ttt_reset(const dogstep_ttt_state* s, int64_t n, void* stream);
+/* env_step — TicTacToe.py:42-59 / TicTacToeV2.py:46-79.  action int8 [n] */
+int dogstep_ttt_step(const dogstep_ttt_state* s, int64_t n, int32_t variant, const int8_t* action, int8_t* reward, uint8_t* done,
+                     void* stream);
+/* policy_function (:96-102) -> logits f32 [n,9] and/or valid_action_mask (:81-82) -> u8 [n,9]; either may be NULL */
+int dogstep_ttt_policy_function(const dogstep_ttt_state* s, int64_t n, int32_t variant, float* logits, uint8_t* valid_mask,
+                                void* stream);
+/* root_fn (:121-126): prior = policy_function(env), value = rollout(env, key), embedding = the env as 18 floats
+ * (board 9, current_player, reward, done, memory 6).  keys u32 [n,2] */
+int dogstep_ttt_root_fn(const dogstep_ttt_state* s, int64_t n, int32_t variant, const uint32_t* keys, float* prior_logits,
+                        float* value, float* embedding, void* stream);
+/* recurrent_fn (:128-140): env_step(embedding, action) then policy_function / rollout value on the successor */
+int dogstep_ttt_recurrent_fn(int64_t n, int32_t variant, const uint32_t* keys, const int32_t* action, const float* embedding_in,
+                             float* prior_logits, float* value, float* reward, float* discount, float* embedding_out,
+                             void* stream);
 
 /* ---------------------------------------------------------------- jax.random on device
  * Stand-ins for the jax.random calls the self-play drivers make around the env functions

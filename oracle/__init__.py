@@ -421,8 +421,9 @@ def mcts_select(tree, sim):
     action = np.empty(tree.n, np.int32)
     emb = np.empty((tree.n, tree.cfg.embed_dim), np.float32)
     isdec = np.empty(tree.n, np.uint8)
+    tree.expand_key = np.empty((tree.n, 2), np.uint32)
     assert lib().orc_mcts_select(C.byref(t), C.c_int64(tree.n), C.byref(tree.cfg), C.c_int32(sim), _p(parent), _p(action),
-                                 _p(emb), _p(isdec)) == 0
+                                 _p(emb), _p(isdec), _p(tree.expand_key)) == 0
     return parent, action, emb, isdec
 
 
@@ -446,3 +447,57 @@ def mcts_policy_output(tree):
 
 def considered_visit(m, S, i):
     return int(lib().orc_considered_visit(C.c_int(m), C.c_int(S), C.c_int(i)))
+
+
+# --------------------------------------------------------------------------- TicTacToe
+class TttState:
+    FIELDS = ("board", "current_player", "reward", "done", "memory")
+
+    def __init__(self, n, variant=1):
+        self.n, self.variant = n, variant
+        self.board = np.zeros((n, 3, 3), np.int8)
+        self.current_player = np.ones(n, np.int8)
+        self.reward = np.zeros(n, np.int8)
+        self.done = np.zeros(n, np.uint8)
+        self.memory = np.full((n, 2, 3), -1, np.int8)
+
+    def args(self):
+        return (_p(self.board), _p(self.current_player), _p(self.reward), _p(self.done), _p(self.memory))
+
+    def fields(self):
+        return {k: getattr(self, k) for k in self.FIELDS}
+
+    def copy(self):
+        o = TttState(self.n, self.variant)
+        for k in self.FIELDS:
+            setattr(o, k, getattr(self, k).copy())
+        return o
+
+
+def ttt_step(s, action):
+    action = _c(action, np.int8).reshape(s.n)
+    lib().orc_ttt_step(C.c_int(s.variant), C.c_int64(s.n), *s.args(), _p(action))
+    return s.reward.copy(), s.done.astype(bool)
+
+
+def ttt_policy(s):
+    out = np.empty((s.n, 9), np.float32)
+    lib().orc_ttt_policy(C.c_int(s.variant), C.c_int64(s.n), *s.args(), _p(out))
+    return out
+
+
+def ttt_root_fn(s, keys):
+    keys = _c(keys, np.uint32)
+    prior, value, emb = np.empty((s.n, 9), np.float32), np.empty(s.n, np.float32), np.empty((s.n, 18), np.float32)
+    lib().orc_ttt_root_fn(C.c_int(s.variant), C.c_int64(s.n), *s.args(), _p(keys), _p(prior), _p(value), _p(emb))
+    return prior, value, emb
+
+
+def ttt_recurrent_fn(variant, keys, action, emb):
+    keys, action, emb = _c(keys, np.uint32), _c(action, np.int32), _c(emb, np.float32)
+    n = action.size
+    prior, value, reward, discount = np.empty((n, 9), np.float32), np.empty(n, np.float32), np.empty(n, np.float32), np.empty(n, np.float32)
+    emb_out = np.empty((n, 18), np.float32)
+    lib().orc_ttt_recurrent_fn(C.c_int(variant), C.c_int64(n), _p(keys), _p(action), _p(emb), _p(prior), _p(value), _p(reward),
+                               _p(discount), _p(emb_out))
+    return prior, value, reward, discount, emb_out

@@ -116,3 +116,21 @@ def iinfo(d):
 
 def finfo(d):
     return _np.finfo(d)
+
+
+class _Ufunc:
+    """jnp ufunc object with .reduce (only logical_or.reduce is used by the reference: TicTacToe.py:51)"""
+
+    def __init__(self, name):
+        self._f = _wrapfn(name)
+        self._np = getattr(_np, name)
+
+    def __call__(self, *a, **k):
+        return self._f(*a, **k)
+
+    def reduce(self, x, axis=0, **k):
+        return wrap(self._np.reduce(_u(x), axis=axis, **k))
+
+
+logical_or = _Ufunc("logical_or")
+logical_and = _Ufunc("logical_and")

@@ -81,7 +81,10 @@ def randint(key, shape, minval, maxval, dtype=_np.int32):
 
 def gumbel(key, shape=(), dtype=_np.float32):
     u = _np.asarray(uniform(key, shape, minval=_np.finfo(_np.float32).tiny, maxval=1.0))
-    return wrap((-_np.log(-_np.log(u))).astype(_np.float32))
+    # float contract of DESIGN.md: log evaluated in float64 and rounded to float32 once per call (XLA's own logf
+    # polynomial cannot be reproduced here; any two faithful logf differ by <= 1 ulp)
+    inner = _np.log(u.astype(_np.float64)).astype(_np.float32)
+    return wrap((-_np.log((-inner).astype(_np.float64)).astype(_np.float32)).astype(_np.float32))
 
 
 def categorical(key, logits, axis=-1, shape=None):

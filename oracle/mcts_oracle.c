@@ -275,13 +275,14 @@ int orc_mcts_init(const dogstep_mcts_tree *tr, int64_t n, const dogstep_mcts_cfg
 
 /* search.simulate */
 int orc_mcts_select(const dogstep_mcts_tree *tr, int64_t n, const dogstep_mcts_cfg *c, int32_t sim, int32_t *parent_out,
-                    int32_t *action_out, float *embedding_out, uint8_t *is_decision_out) {
+                    int32_t *action_out, float *embedding_out, uint8_t *is_decision_out, uint32_t *expand_key_out) {
   (void)sim;
   for (int64_t g = 0; g < n; ++g) {
     gtree t = view(tr, c, g);
     /* rng, simulate_key, expand_key = split(rng, 3); simulate_keys = split(simulate_key, 1) */
     uint32_t k0[2], k1[2], r[2];
     orc_split_i(t.search_key, 0, k0); orc_split_i(t.search_key, 1, k1);
+    if (expand_key_out) orc_split_i(t.search_key, 2, expand_key_out + 2 * g);
     t.search_key[0] = k0[0]; t.search_key[1] = k0[1];
     orc_split_i(k1, 0, r);
     int node = 0, depth = 0, action = 0, parent = 0;
