@@ -106,3 +106,7 @@ class ReplayArrays(C.Structure):
 class ReplayBatch(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("observations", "actions", "rewards", "policies", "values", "masks", "target_values",
                                           "discount_targets", "dice_outcomes", "dice_probs")]
+
+
+class TttState(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("board", "current_player", "reward", "done", "memory")]

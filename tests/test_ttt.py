@@ -52,3 +52,101 @@ def test_oracle_root_and_recurrent_fn(variant):
     assert np.array_equal(r2, z[f"{tag}_rec_reward"][idx]) and np.array_equal(d2, z[f"{tag}_rec_discount"][idx])
     assert np.array_equal(e2[:, :9].reshape(-1, 3, 3), z[f"{tag}_rec_board"][idx]) and np.array_equal(e2[:, 9], z[f"{tag}_rec_cur"][idx])
     assert np.array_equal(e2[:, 11].astype(bool), z[f"{tag}_rec_done"][idx])
+
+
+# ------------------------------------------------------------------------------------------------- GPU
+def _upload(z, tag, variant, sel):
+    from exploring_muzero_on_dog_b200.TicTacToe import TicTacToeV2 as g
+    env = g.env_reset(0, n=len(sel), variant=variant)
+    return env.replace(board=z[f"{tag}_board"][sel], current_player=z[f"{tag}_cur"][sel], reward=z[f"{tag}_reward"][sel],
+                       done=z[f"{tag}_done"][sel], memory=z[f"{tag}_memory"][sel])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", [0, 1])
+def test_cuda_env_and_callbacks_match_reference(variant):
+    import torch
+    from exploring_muzero_on_dog_b200.TicTacToe import TicTacToeV2 as g
+    z = np.load(G)
+    tag = f"v{variant}"
+    n = z[f"{tag}_board"].shape[0]
+    idx = np.array([i for i in range(n) if i % PLIES != PLIES - 1])
+    env = _upload(z, tag, variant, idx)
+    assert np.array_equal(g.policy_function(env).cpu().numpy(), z[f"{tag}_policy"][idx])
+    assert np.array_equal(g.valid_action_mask(env).cpu().numpy(), (z[f"{tag}_board"][idx] == 0) & ~z[f"{tag}_done"][idx][:, None, None])
+    env2, r, d = g.env_step(env, z[f"{tag}_action"][idx])
+    st = env2.numpy()
+    nxt = idx + 1
+    assert np.array_equal(st["board"], z[f"{tag}_board"][nxt]) and np.array_equal(st["current_player"], z[f"{tag}_cur"][nxt])
+    assert np.array_equal(st["reward"], z[f"{tag}_reward"][nxt]) and np.array_equal(st["done"], z[f"{tag}_done"][nxt])
+    if variant == 1:
+        assert np.array_equal(st["memory"], z[f"{tag}_memory"][nxt])
+    ridx = np.flatnonzero(z[f"{tag}_rec_action"] >= 0)
+    env = _upload(z, tag, variant, ridx)
+    keys = torch.from_numpy(z[f"{tag}_key"][ridx]).cuda()
+    root = g.root_fn(env, keys)
+    assert np.array_equal(root.prior_logits.cpu().numpy(), z[f"{tag}_policy"][ridx])
+    assert np.array_equal(root.value.cpu().numpy(), z[f"{tag}_root_value"][ridx])
+    out, nxt_emb = g.make_recurrent_fn(variant)(None, keys, torch.from_numpy(z[f"{tag}_rec_action"][ridx]).cuda(), root.embedding)
+    assert np.array_equal(out.prior_logits.cpu().numpy(), z[f"{tag}_rec_prior"][ridx])
+    assert np.array_equal(out.value.cpu().numpy(), z[f"{tag}_rec_value"][ridx])
+    assert np.array_equal(out.reward.cpu().numpy(), z[f"{tag}_rec_reward"][ridx]) and np.array_equal(out.discount.cpu().numpy(), z[f"{tag}_rec_discount"][ridx])
+    e = nxt_emb.cpu().numpy()
+    assert np.array_equal(e[:, :9].reshape(-1, 3, 3), z[f"{tag}_rec_board"][ridx]) and np.array_equal(e[:, 11].astype(bool), z[f"{tag}_rec_done"][ridx])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", [0, 1])
+def test_cuda_true_env_search_equals_oracle(variant):
+    """run_mcts on the true env: CUDA search + CUDA callbacks vs oracle search + oracle callbacks, simulation by simulation"""
+    import torch
+    from exploring_muzero_on_dog_b200 import _lib, mcts
+    from exploring_muzero_on_dog_b200.TicTacToe import TicTacToeV2 as g
+    n, S = 128, 50
+    rng = np.random.default_rng(variant)
+    s = O.TttState(n, variant)
+    for t in range(3):
+        O.ttt_step(s, rng.integers(0, 9, n))
+    s.done[...] = 0
+    env = g.env_reset(0, n=n, variant=variant).replace(board=s.board, current_player=s.current_player, reward=s.reward,
+                                                        done=s.done.astype(bool), memory=s.memory)
+    keys = rng.integers(0, 2**32, (n, 2), dtype=np.uint64).astype(np.uint32)
+    rkeys = rng.integers(0, 2**32, (n, 2), dtype=np.uint64).astype(np.uint32)
+    d = dict(policy=0, qtransform=0, num_simulations=S, max_depth=9, num_actions=9, num_chance=0, embed_dim=18,
+             max_num_considered_actions=16, q_min=-1.0, q_max=1.0, value_scale=0.1, maxvisit_init=50.0, epsilon=1e-8,
+             pb_c_init=1.25, pb_c_base=19652.0, dirichlet_fraction=0.0, temperature=1.0, gumbel_scale=1.0)
+    search = mcts.Search(_lib.MctsCfg(**d), n)
+    root = g.root_fn(env, torch.from_numpy(rkeys).cuda())
+    search.init(torch.from_numpy(keys).cuda(), root)
+    op, ov, oe = O.ttt_root_fn(s, rkeys)
+    assert np.array_equal(op, root.prior_logits.cpu().numpy()) and np.array_equal(ov, root.value.cpu().numpy())
+    otree = O.MctsTree(O.MctsCfg(**d), n)
+    O.mcts_init(otree, keys, op, ov, oe)
+    rec = g.make_recurrent_fn(variant)
+    for sim in range(S):
+        parent, action, emb, _ = search.select(sim)
+        p2, a2, e2, _ = O.mcts_select(otree, sim)
+        assert np.array_equal(action.cpu().numpy(), a2) and np.array_equal(parent.cpu().numpy(), p2), sim
+        assert np.array_equal(search.expand_key.cpu().numpy(), otree.expand_key)
+        out, nxt = rec(None, search.expand_key, action, emb)
+        search.expand(sim, out.prior_logits, out.value, out.reward, out.discount, nxt)
+        rp, rv, rr, rd, re = O.ttt_recurrent_fn(variant, otree.expand_key, a2, e2)
+        assert np.array_equal(rv, out.value.cpu().numpy()) and np.array_equal(re, nxt.cpu().numpy())
+        O.mcts_expand(otree, sim, p2, a2, rp, rv, rr, rd, re)
+    po, _ = search.policy_output()
+    oa, ow, _ = O.mcts_policy_output(otree)
+    assert np.array_equal(po.action.cpu().numpy(), oa) and np.array_equal(po.action_weights.cpu().numpy(), ow)
+    assert np.array_equal(search.tree.children_visits.cpu().numpy(), otree.children_visits)
+
+
+@pytest.mark.gpu
+def test_config1_lockstep_mcts_selfplay():
+    """BASELINE config 1 shape: 512 lockstep games x 50 simulations per ply; search players never make an illegal move and the
+    classic game between two search players ends by line or full board within 9 plies."""
+    from exploring_muzero_on_dog_b200 import jaxrand
+    from exploring_muzero_on_dog_b200.TicTacToe import mcts as tm
+    env, plies = tm.play_mcts_games(512, jaxrand.PRNGKey(0), num_simulations=50, limit=30, variant=0)
+    st = env.numpy()
+    assert st["done"].all() and (plies.cpu().numpy() <= 9).all() and (st["reward"] >= 0).all()
+    env, plies = tm.play_mcts_games(512, jaxrand.PRNGKey(1), num_simulations=50, limit=30, variant=1, search=tm.run_gumbel)
+    assert (env.numpy()["reward"] >= 0).all() and int(plies.max()) <= 30
