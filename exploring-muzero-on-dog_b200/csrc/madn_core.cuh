@@ -61,27 +61,39 @@ struct MadnRegs {
 
 #define DS_RULE(g, bit) (((g).rules & (bit)) != 0u)
 
+// rules are plain integer logic: callable from the host too, so tests can run them against the oracle on the CPU
+#define DS_FN __host__ __device__ __forceinline__
+
+DS_FN int ds_popcll(uint64_t v) {
+#ifdef __CUDA_ARCH__
+  return __popcll(v);
+#else
+  return __builtin_popcountll(v);
+#endif
+}
+DS_FN uint32_t ds_min_u32(uint32_t a, uint32_t b) { return a < b ? a : b; }
+
 template <typename T>
-__device__ __forceinline__ T pick4(const T (&a)[4], int i) {
+DS_FN T pick4(const T (&a)[4], int i) {
   T r = a[0];
   r = (i == 1) ? a[1] : r;
   r = (i == 2) ? a[2] : r;
   r = (i == 3) ? a[3] : r;
   return r;
 }
-__device__ __forceinline__ int byte_s(uint32_t w, int i) { return (int)(int8_t)(w >> (8 * i)); }
-__device__ __forceinline__ int byte_s64(uint64_t w, int i) { return (int)(int8_t)(w >> (8 * i)); }
-__device__ __forceinline__ int bit64(uint64_t w, int i) { return (int)((w >> i) & 1ull); }
-__device__ __forceinline__ int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
-__device__ __forceinline__ int floormod(int a, int b) { int r = a % b; return r < 0 ? r + b : r; }
+DS_FN int byte_s(uint32_t w, int i) { return (int)(int8_t)(w >> (8 * i)); }
+DS_FN int byte_s64(uint64_t w, int i) { return (int)(int8_t)(w >> (8 * i)); }
+DS_FN int bit64(uint64_t w, int i) { return (int)((w >> i) & 1ull); }
+DS_FN int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+DS_FN int floormod(int a, int b) { int r = a % b; return r < 0 ? r + b : r; }
 // JAX gather index: negative wraps once, then clamp
-__device__ __forceinline__ int gidx(int i, int size) {
+DS_FN int gidx(int i, int size) {
   i = (i < 0) ? i + size : i;
   return min(max(i, 0), size - 1);
 }
 
 // cells of player p's four pins as a bitboard (-1 / out-of-range pins dropped)
-__device__ __forceinline__ uint64_t pins_to_bits(uint32_t w, int total) {
+DS_FN uint64_t pins_to_bits(uint32_t w, int total) {
   uint64_t b = 0;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -92,7 +104,7 @@ __device__ __forceinline__ uint64_t pins_to_bits(uint32_t w, int total) {
 }
 
 // set_pins_on_board (deterministic_madn.py:259-271): later (higher player / pin) writes win
-__device__ __forceinline__ void rebuild_occ(const MadnGeom& g, MadnRegs& s) {
+DS_FN void rebuild_occ(const MadnGeom& g, MadnRegs& s) {
   uint64_t later = 0;
 #pragma unroll
   for (int p = 3; p >= 0; --p) {
@@ -103,26 +115,26 @@ __device__ __forceinline__ void rebuild_occ(const MadnGeom& g, MadnRegs& s) {
 }
 
 // is_player_done (deterministic_madn.py:122-137): the four goal cells are occupied by ANYONE
-__device__ __forceinline__ int player_done(const MadnGeom& g, uint64_t anyocc, int p) {
+DS_FN int player_done(const MadnGeom& g, uint64_t anyocc, int p) {
   return (p >= 0 && p < g.n) ? (int)(((anyocc >> g.goal0[p]) & 0xFull) == 0xFull) : 0;
 }
 
 // team proxy (deterministic_madn.py:184,310)
-__device__ __forceinline__ int mover_of(const MadnGeom& g, const MadnRegs& s, int pid) {
+DS_FN int mover_of(const MadnGeom& g, const MadnRegs& s, int pid) {
   uint64_t any = s.occ[0] | s.occ[1] | s.occ[2] | s.occ[3];
   int cp = (DS_RULE(g, DOGSTEP_RULE_TEAMS) && player_done(g, any, pid)) ? ((pid + 2) & 3) : pid;
   return gidx(cp, g.n);
 }
 
 // goal-lane path check: no own pin on lane cell k with s < k < e (lane = own bits of the 4 goal cells)
-__device__ __forceinline__ int lane_clear(uint32_t lane, int s, int e) {
+DS_FN int lane_clear(uint32_t lane, int s, int e) {
   int lo = max(s + 1, 0), hi = min(e - 1, 3);
   uint32_t m = (lo > hi) ? 0u : (((2u << hi) - 1u) & ~((1u << lo) - 1u));
   return (lane & m) == 0u;
 }
 
 // 4-bit mask, bit q = pins_on_start[q] = (board[start[q]] == q)
-__device__ __forceinline__ uint32_t pins_on_start_mask(const MadnGeom& g, const MadnRegs& s) {
+DS_FN uint32_t pins_on_start_mask(const MadnGeom& g, const MadnRegs& s) {
   uint32_t m = 0;
 #pragma unroll
   for (int q = 0; q < 4; ++q) m |= (q < g.n) ? ((uint32_t)bit64(s.occ[q], g.start[q]) << q) : 0u;
@@ -130,7 +142,7 @@ __device__ __forceinline__ uint32_t pins_on_start_mask(const MadnGeom& g, const 
 }
 
 // One (pin position, move) cell of valid_action before home-pin / action-set handling.
-__device__ __forceinline__ int move_ok(const MadnGeom& g, uint64_t own, uint32_t posmask, int cp, int pos, int m) {
+DS_FN int move_ok(const MadnGeom& g, uint64_t own, uint32_t posmask, int cp, int pos, int m) {
   const int mts = DS_RULE(g, DOGSTEP_RULE_MUST_TRAVERSE_START);
   const int circ = DS_RULE(g, DOGSTEP_RULE_CIRCULAR_BOARD);
   const int jump = DS_RULE(g, DOGSTEP_RULE_JUMP_IN_GOAL);
@@ -167,7 +179,7 @@ __device__ __forceinline__ int move_ok(const MadnGeom& g, uint64_t own, uint32_t
 // Bit-parallel form of move_ok for the six moves m = 1..6 of one pin (bit m-1), valid when
 // start blocking is off (then x is never overridden and the start lookups drop out).  Same
 // reference lines as move_ok; cross-checked against it over random rule sets in tests/.
-__device__ __forceinline__ uint32_t move_row_fast(const MadnGeom& g, uint64_t own, int cp, int pos) {
+DS_FN uint32_t move_row_fast(const MadnGeom& g, uint64_t own, int cp, int pos) {
   const int mts = DS_RULE(g, DOGSTEP_RULE_MUST_TRAVERSE_START);
   const int circ = DS_RULE(g, DOGSTEP_RULE_CIRCULAR_BOARD);
   const int jump = DS_RULE(g, DOGSTEP_RULE_JUMP_IN_GOAL);
@@ -201,7 +213,7 @@ __device__ __forceinline__ uint32_t move_row_fast(const MadnGeom& g, uint64_t ow
 }
 
 // valid_action, deterministic variant -> 24-bit mask, bit pin*6 + (move-1)
-__device__ __forceinline__ uint32_t madn_det_valid_mask(const MadnGeom& g, const MadnRegs& s) {
+DS_FN uint32_t madn_det_valid_mask(const MadnGeom& g, const MadnRegs& s) {
   const int pid = s.cur;
   const int cp = mover_of(g, s, pid);
   const uint64_t own = pick4(s.occ, cp);
@@ -235,7 +247,7 @@ __device__ __forceinline__ uint32_t madn_det_valid_mask(const MadnGeom& g, const
 }
 
 // valid_action, classic variant -> 4-bit mask
-__device__ __forceinline__ uint32_t madn_cls_valid_mask(const MadnGeom& g, const MadnRegs& s) {
+DS_FN uint32_t madn_cls_valid_mask(const MadnGeom& g, const MadnRegs& s) {
   const int pid = s.cur, die = s.die;
   const int cp = mover_of(g, s, pid);
   const uint64_t own = pick4(s.occ, cp);
@@ -254,12 +266,12 @@ __device__ __forceinline__ uint32_t madn_cls_valid_mask(const MadnGeom& g, const
 }
 
 // exact zero-byte detector: 0x80 in every byte of v that is zero
-__device__ __forceinline__ uint32_t zero_bytes(uint32_t v) {
+DS_FN uint32_t zero_bytes(uint32_t v) {
   return ~(((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v | 0x7F7F7F7Fu);
 }
 
 // Shared move application (deterministic_madn.py:188-230 / classic_madn.py:278-321).
-__device__ __forceinline__ void madn_apply_move(const MadnGeom& g, MadnRegs& s, int cp, int pin, int move, int invalid) {
+DS_FN void madn_apply_move(const MadnGeom& g, MadnRegs& s, int cp, int pin, int move, int invalid) {
   const int mts = DS_RULE(g, DOGSTEP_RULE_MUST_TRAVERSE_START);
   const int jump = DS_RULE(g, DOGSTEP_RULE_JUMP_IN_GOAL);
   const uint64_t own = pick4(s.occ, cp);
@@ -300,7 +312,7 @@ __device__ __forceinline__ void madn_apply_move(const MadnGeom& g, MadnRegs& s, 
 }
 
 // get_winner (deterministic_madn.py:139-168) -> 4-bit mask
-__device__ __forceinline__ uint32_t madn_winner_mask(const MadnGeom& g, const MadnRegs& s) {
+DS_FN uint32_t madn_winner_mask(const MadnGeom& g, const MadnRegs& s) {
   uint64_t any = s.occ[0] | s.occ[1] | s.occ[2] | s.occ[3];
   uint32_t pd = 0;
 #pragma unroll
@@ -313,7 +325,7 @@ __device__ __forceinline__ uint32_t madn_winner_mask(const MadnGeom& g, const Ma
   return pd;
 }
 
-__device__ __forceinline__ void madn_finish_step(const MadnGeom& g, MadnRegs& s, int pid, int cp, int invalid, int move) {
+DS_FN void madn_finish_step(const MadnGeom& g, MadnRegs& s, int pid, int cp, int invalid, int move) {
   uint32_t win = madn_winner_mask(g, s);
   int reward = s.done ? 0 : (invalid ? -1 : (int)((win >> cp) & 1u));
   int done = s.done || (win != 0u);
@@ -324,7 +336,7 @@ __device__ __forceinline__ void madn_finish_step(const MadnGeom& g, MadnRegs& s,
 }
 
 // env_step, deterministic (deterministic_madn.py:170-257). `valid_bit` = valid_action[pin, move-1].
-__device__ __forceinline__ void madn_det_step(const MadnGeom& g, MadnRegs& s, int pin_in, int move_in, uint32_t vmask) {
+DS_FN void madn_det_step(const MadnGeom& g, MadnRegs& s, int pin_in, int move_in, uint32_t vmask) {
   const int pid = s.cur;
   const int cp = mover_of(g, s, pid);
   const int pin = gidx(pin_in, 4), mi = gidx(move_in - 1, 6);
@@ -351,7 +363,7 @@ __device__ __forceinline__ void madn_det_step(const MadnGeom& g, MadnRegs& s, in
 }
 
 // no_step, deterministic (deterministic_madn.py:283-297)
-__device__ __forceinline__ void madn_det_no_step(const MadnGeom& g, MadnRegs& s) {
+DS_FN void madn_det_no_step(const MadnGeom& g, MadnRegs& s) {
   const int pid = s.cur;
   if (pid >= -g.n && pid < g.n) {
     const int row = gidx(pid, g.n);
@@ -362,7 +374,7 @@ __device__ __forceinline__ void madn_det_no_step(const MadnGeom& g, MadnRegs& s)
 }
 
 // env_step, classic (classic_madn.py:257-337)
-__device__ __forceinline__ void madn_cls_step(const MadnGeom& g, MadnRegs& s, int pin_in, uint32_t vmask) {
+DS_FN void madn_cls_step(const MadnGeom& g, MadnRegs& s, int pin_in, uint32_t vmask) {
   const int pid = s.cur;
   const int cp = mover_of(g, s, pid);
   const int pin = gidx(pin_in, 4);
@@ -372,7 +384,7 @@ __device__ __forceinline__ void madn_cls_step(const MadnGeom& g, MadnRegs& s, in
 }
 
 // is_soft_locked (classic_madn.py:180-206); uses the UN-proxied current player
-__device__ __forceinline__ int madn_soft_locked(const MadnGeom& g, const MadnRegs& s) {
+DS_FN int madn_soft_locked(const MadnGeom& g, const MadnRegs& s) {
   const int p = gidx(s.cur, g.n);
   const uint32_t pw = pick4(s.pins, p);
   int not_home = 4;

@@ -8,11 +8,13 @@
 // persistent play_random kernel keeps the game in registers across all lockstep iterations.
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include "../../include/dogstep.h"
 #include "common.cuh"
 #include "jaxrand.cuh"
 #include "madn_core.cuh"
+#include "madn_fast.cuh"
 
 namespace dogstep {
 
@@ -415,6 +417,301 @@ __global__ void __launch_bounds__(kThreads) k_madn_det_play_random(const __grid_
   }
 }
 
+// Persistent lockstep loop, second generation (4 players, distance 10 — every configuration of the reference).
+// One warp per CTA (2,048 CTAs for 65,536 games spread evenly over the 148 SMs), one game per lane held in
+// registers for all its plies.  Per lockstep iteration:
+//   1. each lane derives its step key and the 24-bit legal mask (madn_fast.cuh: branch-free bit rows);
+//   2. the (game, action) pairs of the warp are compacted into a shared list and dealt out evenly to the 32 lanes,
+//      two per lane and pass, so the Threefry calls — one per LEGAL action, the bulk of the arithmetic — are
+//      load-balanced and two independent chains are in flight per lane;
+//   3. the argmax of the categorical draw is a shared-memory atomicMax per game on (mantissa << 5 | 23 - action):
+//      largest 23-bit mantissa first, lowest action index on ties — jax.random.categorical's choice;
+//   4. each lane applies its game's move (incremental bitboard update).
+// A warp that loaded a non-canonical game (see madn_fast.cuh) runs the generic rules of madn_core.cuh instead.
+template <uint32_t CT>
+__global__ void __launch_bounds__(32) k_madn_det_play_fast(const __grid_constant__ MadnGeom g, MadnPtrs p, int64_t n, Key2 rng0,
+                                                           int64_t game_offset, int max_steps, int32_t* __restrict__ game_len,
+                                                           unsigned long long* __restrict__ total_steps) {
+  __shared__ uint16_t s_items[32 * 24];
+  __shared__ uint32_t s_best[32];
+  __shared__ uint2 s_key[32];
+  const int lane = threadIdx.x;
+  const uint32_t FULL = 0xFFFFFFFFu;
+  const int64_t i = (int64_t)blockIdx.x * 32 + lane;
+  const RuleSet<CT> R{g.rules};
+  int len = 0;
+  MadnRegs s;
+  bool alive = false, canon = true;
+  if (i < n) {
+    load_state<true>(g, p, i, s);
+    canon = is_canonical4(s, s.occ);
+    alive = !s.done;
+  }
+  const bool fast = !__any_sync(FULL, !canon);
+  Key2 rng = rng0;
+  const uint32_t my = (uint32_t)(game_offset + i + 1);
+  const uint32_t lane_hi = (uint32_t)lane << 8;
+  s_best[lane] = 0u;
+  __syncwarp();
+#pragma unroll 1
+  for (int t = 0; t < max_steps; ++t) {
+    if (!__any_sync(FULL, alive)) break;
+    const Key2 key = split_i(rng, my);  // split(rng, N+1)[j+1]   (game_agent.py:60 / evaluate_agent.py:336)
+    rng = split_i(rng, 0u);             // split(rng, N+1)[0]
+    int cp = 0;
+    uint32_t m = 0u;
+    if (alive) m = fast ? det_valid_mask4(R, g, s, cp) : madn_det_valid_mask(g, s);
+    s_key[lane] = make_uint2(key.a, key.b);
+    // warp-wide compaction of the (lane, action) pairs
+    const int cnt = __popc(m);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(FULL, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(FULL, incl, 31);
+    {  // predicated stores, no find-first-set chain: 24 x (store, bump) under the mask bits
+      uint16_t* dst = s_items + (incl - cnt);
+#pragma unroll
+      for (int a = 0; a < 24; ++a) {
+        if ((m >> a) & 1u) *dst++ = (uint16_t)(lane_hi | (uint32_t)a);
+      }
+    }
+    __syncwarp();
+    for (int base = 0; base < total; base += 64) {
+      const int j0 = base + lane, j1 = j0 + 32;
+      if (base + 32 < total) {  // warp-uniform: two independent Threefry chains per lane
+        const uint32_t it0 = s_items[j0], it1 = (j1 < total) ? (uint32_t)s_items[j1] : 0u;
+        const uint32_t o0 = it0 >> 8, a0 = it0 & 0xFFu, o1 = it1 >> 8, a1 = it1 & 0xFFu;
+        const uint2 k0 = s_key[o0], k1 = s_key[o1];
+        const uint32_t v0 = bits_i(Key2{k0.x, k0.y}, a0) >> 9, v1 = bits_i(Key2{k1.x, k1.y}, a1) >> 9;
+        atomicMax(&s_best[o0], (v0 << 5) | (23u - a0));
+        if (j1 < total) atomicMax(&s_best[o1], (v1 << 5) | (23u - a1));
+      } else if (j0 < total) {
+        const uint32_t it0 = s_items[j0];
+        const uint32_t o0 = it0 >> 8, a0 = it0 & 0xFFu;
+        const uint2 k0 = s_key[o0];
+        const uint32_t v0 = bits_i(Key2{k0.x, k0.y}, a0) >> 9;
+        atomicMax(&s_best[o0], (v0 << 5) | (23u - a0));
+      }
+    }
+    __syncwarp();
+    if (alive) {
+      if (m) {
+        const int a = 23 - (int)(s_best[lane] & 31u);
+        if (fast) det_step4(R, s, cp, a);
+        else madn_det_step(g, s, a / 6, a % 6 + 1, m);  // map_action (deterministic_madn.py:469-479)
+      } else {
+        if (fast) det_no_step4(s);
+        else madn_det_no_step(g, s);
+      }
+      ++len;
+      alive = !s.done;
+    }
+    s_best[lane] = 0u;
+    __syncwarp();
+  }
+  if (i < n) {
+    store_det_all(g, p, i, s);
+    if (game_len) game_len[i] = len;
+  }
+  if (total_steps) {
+    unsigned v = (unsigned)len;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    if (lane == 0 && v) atomicAdd(total_steps, (unsigned long long)v);
+  }
+}
+
+// Third generation: the same per-warp pooled iteration, but one CTA per SM (up to 512 games) with a compaction point
+// every kPlayRound lockstep iterations.  Games end at different plies (mean 403, max ~850 in config 2), so a warp that
+// keeps its 32 games to the end idles 30 % of its lane-iterations; at a compaction point the live games of the CTA are
+// packed into the lowest warps through shared memory (23 words per game) and the emptied warps only wait at the barriers.
+// A finished game is written back at once by the lane that holds it.  The key chain value travels through shared memory
+// because a warp that ran empty and is refilled has not advanced it.
+constexpr int kPlayRound = 32;
+constexpr int kPlayMaxThreads = 512;
+constexpr int kXWords = 23;  // occ 8, pins 4, action set 8, cur|reward, len, game index
+
+static size_t play_smem_bytes(int threads) {
+  return (size_t)(threads / 32) * (24 * 32 * 2 + 32 * 4 + 32 * 8) + (size_t)kXWords * threads * 4 + 2 * 34 * 4;
+}
+
+template <uint32_t CT>
+__global__ void __launch_bounds__(kPlayMaxThreads) k_madn_det_play_cta(const __grid_constant__ MadnGeom g, MadnPtrs p, int64_t n,
+                                                                      Key2 rng0, int64_t game_offset, int max_steps,
+                                                                      int32_t* __restrict__ game_len,
+                                                                      unsigned long long* __restrict__ total_steps) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int T = blockDim.x, W = T >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint2* s_key = reinterpret_cast<uint2*>(smem_raw) + warp * 32;                                  // [W][32]
+  uint32_t* s_best = reinterpret_cast<uint32_t*>(smem_raw + (size_t)W * 256) + warp * 32;         // [W][32]
+  uint16_t* s_items = reinterpret_cast<uint16_t*>(smem_raw + (size_t)W * 384) + warp * (24 * 32);  // [W][768]
+  uint32_t* s_x = reinterpret_cast<uint32_t*>(smem_raw + (size_t)W * 1920);                       // [kXWords][T]
+  uint32_t* s_cnt = s_x + (size_t)kXWords * T;                                                    // 2 x ([32] counts, key[2])
+  const uint32_t FULL = 0xFFFFFFFFu;
+  const int64_t cta_base = (int64_t)blockIdx.x * T;
+  int gi = threadIdx.x;  // game held by this lane, relative to cta_base
+  const RuleSet<CT> R{g.rules};
+  int len = 0;
+  unsigned steps_done = 0;
+  MadnRegs s;
+  bool alive = false, canon = true;
+  if (cta_base + gi < n) {
+    load_state<true>(g, p, cta_base + gi, s);
+    canon = is_canonical4(s, s.occ);
+    alive = !s.done;
+    if (!alive && game_len) game_len[cta_base + gi] = 0;
+  }
+  const bool fast = !__syncthreads_or(!canon);
+  Key2 rng = rng0;
+  const uint32_t lane_hi = (uint32_t)lane << 8;
+  s_best[lane] = 0u;
+  bool rng_current = true;  // this warp's copy of the key chain is the one for iteration t
+  int t = 0, round = 0;
+  while (true) {
+    // ---- compaction point
+    // (counts and key are double-buffered by round parity: an empty warp can reach the next point while others still read)
+    const uint32_t ab = __ballot_sync(FULL, alive);
+    uint32_t* cnt = s_cnt + (round & 1) * 34;
+    if (lane == 0) {
+      cnt[warp] = (uint32_t)__popc(ab);
+      if (rng_current) { cnt[32] = rng.a; cnt[33] = rng.b; }
+    }
+    ++round;
+    __syncthreads();
+    int before = 0, live = 0, nonempty = 0;
+    for (int w = 0; w < W; ++w) {
+      const int c = (int)cnt[w];
+      before += (w < warp) ? c : 0;
+      live += c;
+      nonempty += (c > 0);
+    }
+    if (live == 0 || t >= max_steps) break;
+    rng = Key2{cnt[32], cnt[33]};
+    rng_current = true;
+    if (((live + 31) >> 5) < nonempty) {  // CTA-uniform: packing frees at least one warp
+      if (alive) {
+        const int slot = before + __popc(ab & ((1u << lane) - 1u));
+        uint32_t* x = s_x + slot;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          x[(2 * q) * T] = (uint32_t)s.occ[q];
+          x[(2 * q + 1) * T] = (uint32_t)(s.occ[q] >> 32);
+          x[(8 + q) * T] = s.pins[q];
+          x[(12 + 2 * q) * T] = (uint32_t)s.as[q];
+          x[(13 + 2 * q) * T] = (uint32_t)(s.as[q] >> 32);
+        }
+        x[20 * T] = (uint32_t)(s.cur & 0xFF) | ((uint32_t)(s.reward & 0xFF) << 8);
+        x[21 * T] = (uint32_t)len;
+        x[22 * T] = (uint32_t)gi;
+      }
+      __syncthreads();
+      alive = (int)threadIdx.x < live;
+      if (alive) {
+        const uint32_t* x = s_x + threadIdx.x;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          s.occ[q] = (uint64_t)x[(2 * q) * T] | ((uint64_t)x[(2 * q + 1) * T] << 32);
+          s.pins[q] = x[(8 + q) * T];
+          s.as[q] = (uint64_t)x[(12 + 2 * q) * T] | ((uint64_t)x[(13 + 2 * q) * T] << 32);
+        }
+        const uint32_t misc = x[20 * T];
+        s.cur = (int)(int8_t)(misc & 0xFFu);
+        s.reward = (int)(int8_t)((misc >> 8) & 0xFFu);
+        s.done = 0;
+        s.die = 0;
+        len = (int)x[21 * T];
+        gi = (int)x[22 * T];
+      }
+      // the next write to s_x happens after the next round's first barrier, i.e. after every read above
+    }
+    // ---- kPlayRound lockstep iterations
+    const int tend = min(t + kPlayRound, max_steps);
+    const uint32_t my = (uint32_t)(game_offset + cta_base + gi + 1);
+#pragma unroll 1
+    for (; t < tend; ++t) {
+      if (!__any_sync(FULL, alive)) { rng_current = false; break; }
+      const Key2 key = split_i(rng, my);  // split(rng, N+1)[j+1]   (game_agent.py:60 / evaluate_agent.py:336)
+      rng = split_i(rng, 0u);             // split(rng, N+1)[0]
+      int cp = 0;
+      uint32_t m = 0u;
+      if (alive) m = fast ? det_valid_mask4(R, g, s, cp) : madn_det_valid_mask(g, s);
+      s_key[lane] = make_uint2(key.a, key.b);
+      const int cnt = __popc(m);
+      int incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += v;
+      }
+      const int total = __shfl_sync(FULL, incl, 31);
+      {  // predicated stores, no find-first-set chain: 24 x (store, bump) under the mask bits
+        uint16_t* dst = s_items + (incl - cnt);
+#pragma unroll
+        for (int a = 0; a < 24; ++a) {
+          if ((m >> a) & 1u) *dst++ = (uint16_t)(lane_hi | (uint32_t)a);
+        }
+      }
+      __syncwarp();
+      for (int base = 0; base < total; base += 64) {
+        const int j0 = base + lane, j1 = j0 + 32;
+        if (base + 32 < total) {  // warp-uniform: two independent Threefry chains per lane
+          const uint32_t it0 = s_items[j0], it1 = (j1 < total) ? (uint32_t)s_items[j1] : 0u;
+          const uint32_t o0 = it0 >> 8, a0 = it0 & 0xFFu, o1 = it1 >> 8, a1 = it1 & 0xFFu;
+          const uint2 k0 = s_key[o0], k1 = s_key[o1];
+          const uint32_t v0 = bits_i(Key2{k0.x, k0.y}, a0) >> 9, v1 = bits_i(Key2{k1.x, k1.y}, a1) >> 9;
+          atomicMax(&s_best[o0], (v0 << 5) | (23u - a0));
+          if (j1 < total) atomicMax(&s_best[o1], (v1 << 5) | (23u - a1));
+        } else if (j0 < total) {
+          const uint32_t it0 = s_items[j0];
+          const uint32_t o0 = it0 >> 8, a0 = it0 & 0xFFu;
+          const uint2 k0 = s_key[o0];
+          const uint32_t v0 = bits_i(Key2{k0.x, k0.y}, a0) >> 9;
+          atomicMax(&s_best[o0], (v0 << 5) | (23u - a0));
+        }
+      }
+      __syncwarp();
+      if (alive) {
+        if (m) {
+          const int a = 23 - (int)(s_best[lane] & 31u);
+          if (fast) det_step4(R, s, cp, a);
+          else madn_det_step(g, s, a / 6, a % 6 + 1, m);  // map_action (deterministic_madn.py:469-479)
+        } else {
+          if (fast) det_no_step4(s);
+          else madn_det_no_step(g, s);
+        }
+        ++len;
+        ++steps_done;
+        if (s.done) {  // finished: write the game back now, the lane is free from here on
+          alive = false;
+          store_det_all(g, p, cta_base + gi, s);
+          if (game_len) game_len[cta_base + gi] = len;
+        }
+      }
+      s_best[lane] = 0u;
+      __syncwarp();
+    }
+    t = tend;
+  }
+  if (alive) {  // max_steps reached with the game still running
+    store_det_all(g, p, cta_base + gi, s);
+    if (game_len) game_len[cta_base + gi] = len;
+  }
+  if (total_steps) {
+    unsigned v = steps_done;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    if (lane == 0 && v) atomicAdd(total_steps, (unsigned long long)v);
+  }
+}
+
+// MuZero_det_MADN/game_agent.py:12-22 — the rule dict of every training / benchmark configuration gets its own program
+constexpr uint32_t kTrainRules = DOGSTEP_RULE_TEAMS | DOGSTEP_RULE_INITIAL_FREE_PIN | DOGSTEP_RULE_JUMP_IN_GOAL |
+                                 DOGSTEP_RULE_START_ON_1 | DOGSTEP_RULE_BONUS_TURN_ON_6;
+
 __global__ void __launch_bounds__(kThreads) k_madn_cls_throw_die(const __grid_constant__ MadnGeom g, MadnPtrs p, int64_t n,
                                                                  float* __restrict__ probs, int write_die, int only_active) {
   int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
@@ -695,8 +992,39 @@ int dogstep_madn_det_play_random(const dogstep_madn_det_state* s, int64_t n, con
   DS_PROLOGUE(det_ptrs)
   if (!host_rng_key || max_steps < 0) return DOGSTEP_ERR_INVALID_ARG;
   Key2 rng{host_rng_key[0], host_rng_key[1]};
-  k_madn_det_play_random<<<blocks_for(n, kThreads), kThreads, 0, st>>>(g, p, n, rng, game_offset, max_steps, game_len,
-                                                                       total_steps);
+  if (g.n == 4 && g.d == 10) {
+    // one CTA per SM when the games fit (config 2: 65,536 games -> 147 CTAs of 448), else CTAs of 512
+    static int sms = 0;
+    if (!sms) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      if (sms <= 0) sms = 148;
+    }
+    int64_t per = (n + sms - 1) / sms;
+    int threads = (int)(((per + 31) / 32) * 32);
+    if (threads > kPlayMaxThreads) threads = kPlayMaxThreads;
+    const size_t smem = play_smem_bytes(threads);
+    const unsigned blocks = blocks_for(n, threads);
+    const char* variant = getenv("DOGSTEP_PLAY_VARIANT");
+    if (variant && variant[0] == '2') {
+      if (g.rules == kTrainRules)
+        k_madn_det_play_fast<kTrainRules><<<blocks_for(n, 32), 32, 0, st>>>(g, p, n, rng, game_offset, max_steps, game_len, total_steps);
+      else
+        k_madn_det_play_fast<kRulesRuntime><<<blocks_for(n, 32), 32, 0, st>>>(g, p, n, rng, game_offset, max_steps, game_len, total_steps);
+    } else if (g.rules == kTrainRules) {
+      static bool attr_a = false;
+      if (!attr_a) { cudaFuncSetAttribute(k_madn_det_play_cta<kTrainRules>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)play_smem_bytes(kPlayMaxThreads)); attr_a = true; }
+      k_madn_det_play_cta<kTrainRules><<<blocks, threads, smem, st>>>(g, p, n, rng, game_offset, max_steps, game_len, total_steps);
+    } else {
+      static bool attr_b = false;
+      if (!attr_b) { cudaFuncSetAttribute(k_madn_det_play_cta<kRulesRuntime>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)play_smem_bytes(kPlayMaxThreads)); attr_b = true; }
+      k_madn_det_play_cta<kRulesRuntime><<<blocks, threads, smem, st>>>(g, p, n, rng, game_offset, max_steps, game_len, total_steps);
+    }
+  } else {
+    k_madn_det_play_random<<<blocks_for(n, kThreads), kThreads, 0, st>>>(g, p, n, rng, game_offset, max_steps, game_len,
+                                                                         total_steps);
+  }
   return check_launch();
 }
 
