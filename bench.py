@@ -319,7 +319,7 @@ def main():
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-                traffic = json.load(f).get("k_madn_det_play_random_dram_bytes_per_launch")
+                traffic = json.load(f).get("k_madn_det_play_cta_dram_bytes_per_launch")
         except Exception:
             pass
         line = {
@@ -333,10 +333,10 @@ def main():
             "e2e": {"value": all_e2e_steps / (e2e_max_ms / 1e3), "unit": "env_steps/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_max_ms / args.steps},
             "gpu_launches": 2 * args.steps,
-            "roofline": {"bound": "hbm", "kernel": "k_madn_det_play_random", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "k_madn_det_play_cta", "achieved": achieved, "peak": peak,
                          "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "algorithmic_bytes_per_env_step": BYTES_PER_STEP, "kernel_ms_per_launch": sum(play_ms) / args.steps,
-                         "note": "algorithmic bytes of the per-step reference dataflow; the persistent kernel keeps a game in registers, so it is integer-ALU bound, not HBM bound"},
+                         "note": "algorithmic bytes of the per-step reference dataflow; the persistent kernel keeps a game in registers (DRAM traffic = one read + one write of the state), so it is integer-issue bound, not HBM bound"},
             "clocks": clk,
         }
         if extras:

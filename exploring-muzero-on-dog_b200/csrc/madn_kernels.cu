@@ -417,119 +417,23 @@ __global__ void __launch_bounds__(kThreads) k_madn_det_play_random(const __grid_
   }
 }
 
-// Persistent lockstep loop, second generation (4 players, distance 10 — every configuration of the reference).
-// One warp per CTA (2,048 CTAs for 65,536 games spread evenly over the 148 SMs), one game per lane held in
-// registers for all its plies.  Per lockstep iteration:
-//   1. each lane derives its step key and the 24-bit legal mask (madn_fast.cuh: branch-free bit rows);
+// Persistent lockstep loop for 4 players, distance 10 — every configuration of the reference (the generic kernel above
+// covers other geometries).  One CTA per SM (up to 512 games), one game per lane held in registers.  Per iteration:
+//   1. each lane takes its step key and derives the 24-bit legal mask (madn_fast.cuh: branch-free bit rows);
 //   2. the (game, action) pairs of the warp are compacted into a shared list and dealt out evenly to the 32 lanes,
-//      two per lane and pass, so the Threefry calls — one per LEGAL action, the bulk of the arithmetic — are
-//      load-balanced and two independent chains are in flight per lane;
+//      two per lane and pass, so the Threefry calls — one per LEGAL action, half of all instructions — are
+//      load-balanced; the first pass also derives the NEXT iteration's step key (a third independent chain);
 //   3. the argmax of the categorical draw is a shared-memory atomicMax per game on (mantissa << 5 | 23 - action):
 //      largest 23-bit mantissa first, lowest action index on ties — jax.random.categorical's choice;
-//   4. each lane applies its game's move (incremental bitboard update).
-// A warp that loaded a non-canonical game (see madn_fast.cuh) runs the generic rules of madn_core.cuh instead.
-template <uint32_t CT>
-__global__ void __launch_bounds__(32) k_madn_det_play_fast(const __grid_constant__ MadnGeom g, MadnPtrs p, int64_t n, Key2 rng0,
-                                                           int64_t game_offset, int max_steps, int32_t* __restrict__ game_len,
-                                                           unsigned long long* __restrict__ total_steps) {
-  __shared__ uint16_t s_items[32 * 24];
-  __shared__ uint32_t s_best[32];
-  __shared__ uint2 s_key[32];
-  const int lane = threadIdx.x;
-  const uint32_t FULL = 0xFFFFFFFFu;
-  const int64_t i = (int64_t)blockIdx.x * 32 + lane;
-  const RuleSet<CT> R{g.rules};
-  int len = 0;
-  MadnRegs s;
-  bool alive = false, canon = true;
-  if (i < n) {
-    load_state<true>(g, p, i, s);
-    canon = is_canonical4(s, s.occ);
-    alive = !s.done;
-  }
-  const bool fast = !__any_sync(FULL, !canon);
-  Key2 rng = rng0;
-  const uint32_t my = (uint32_t)(game_offset + i + 1);
-  const uint32_t lane_hi = (uint32_t)lane << 8;
-  s_best[lane] = 0u;
-  __syncwarp();
-#pragma unroll 1
-  for (int t = 0; t < max_steps; ++t) {
-    if (!__any_sync(FULL, alive)) break;
-    const Key2 key = split_i(rng, my);  // split(rng, N+1)[j+1]   (game_agent.py:60 / evaluate_agent.py:336)
-    rng = split_i(rng, 0u);             // split(rng, N+1)[0]
-    int cp = 0;
-    uint32_t m = 0u;
-    if (alive) m = fast ? det_valid_mask4(R, g, s, cp) : madn_det_valid_mask(g, s);
-    s_key[lane] = make_uint2(key.a, key.b);
-    // warp-wide compaction of the (lane, action) pairs
-    const int cnt = __popc(m);
-    int incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(FULL, incl, o);
-      if (lane >= o) incl += v;
-    }
-    const int total = __shfl_sync(FULL, incl, 31);
-    {  // predicated stores, no find-first-set chain: 24 x (store, bump) under the mask bits
-      uint16_t* dst = s_items + (incl - cnt);
-#pragma unroll
-      for (int a = 0; a < 24; ++a) {
-        if ((m >> a) & 1u) *dst++ = (uint16_t)(lane_hi | (uint32_t)a);
-      }
-    }
-    __syncwarp();
-    for (int base = 0; base < total; base += 64) {
-      const int j0 = base + lane, j1 = j0 + 32;
-      if (base + 32 < total) {  // warp-uniform: two independent Threefry chains per lane
-        const uint32_t it0 = s_items[j0], it1 = (j1 < total) ? (uint32_t)s_items[j1] : 0u;
-        const uint32_t o0 = it0 >> 8, a0 = it0 & 0xFFu, o1 = it1 >> 8, a1 = it1 & 0xFFu;
-        const uint2 k0 = s_key[o0], k1 = s_key[o1];
-        const uint32_t v0 = bits_i(Key2{k0.x, k0.y}, a0) >> 9, v1 = bits_i(Key2{k1.x, k1.y}, a1) >> 9;
-        atomicMax(&s_best[o0], (v0 << 5) | (23u - a0));
-        if (j1 < total) atomicMax(&s_best[o1], (v1 << 5) | (23u - a1));
-      } else if (j0 < total) {
-        const uint32_t it0 = s_items[j0];
-        const uint32_t o0 = it0 >> 8, a0 = it0 & 0xFFu;
-        const uint2 k0 = s_key[o0];
-        const uint32_t v0 = bits_i(Key2{k0.x, k0.y}, a0) >> 9;
-        atomicMax(&s_best[o0], (v0 << 5) | (23u - a0));
-      }
-    }
-    __syncwarp();
-    if (alive) {
-      if (m) {
-        const int a = 23 - (int)(s_best[lane] & 31u);
-        if (fast) det_step4(R, s, cp, a);
-        else madn_det_step(g, s, a / 6, a % 6 + 1, m);  // map_action (deterministic_madn.py:469-479)
-      } else {
-        if (fast) det_no_step4(s);
-        else madn_det_no_step(g, s);
-      }
-      ++len;
-      alive = !s.done;
-    }
-    s_best[lane] = 0u;
-    __syncwarp();
-  }
-  if (i < n) {
-    store_det_all(g, p, i, s);
-    if (game_len) game_len[i] = len;
-  }
-  if (total_steps) {
-    unsigned v = (unsigned)len;
-#pragma unroll
-    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-    if (lane == 0 && v) atomicAdd(total_steps, (unsigned long long)v);
-  }
-}
-
-// Third generation: the same per-warp pooled iteration, but one CTA per SM (up to 512 games) with a compaction point
-// every kPlayRound lockstep iterations.  Games end at different plies (mean 403, max ~850 in config 2), so a warp that
-// keeps its 32 games to the end idles 30 % of its lane-iterations; at a compaction point the live games of the CTA are
-// packed into the lowest warps through shared memory (23 words per game) and the emptied warps only wait at the barriers.
-// A finished game is written back at once by the lane that holds it.  The key chain value travels through shared memory
-// because a warp that ran empty and is refilled has not advanced it.
+//   4. each lane applies its game's move (incremental bitboard update); a finished game is written back at once.
+// Games end at different plies (mean 403, max ~850 in config 2), so a warp that kept its 32 games to the end would idle
+// 30 % of its lane-iterations: every kPlayRound iterations the live games of the CTA are packed into the lowest warps
+// through shared memory (23 words per game) and the emptied warps only wait at the barriers.  The key chain value
+// travels through shared memory too, because a warp that ran empty and is refilled has not advanced it.
+// A CTA that loaded a non-canonical game (see madn_fast.cuh) runs the generic rules of madn_core.cuh instead.
+#ifdef DOGSTEP_TRACE
+__device__ unsigned long long g_play_trace[128];
+#endif
 constexpr int kPlayRound = 32;
 constexpr int kPlayMaxThreads = 512;
 constexpr int kXWords = 23;  // occ 8, pins 4, action set 8, cur|reward, len, game index
@@ -542,7 +446,7 @@ template <uint32_t CT>
 __global__ void __launch_bounds__(kPlayMaxThreads) k_madn_det_play_cta(const __grid_constant__ MadnGeom g, MadnPtrs p, int64_t n,
                                                                       Key2 rng0, int64_t game_offset, int max_steps,
                                                                       int32_t* __restrict__ game_len,
-                                                                      unsigned long long* __restrict__ total_steps) {
+                                                                      unsigned long long* __restrict__ total_steps, int round_len) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int T = blockDim.x, W = T >> 5;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -589,6 +493,14 @@ __global__ void __launch_bounds__(kPlayMaxThreads) k_madn_det_play_cta(const __g
       live += c;
       nonempty += (c > 0);
     }
+#ifdef DOGSTEP_TRACE
+    if (blockIdx.x == 0 && threadIdx.x == 0 && round <= 64) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+      g_play_trace[2 * (round - 1)] = now;
+      g_play_trace[2 * (round - 1) + 1] = (unsigned long long)live | ((unsigned long long)nonempty << 32);
+    }
+#endif
     if (live == 0 || t >= max_steps) break;
     rng = Key2{cnt[32], cnt[33]};
     rng_current = true;
@@ -629,13 +541,13 @@ __global__ void __launch_bounds__(kPlayMaxThreads) k_madn_det_play_cta(const __g
       // the next write to s_x happens after the next round's first barrier, i.e. after every read above
     }
     // ---- kPlayRound lockstep iterations
-    const int tend = min(t + kPlayRound, max_steps);
+    const int tend = min(t + round_len, max_steps);
     const uint32_t my = (uint32_t)(game_offset + cta_base + gi + 1);
+    Key2 key = split_i(rng, my);  // split(rng, N+1)[j+1]   (game_agent.py:60 / evaluate_agent.py:336)
 #pragma unroll 1
     for (; t < tend; ++t) {
       if (!__any_sync(FULL, alive)) { rng_current = false; break; }
-      const Key2 key = split_i(rng, my);  // split(rng, N+1)[j+1]   (game_agent.py:60 / evaluate_agent.py:336)
-      rng = split_i(rng, 0u);             // split(rng, N+1)[0]
+      const Key2 rng_next = split_i(rng, 0u);  // split(rng, N+1)[0]
       int cp = 0;
       uint32_t m = 0u;
       if (alive) m = fast ? det_valid_mask4(R, g, s, cp) : madn_det_valid_mask(g, s);
@@ -656,7 +568,19 @@ __global__ void __launch_bounds__(kPlayMaxThreads) k_madn_det_play_cta(const __g
         }
       }
       __syncwarp();
-      for (int base = 0; base < total; base += 64) {
+      Key2 key_next;
+      {  // first pass, peeled: items lane and lane + 32 plus NEXT iteration's step key — three independent Threefry
+         // chains per lane, and the key derivation is off the critical path of the following iteration
+        const bool h0 = lane < total, h1 = lane + 32 < total;
+        const uint32_t it0 = h0 ? (uint32_t)s_items[lane] : 0u, it1 = h1 ? (uint32_t)s_items[lane + 32] : 0u;
+        const uint32_t o0 = it0 >> 8, a0 = it0 & 0xFFu, o1 = it1 >> 8, a1 = it1 & 0xFFu;
+        const uint2 k0 = s_key[o0], k1 = s_key[o1];
+        const uint32_t v0 = bits_i(Key2{k0.x, k0.y}, a0) >> 9, v1 = bits_i(Key2{k1.x, k1.y}, a1) >> 9;
+        key_next = split_i(rng_next, my);
+        if (h0) atomicMax(&s_best[o0], (v0 << 5) | (23u - a0));
+        if (h1) atomicMax(&s_best[o1], (v1 << 5) | (23u - a1));
+      }
+      for (int base = 64; base < total; base += 64) {
         const int j0 = base + lane, j1 = j0 + 32;
         if (base + 32 < total) {  // warp-uniform: two independent Threefry chains per lane
           const uint32_t it0 = s_items[j0], it1 = (j1 < total) ? (uint32_t)s_items[j1] : 0u;
@@ -692,6 +616,8 @@ __global__ void __launch_bounds__(kPlayMaxThreads) k_madn_det_play_cta(const __g
         }
       }
       s_best[lane] = 0u;
+      key = key_next;
+      rng = rng_next;
       __syncwarp();
     }
     t = tend;
@@ -994,37 +920,37 @@ int dogstep_madn_det_play_random(const dogstep_madn_det_state* s, int64_t n, con
   Key2 rng{host_rng_key[0], host_rng_key[1]};
   if (g.n == 4 && g.d == 10) {
     // one CTA per SM when the games fit (config 2: 65,536 games -> 147 CTAs of 448), else CTAs of 512
-    static int sms = 0;
-    if (!sms) {
-      int dev = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-      if (sms <= 0) sms = 148;
-    }
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
     int64_t per = (n + sms - 1) / sms;
     int threads = (int)(((per + 31) / 32) * 32);
     if (threads > kPlayMaxThreads) threads = kPlayMaxThreads;
     const size_t smem = play_smem_bytes(threads);
     const unsigned blocks = blocks_for(n, threads);
-    const char* variant = getenv("DOGSTEP_PLAY_VARIANT");
-    if (variant && variant[0] == '2') {
-      if (g.rules == kTrainRules)
-        k_madn_det_play_fast<kTrainRules><<<blocks_for(n, 32), 32, 0, st>>>(g, p, n, rng, game_offset, max_steps, game_len, total_steps);
-      else
-        k_madn_det_play_fast<kRulesRuntime><<<blocks_for(n, 32), 32, 0, st>>>(g, p, n, rng, game_offset, max_steps, game_len, total_steps);
-    } else if (g.rules == kTrainRules) {
-      static bool attr_a = false;
-      if (!attr_a) { cudaFuncSetAttribute(k_madn_det_play_cta<kTrainRules>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)play_smem_bytes(kPlayMaxThreads)); attr_a = true; }
-      k_madn_det_play_cta<kTrainRules><<<blocks, threads, smem, st>>>(g, p, n, rng, game_offset, max_steps, game_len, total_steps);
+    const int round_len = kPlayRound;
+    if (g.rules == kTrainRules) {
+      cudaFuncSetAttribute(k_madn_det_play_cta<kTrainRules>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      k_madn_det_play_cta<kTrainRules><<<blocks, threads, smem, st>>>(g, p, n, rng, game_offset, max_steps, game_len, total_steps, round_len);
     } else {
-      static bool attr_b = false;
-      if (!attr_b) { cudaFuncSetAttribute(k_madn_det_play_cta<kRulesRuntime>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)play_smem_bytes(kPlayMaxThreads)); attr_b = true; }
-      k_madn_det_play_cta<kRulesRuntime><<<blocks, threads, smem, st>>>(g, p, n, rng, game_offset, max_steps, game_len, total_steps);
+      cudaFuncSetAttribute(k_madn_det_play_cta<kRulesRuntime>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      k_madn_det_play_cta<kRulesRuntime><<<blocks, threads, smem, st>>>(g, p, n, rng, game_offset, max_steps, game_len, total_steps, round_len);
     }
   } else {
     k_madn_det_play_random<<<blocks_for(n, kThreads), kThreads, 0, st>>>(g, p, n, rng, game_offset, max_steps, game_len,
                                                                          total_steps);
   }
+#ifdef DOGSTEP_TRACE
+  if (getenv("DOGSTEP_PLAY_TRACE")) {
+    cudaStreamSynchronize(st);
+    unsigned long long h[128];
+    cudaMemcpyFromSymbol(h, g_play_trace, sizeof(h));
+    for (int r = 0; r < 64 && h[2 * r]; ++r)
+      fprintf(stderr, "round %2d (%d)  +%8.1f us  live %5llu  warps %3llu\n", r, r, (h[2 * r] - h[0]) / 1e3,
+              h[2 * r + 1] & 0xFFFFFFFFull, h[2 * r + 1] >> 32);
+  }
+#endif
   return check_launch();
 }
 

@@ -2,7 +2,9 @@
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from exploring_muzero_on_dog_b200 import jaxrand
+from exploring_muzero_on_dog_b200 import jaxrand, _lib
+if os.environ.get('DOGSTEP_LIB'):
+    _lib.LIB_PATH = os.environ['DOGSTEP_LIB']  # instrumented build (scripts/microbench)
 from exploring_muzero_on_dog_b200.MADN import deterministic_madn as dm
 R = dict(enable_teams=True, enable_initial_free_pin=True, enable_circular_board=False, enable_friendly_fire=False,
          enable_start_blocking=False, enable_jump_in_goal_area=True, enable_start_on_1=True,
