@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 #include "../../include/dogstep.h"
 #include "jaxrand.cuh"
+#include "hostdev.cuh"
 
 namespace dogstep {
 
@@ -80,13 +81,13 @@ struct DogS {
 
 #define DG_RULE(g, bit) (((g).rules & (bit)) != 0u)
 
-__device__ __forceinline__ int d_fdiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
-__device__ __forceinline__ int d_fmod(int a, int b) { int r = a % b; return r < 0 ? r + b : r; }
-__device__ __forceinline__ int d_gidx(int i, int size) { i = (i < 0) ? i + size : i; return min(max(i, 0), size - 1); }
-__device__ __forceinline__ int d_sidx(int i, int size) { i = (i < 0) ? i + size : i; return (i < 0 || i >= size) ? -1 : i; }
+DS_FN int d_fdiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+DS_FN int d_fmod(int a, int b) { int r = a % b; return r < 0 ? r + b : r; }
+DS_FN int d_gidx(int i, int size) { i = (i < 0) ? i + size : i; return min(max(i, 0), size - 1); }
+DS_FN int d_sidx(int i, int size) { i = (i < 0) ? i + size : i; return (i < 0 || i >= size) ? -1 : i; }
 
 // lexicographic (a,b,c) enumeration of the 120 splits of 7 (utility_funcs.py:4-21) -> split k
-__device__ __forceinline__ void dog_dist_of(int k, int d[4]) {
+DS_FN void dog_dist_of(int k, int d[4]) {
   // number of (b,c) with b+c <= 7-a is T(8-a) = (8-a)(9-a)/2; cumulative over a
   int a = 0, rem = k;
   while (true) {
@@ -105,7 +106,7 @@ __device__ __forceinline__ void dog_dist_of(int k, int d[4]) {
   d[0] = a; d[1] = b; d[2] = rem; d[3] = 7 - a - b - rem;
 }
 
-__device__ __forceinline__ void dog_set_pins_on_board(const DogGeom& g, const int32_t pins[4][4], int8_t* board) {
+DS_FN void dog_set_pins_on_board(const DogGeom& g, const int32_t pins[4][4], int8_t* board) {
   for (int k = 0; k < g.total; ++k) board[k] = -1;
   for (int p = 0; p < g.n; ++p)
     for (int i = 0; i < 4; ++i) {
@@ -114,7 +115,7 @@ __device__ __forceinline__ void dog_set_pins_on_board(const DogGeom& g, const in
     }
 }
 
-__device__ __forceinline__ int dog_player_done(const DogGeom& g, const int8_t* board, int player) {
+DS_FN int dog_player_done(const DogGeom& g, const int8_t* board, int player) {
   if (player >= g.n) return 0;
   int p = d_gidx(player, g.n);
   for (int k = 0; k < 4; ++k)
@@ -122,7 +123,7 @@ __device__ __forceinline__ int dog_player_done(const DogGeom& g, const int8_t* b
   return 1;
 }
 
-__device__ __forceinline__ uint32_t dog_winner_mask(const DogGeom& g, const int8_t* board) {
+DS_FN uint32_t dog_winner_mask(const DogGeom& g, const int8_t* board) {
   uint32_t pd = 0;
   for (int p = 0; p < 4; ++p) pd |= (uint32_t)dog_player_done(g, board, p) << p;
   if (DG_RULE(g, DOGSTEP_RULE_TEAMS)) {
@@ -133,27 +134,27 @@ __device__ __forceinline__ uint32_t dog_winner_mask(const DogGeom& g, const int8
   return pd;
 }
 
-__device__ __forceinline__ int dog_mover(const DogGeom& g, const DogS& s) {
+DS_FN int dog_mover(const DogGeom& g, const DogS& s) {
   int pid = s.cur;
   int cp = (DG_RULE(g, DOGSTEP_RULE_TEAMS) && dog_player_done(g, s.board, pid)) ? ((pid + 2) & 3) : pid;
   return d_gidx(cp, g.n);
 }
 
-__device__ __forceinline__ int dog_in_goal(const DogGeom& g, int cp, int pos) { return pos >= g.goal0[cp] && pos <= g.goal0[cp] + 3; }
+DS_FN int dog_in_goal(const DogGeom& g, int cp, int pos) { return pos >= g.goal0[cp] && pos <= g.goal0[cp] + 3; }
 
-__device__ __forceinline__ int dog_path_clear(const DogGeom& g, const int8_t* board, int cp, int s, int e) {
+DS_FN int dog_path_clear(const DogGeom& g, const int8_t* board, int cp, int s, int e) {
   for (int k = 0; k < 4; ++k)
     if (s < k && k < e && board[g.goal0[cp] + k] == cp) return 0;
   return 1;
 }
 
-__device__ __forceinline__ int dog_pins_on_start(const DogGeom& g, const int8_t* board, int q) {
+DS_FN int dog_pins_on_start(const DogGeom& g, const int8_t* board, int q) {
   q = d_gidx(q, g.n);
   return board[g.start[q]] == q;
 }
 
 // val_swap: result[i][cell] = pin_ok bit i & cell_ok bit cell
-__device__ __forceinline__ void dog_val_swap(const DogGeom& g, const DogS& s, int cp, uint32_t& pin_ok, uint64_t& cell_ok) {
+DS_FN void dog_val_swap(const DogGeom& g, const DogS& s, int cp, uint32_t& pin_ok, uint64_t& cell_ok) {
   const int sb = DG_RULE(g, DOGSTEP_RULE_START_BLOCKING);
   uint64_t ok = 0;
   for (int k = 0; k < g.total; ++k) ok |= (uint64_t)(s.board[k] != -1 && s.board[k] != cp) << k;
@@ -178,7 +179,7 @@ __device__ __forceinline__ void dog_val_swap(const DogGeom& g, const DogS& s, in
 }
 
 // val_action_normal_move for ONE pin
-__device__ __forceinline__ int dog_val_normal(const DogGeom& g, const DogS& s, int cp, int i, int move) {
+DS_FN int dog_val_normal(const DogGeom& g, const DogS& s, int cp, int i, int move) {
   const int8_t* board = s.board;
   const int mts = DG_RULE(g, DOGSTEP_RULE_MUST_TRAVERSE_START), sb = DG_RULE(g, DOGSTEP_RULE_START_BLOCKING);
   const int circ = DG_RULE(g, DOGSTEP_RULE_CIRCULAR_BOARD), jump = DG_RULE(g, DOGSTEP_RULE_JUMP_IN_GOAL);
@@ -207,7 +208,7 @@ __device__ __forceinline__ int dog_val_normal(const DogGeom& g, const DogS& s, i
 }
 
 // val_neg_move for ONE pin
-__device__ __forceinline__ int dog_val_neg(const DogGeom& g, const DogS& s, int cp, int i, int move) {
+DS_FN int dog_val_neg(const DogGeom& g, const DogS& s, int cp, int i, int move) {
   const int8_t* board = s.board;
   int pos = s.pins[cp][i];
   int moved = pos + move, fitted = d_fmod(moved, g.bs);
@@ -221,11 +222,11 @@ __device__ __forceinline__ int dog_val_neg(const DogGeom& g, const DogS& s, int 
   return result;
 }
 
-__device__ __forceinline__ int d_sgn(int v) { return (v > 0) - (v < 0); }
+DS_FN int d_sgn(int v) { return (v > 0) - (v < 0); }
 
 // own-goal-lane occupancy of tmp_board (dog.py:454-455, 934-935): the board with cp's in-goal pins already
 // at their moved cells.  Only cp's lane cells matter for the path check, so 4 bits suffice.
-__device__ __forceinline__ uint32_t dog_hot7_tmp_lane(const DogGeom& g, const DogS& s, int cp, const int moved[4]) {
+DS_FN uint32_t dog_hot7_tmp_lane(const DogGeom& g, const DogS& s, int cp, const int moved[4]) {
   // set_pins_on_board: later players overwrite earlier ones on the same cell
   const int g0 = g.goal0[cp];
   uint32_t lane = 0;
@@ -242,14 +243,14 @@ __device__ __forceinline__ uint32_t dog_hot7_tmp_lane(const DogGeom& g, const Do
   return lane;
 }
 
-__device__ __forceinline__ int d_lane_clear(uint32_t lane, int s, int e) {
+DS_FN int d_lane_clear(uint32_t lane, int s, int e) {
   for (int k = 0; k < 4; ++k)
     if (s < k && k < e && ((lane >> k) & 1u)) return 0;
   return 1;
 }
 
 // val_action_7 -> scalar
-__device__ __forceinline__ int dog_val_7(const DogGeom& g, const DogS& s, int cp, const int dist[4]) {
+DS_FN int dog_val_7(const DogGeom& g, const DogS& s, int cp, const int dist[4]) {
   const int8_t* board = s.board;
   const int mts = DG_RULE(g, DOGSTEP_RULE_MUST_TRAVERSE_START), sb = DG_RULE(g, DOGSTEP_RULE_START_BLOCKING);
   const int circ = DG_RULE(g, DOGSTEP_RULE_CIRCULAR_BOARD), jump = DG_RULE(g, DOGSTEP_RULE_JUMP_IN_GOAL);
@@ -291,7 +292,7 @@ __device__ __forceinline__ int dog_val_7(const DogGeom& g, const DogS& s, int cp
 }
 
 // ---- legal mask, lane-parallel: base action b in [0, half) -> validity ignoring the card in hand ----
-__device__ __forceinline__ int dog_base_action_valid(const DogGeom& g, const DogS& s, int cp, int b, uint32_t pin_ok,
+DS_FN int dog_base_action_valid(const DogGeom& g, const DogS& s, int cp, int b, uint32_t pin_ok,
                                                       uint64_t cell_ok, int& card) {
   const int pxb = 4 * g.total;
   if (b < pxb) {
@@ -358,13 +359,13 @@ __device__ __forceinline__ void dog_build_mask(const DogGeom& g, DogS& s, int la
 }
 
 // ---- state transition of one action: lane 0 only -----------------------------------------------------
-__device__ __forceinline__ void dog_finish_substep(const DogGeom& g, const DogS& s, int cp, int invalid, int& reward, int& done) {
+DS_FN void dog_finish_substep(const DogGeom& g, const DogS& s, int cp, int invalid, int& reward, int& done) {
   uint32_t w = dog_winner_mask(g, s.board);
   done = s.done || (w != 0u);
   reward = s.done ? 0 : (invalid ? -1 : (int)((w >> cp) & 1u));
 }
 
-__device__ __forceinline__ void dog_capture_and_place(const DogGeom& g, DogS& s, int cp, int pin, int new_pos) {
+DS_FN void dog_capture_and_place(const DogGeom& g, DogS& s, int cp, int pin, int new_pos) {
   int pin_at_pos = s.board[d_gidx(new_pos, g.total)];
   if (pin_at_pos != -1 && (pin_at_pos != cp || DG_RULE(g, DOGSTEP_RULE_FRIENDLY_FIRE))) {
     int q = d_gidx(pin_at_pos, g.n);
@@ -375,7 +376,7 @@ __device__ __forceinline__ void dog_capture_and_place(const DogGeom& g, DogS& s,
   dog_set_pins_on_board(g, s.pins, s.board);
 }
 
-__device__ inline void dog_step_swap(const DogGeom& g, DogS& s, int pin_idx, int swap_pos, int& reward, int& done) {
+__host__ __device__ inline void dog_step_swap(const DogGeom& g, DogS& s, int pin_idx, int swap_pos, int& reward, int& done) {
   int cp = dog_mover(g, s);
   uint32_t pin_ok;
   uint64_t cell_ok;
@@ -394,7 +395,7 @@ __device__ inline void dog_step_swap(const DogGeom& g, DogS& s, int pin_idx, int
   dog_finish_substep(g, s, cp, invalid, reward, done);
 }
 
-__device__ inline void dog_step_normal(const DogGeom& g, DogS& s, int pin_in, int move, int& reward, int& done) {
+__host__ __device__ inline void dog_step_normal(const DogGeom& g, DogS& s, int pin_in, int move, int& reward, int& done) {
   int cp = dog_mover(g, s);
   int pin = d_gidx(pin_in, 4);
   int invalid = !dog_val_normal(g, s, cp, pin, move);
@@ -418,7 +419,7 @@ __device__ inline void dog_step_normal(const DogGeom& g, DogS& s, int pin_in, in
   dog_finish_substep(g, s, cp, invalid, reward, done);
 }
 
-__device__ inline void dog_step_neg(const DogGeom& g, DogS& s, int pin_in, int move, int& reward, int& done) {
+__host__ __device__ inline void dog_step_neg(const DogGeom& g, DogS& s, int pin_in, int move, int& reward, int& done) {
   int cp = dog_mover(g, s);
   int pin = d_gidx(pin_in, 4);
   int invalid = !dog_val_neg(g, s, cp, pin, move);
@@ -427,13 +428,13 @@ __device__ inline void dog_step_neg(const DogGeom& g, DogS& s, int pin_in, int m
 }
 
 // get_path_matrix membership (utility_funcs.py:256-277)
-__device__ __forceinline__ int d_giv(int si, int ei, int idx, int same_area) {
+DS_FN int d_giv(int si, int ei, int idx, int same_area) {
   if (si == -1 || ei == -1 || (same_area && si == ei)) return 0;
   if (si <= ei) return idx >= si && idx <= ei;
   return idx >= si || idx <= ei;
 }
 
-__device__ inline void dog_step_hot7(const DogGeom& g, DogS& s, const int dist[4], int& reward, int& done) {
+__host__ __device__ inline void dog_step_hot7(const DogGeom& g, DogS& s, const int dist[4], int& reward, int& done) {
   int cp = dog_mover(g, s);
   int invalid = !dog_val_7(g, s, cp, dist);
   if (!invalid) {
@@ -488,7 +489,7 @@ __device__ inline void dog_step_hot7(const DogGeom& g, DogS& s, const int dist[4
 }
 
 // first seat after `from` that still holds cards; all_empty = all(hand_cards == 0)
-__device__ __forceinline__ int dog_next_with_cards(const DogGeom& g, const DogS& s, int from, int& all_empty, int& any_left) {
+DS_FN int dog_next_with_cards(const DogGeom& g, const DogS& s, int from, int& all_empty, int& any_left) {
   int sums[4];
   int nz = 0, pos = 0;
   for (int q = 0; q < g.n; ++q) {
@@ -509,7 +510,7 @@ __device__ __forceinline__ int dog_next_with_cards(const DogGeom& g, const DogS&
 }
 
 // map_action_to_move (dog.py:1134-1196)
-__device__ __forceinline__ void dog_map_action_to_move(const DogGeom& g, int action, int mv[6]) {
+DS_FN void dog_map_action_to_move(const DogGeom& g, int action, int mv[6]) {
   const int pxb = 4 * g.total;
   int is_joker = (action - g.half) < 0;
   int act = d_fmod(action, g.half);
@@ -534,7 +535,7 @@ __device__ __forceinline__ void dog_map_action_to_move(const DogGeom& g, int act
   mv[2] = d[0]; mv[3] = d[1]; mv[4] = d[2]; mv[5] = d[3];
 }
 
-__device__ __forceinline__ int dog_map_action_to_card(const int mv[6]) {
+DS_FN int dog_map_action_to_card(const int mv[6]) {
   int sum = mv[2] + mv[3] + mv[4] + mv[5];
   if (mv[0] == 1) return 0;
   if (mv[1] == 1) return 1;

@@ -7,6 +7,7 @@
 #include "common.cuh"
 #include "jaxrand.cuh"
 #include "dog_core.cuh"
+#include "dog_fast.cuh"
 
 namespace dogstep {
 
@@ -47,6 +48,20 @@ __device__ __forceinline__ void dog_load(const DogGeom& g, const DogPtrs& p, int
     s.hand_size = p.hand_size[i];
   }
   __syncwarp();
+  // canonical 4-player / distance-10 records take the bitboard rules of dog_fast.cuh (warp-uniform flag)
+  const bool fast = g.n == 4 && g.d == 10 && dog4_canonical_warp(s, lane);
+  if (lane == 0) s.scratch[7] = fast;
+  __syncwarp();
+}
+
+__device__ __forceinline__ void dog_build_mask_any(const DogGeom& g, DogS& s, int lane) {
+  if (s.scratch[7]) dog4_build_mask(dg4_rules(g.rules), s, lane);
+  else dog_build_mask(g, s, lane);
+}
+
+__device__ __forceinline__ void dog_env_step_any(const DogGeom& g, DogS& s, int lane, int action, int& r, int& d) {
+  if (s.scratch[7]) dog4_env_step(dg4_rules(g.rules), g, s, lane, action, r, d);
+  else dog_env_step(g, s, lane, action, r, d);
 }
 
 __device__ __forceinline__ void dog_store(const DogGeom& g, const DogPtrs& p, int64_t i, const DogS& s, int lane) {
@@ -150,7 +165,7 @@ __global__ void __launch_bounds__(kDogThreads) k_dog_valid_actions(const __grid_
   DOG_KERNEL_PROLOGUE
   if (i >= n) return;
   dog_load(g, p, i, s, lane);
-  dog_build_mask(g, s, lane);
+  dog_build_mask_any(g, s, lane);
   uint8_t* out = mask + i * g.num_actions;
   for (int a = lane; a < g.num_actions; a += 32) out[a] = (uint8_t)((s.mask[a >> 5] >> (a & 31)) & 1u);
 }
@@ -162,7 +177,7 @@ __global__ void __launch_bounds__(kDogThreads) k_dog_step(const __grid_constant_
   if (i >= n) return;
   dog_load(g, p, i, s, lane);
   int r, d;
-  dog_env_step(g, s, lane, action[i], r, d);
+  dog_env_step_any(g, s, lane, action[i], r, d);
   dog_store(g, p, i, s, lane);
   if (lane == 0) {
     if (reward) reward[i] = (int8_t)r;
@@ -219,11 +234,11 @@ __global__ void __launch_bounds__(kDogThreads) k_dog_substep(const __grid_consta
 }
 
 __device__ __forceinline__ void dog_random_turn(const DogGeom& g, DogS& s, int lane, Key2 key) {
-  dog_build_mask(g, s, lane);
+  dog_build_mask_any(g, s, lane);
   int a = dog_categorical(g, s, lane, key);
   if (a >= 0) {
     int r, d;
-    dog_env_step(g, s, lane, a, r, d);
+    dog_env_step_any(g, s, lane, a, r, d);
   } else {
     dog_no_step(g, s, lane);
   }

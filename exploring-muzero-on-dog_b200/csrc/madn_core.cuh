@@ -15,6 +15,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 #include "../../include/dogstep.h"
+#include "hostdev.cuh"
 
 namespace dogstep {
 
@@ -60,18 +61,6 @@ struct MadnRegs {
 };
 
 #define DS_RULE(g, bit) (((g).rules & (bit)) != 0u)
-
-// rules are plain integer logic: callable from the host too, so tests can run them against the oracle on the CPU
-#define DS_FN __host__ __device__ __forceinline__
-
-DS_FN int ds_popcll(uint64_t v) {
-#ifdef __CUDA_ARCH__
-  return __popcll(v);
-#else
-  return __builtin_popcountll(v);
-#endif
-}
-DS_FN uint32_t ds_min_u32(uint32_t a, uint32_t b) { return a < b ? a : b; }
 
 template <typename T>
 DS_FN T pick4(const T (&a)[4], int i) {
