@@ -65,7 +65,7 @@ inline int dog_make_geom(const dogstep_madn_cfg* cfg, DogGeom* g) {
 }
 
 // per-warp shared record
-struct DogS {
+struct alignas(16) DogS {
   int32_t pins[4][4];
   int8_t board[64];
   int8_t hands[4][16];
@@ -77,6 +77,7 @@ struct DogS {
   uint32_t sortkey[128];
   uint16_t items[2 * (4 * (13 + 64) + 120) + kNCard + 2];
   int scratch[8];
+  uint64_t pbits[4];  // bit c of pbits[p]: a pin of player p stands on cell c (kept by the dog_fast.cuh path)
 };
 
 #define DG_RULE(g, bit) (((g).rules & (bit)) != 0u)
@@ -319,7 +320,7 @@ DS_FN int dog_base_action_valid(const DogGeom& g, const DogS& s, int cp, int b, 
 }
 
 // valid_actions (dog.py:693-711) into s.mask (bit a = action a legal).  All 32 lanes must call it.
-__device__ __forceinline__ void dog_build_mask(const DogGeom& g, DogS& s, int lane) {
+__device__ __noinline__ void dog_build_mask(const DogGeom& g, DogS& s, int lane) {
   const uint32_t FULL = 0xFFFFFFFFu;
   for (int w = lane; w < kDogMaskWords; w += 32) s.mask[w] = 0u;
   __syncwarp();
@@ -544,7 +545,7 @@ DS_FN int dog_map_action_to_card(const int mv[6]) {
 }
 
 // distribute_cards (dog.py:201-298).  All 32 lanes must call it.
-__device__ inline void dog_distribute_cards(const DogGeom& g, DogS& s, int lane) {
+__device__ __noinline__ void dog_distribute_cards(const DogGeom& g, DogS& s, int lane) {
   const int n = g.n, quantity = s.hand_size;
   __syncwarp();
   if (lane == 0) {
@@ -575,6 +576,7 @@ __device__ inline void dog_distribute_cards(const DogGeom& g, DogS& s, int lane)
     uint32_t mine = s.sortkey[j];
     if (mine != 0xFFFFFFFFu) {
       int rank = 0;
+#pragma unroll 8
       for (int k = 0; k < 120; ++k) rank += (s.sortkey[k] < mine);
       if (rank < need) {
         int c = 0, acc = s.deck[0];
@@ -606,32 +608,37 @@ __device__ inline void dog_distribute_cards(const DogGeom& g, DogS& s, int lane)
   __syncwarp();
 }
 
+// env_step_swap_phase (dog.py:1078-1114) on the staged record: scalar, no board access
+DS_FN void dog_swap_phase(const DogGeom& g, DogS& s, int action) {
+  int card_idx = action - g.play_actions;
+  int cur = s.cur;
+  int cs = d_sidx(card_idx, kNCard), row = d_sidx(cur, g.n);
+  if (cs >= 0 && row >= 0) s.hands[row][cs] = (int8_t)(s.hands[row][cs] - 1);
+  int sc = d_sidx(cur, 4);
+  if (sc >= 0) s.swap_choices[sc] = (int8_t)card_idx;
+  int next = d_fmod(cur + 1, g.n);
+  if (next == s.round_starter) {
+    const int partners[4] = {2, 3, 0, 1};
+    for (int q = 0; q < g.n; ++q) {  // execute_team_swap (:1065-1075)
+      int rc = s.swap_choices[partners[q]];
+      if (rc >= 0 && rc < kNCard) s.hands[q][rc] = (int8_t)(s.hands[q][rc] + 1);
+    }
+    s.phase = 0;
+    s.cur = s.round_starter;
+    for (int q = 0; q < 4; ++q) s.swap_choices[q] = -1;
+  } else {
+    s.cur = next;
+  }
+  s.reward = 0;
+}
+
 // env_step (dog.py:1117-1131).  All lanes call; lane 0 applies the move, all lanes deal if needed.
-__device__ inline void dog_env_step(const DogGeom& g, DogS& s, int lane, int action, int& reward_out, int& done_out) {
+__device__ __noinline__ void dog_env_step(const DogGeom& g, DogS& s, int lane, int action, int& reward_out, int& done_out) {
   __syncwarp();
   if (lane == 0) {
     int deal = 0, reward = 0, done = s.done;
-    if (s.phase == 1) {  // env_step_swap_phase (:1078-1114)
-      int card_idx = action - g.play_actions;
-      int cur = s.cur;
-      int cs = d_sidx(card_idx, kNCard), row = d_sidx(cur, g.n);
-      if (cs >= 0 && row >= 0) s.hands[row][cs] = (int8_t)(s.hands[row][cs] - 1);
-      int sc = d_sidx(cur, 4);
-      if (sc >= 0) s.swap_choices[sc] = (int8_t)card_idx;
-      int next = d_fmod(cur + 1, g.n);
-      if (next == s.round_starter) {
-        const int partners[4] = {2, 3, 0, 1};
-        for (int q = 0; q < g.n; ++q) {  // execute_team_swap (:1065-1075)
-          int rc = s.swap_choices[partners[q]];
-          if (rc >= 0 && rc < kNCard) s.hands[q][rc] = (int8_t)(s.hands[q][rc] + 1);
-        }
-        s.phase = 0;
-        s.cur = s.round_starter;
-        for (int q = 0; q < 4; ++q) s.swap_choices[q] = -1;
-      } else {
-        s.cur = next;
-      }
-      s.reward = 0;
+    if (s.phase == 1) {
+      dog_swap_phase(g, s, action);
       reward = 0;
       done = s.done;
     } else {  // env_step_play_phase (:987-1062)
@@ -678,7 +685,7 @@ __device__ inline void dog_env_step(const DogGeom& g, DogS& s, int lane, int act
 }
 
 // no_step (dog.py:713-752)
-__device__ inline void dog_no_step(const DogGeom& g, DogS& s, int lane) {
+__device__ __noinline__ void dog_no_step(const DogGeom& g, DogS& s, int lane) {
   __syncwarp();
   if (lane == 0) {
     int row = d_sidx(s.cur, g.n);

@@ -81,26 +81,32 @@ DS_FN bool dg4_canonical(const int32_t (*pins)[4], const int8_t* board, int cur)
   return ok;
 }
 
-DS_FN void dg4_view(const Dog4Rules& R, const int32_t (*pins)[4], int pid, Dog4View& v) {
-  uint64_t bits[4];
-#pragma unroll
-  for (int p = 0; p < 4; ++p) bits[p] = dg4_pin_bits(pins[p]);
-  v.occ[3] = bits[3];
-  v.occ[2] = bits[2] & ~bits[3];
-  v.occ[1] = bits[1] & ~(bits[2] | bits[3]);
-  v.occ[0] = bits[0] & ~(bits[1] | bits[2] | bits[3]);
-  v.any = bits[0] | bits[1] | bits[2] | bits[3];
+// view from the per-player pin bitboards (bits[p] = cells holding a pin of p) and the mover's pin row
+DS_FN void dg4_view_bits(const Dog4Rules& R, const uint64_t* bits, const int32_t (*pins)[4], int pid, Dog4View& v) {
+  const uint64_t b0 = bits[0], b1 = bits[1], b2 = bits[2], b3 = bits[3];
+  v.occ[3] = b3;
+  v.occ[2] = b2 & ~b3;
+  v.occ[1] = b1 & ~(b2 | b3);
+  v.occ[0] = b0 & ~(b1 | b2 | b3);
+  v.any = b0 | b1 | b2 | b3;
   v.pid = pid;
   const bool pid_done = (((uint32_t)(v.any >> 40) >> (4 * pid)) & 0xFu) == 0xFu;  // is_player_done: ANY occupant
   const int cp = (R.teams && pid_done) ? (pid ^ 2) : pid;
   v.cp = cp;
-  v.later = (cp < 1 ? bits[1] : 0ull) | (cp < 2 ? bits[2] : 0ull) | (cp < 3 ? bits[3] : 0ull);
-  v.posmask = 0;
-#pragma unroll
-  for (int q = 0; q < 4; ++q) v.posmask |= (uint32_t)dg4_bit(v.occ[q], dg4_start(q)) << q;
+  v.later = (cp < 1 ? b1 : 0ull) | (cp < 2 ? b2 : 0ull) | (cp < 3 ? b3 : 0ull);
+  v.posmask = (uint32_t)dg4_bit(v.occ[0], 0) | ((uint32_t)dg4_bit(v.occ[1], 10) << 1) | ((uint32_t)dg4_bit(v.occ[2], 20) << 2) |
+              ((uint32_t)dg4_bit(v.occ[3], 30) << 3);
 #pragma unroll
   for (int i = 0; i < 4; ++i) v.cur[i] = pins[cp][i];
-  v.lane = (uint32_t)(v.occ[cp == 0 ? 0 : cp == 1 ? 1 : cp == 2 ? 2 : 3] >> dg4_goal(cp)) & 0xFu;
+  const uint64_t own = cp == 0 ? v.occ[0] : cp == 1 ? v.occ[1] : cp == 2 ? v.occ[2] : v.occ[3];
+  v.lane = (uint32_t)(own >> dg4_goal(cp)) & 0xFu;
+}
+
+DS_FN void dg4_view(const Dog4Rules& R, const int32_t (*pins)[4], int pid, Dog4View& v) {
+  uint64_t bits[4];
+#pragma unroll
+  for (int p = 0; p < 4; ++p) bits[p] = dg4_pin_bits(pins[p]);
+  dg4_view_bits(R, bits, pins, pid, v);
 }
 
 DS_FN uint64_t dg4_own(const Dog4View& v) { return v.cp == 0 ? v.occ[0] : v.cp == 1 ? v.occ[1] : v.cp == 2 ? v.occ[2] : v.occ[3]; }
@@ -472,10 +478,14 @@ DS_FN void dg4_map_action_to_move(int action, int mv[6]) {
 
 // sum of a 16-byte hand row (two zero pad bytes)
 DS_FN int dg4_hand_sum(const int8_t* row) {
+#ifdef __CUDA_ARCH__
+  const int4 w = *reinterpret_cast<const int4*>(row);  // 16-byte row, pad bytes are zero
+  return __dp4a(w.x, 0x01010101, __dp4a(w.y, 0x01010101, __dp4a(w.z, 0x01010101, __dp4a(w.w, 0x01010101, 0))));
+#else
   int sum = 0;
-#pragma unroll
   for (int k = 0; k < kNCard; ++k) sum += row[k];
   return sum;
+#endif
 }
 
 // first seat after `from` that still holds cards (dog.py:1043-1047, :733-741)
@@ -504,7 +514,11 @@ DS_FN int dg4_next_with_cards(const DogS& s, int from, int& all_empty, int& any_
 // updated; s.board is NOT (the caller rebuilds it from the pins before anything reads it).  Returns "deal next".
 DS_FN int dg4_play_phase(const Dog4Rules& R, DogS& s, int action, int& reward_out, int& done_out) {
   Dog4View v;
+#ifdef __CUDA_ARCH__
+  dg4_view_bits(R, s.pbits, s.pins, s.cur, v);  // kept current by dog4_rebuild_board_warp
+#else
   dg4_view(R, s.pins, s.cur, v);
+#endif
   const int pid = s.cur, cp = v.cp;
   int mv[6];
   dg4_map_action_to_move(action, mv);
@@ -538,8 +552,9 @@ DS_FN int dg4_play_phase(const Dog4Rules& R, DogS& s, int action, int& reward_ou
 // the 120 splits of 7 (utility_funcs.py:4-21), packed a | b<<3 | c<<6 | d<<9; same order as dg4_dist_of
 __device__ const uint16_t g_dog_splits7[120] = {3584, 3136, 2688, 2240, 1792, 1344, 896, 448, 3080, 2632, 2184, 1736, 1288, 840, 392, 2576, 2128, 1680, 1232, 784, 336, 2072, 1624, 1176, 728, 280, 1568, 1120, 672, 224, 1064, 616, 168, 560, 112, 56, 3073, 2625, 2177, 1729, 1281, 833, 385, 2569, 2121, 1673, 1225, 777, 329, 2065, 1617, 1169, 721, 273, 1561, 1113, 665, 217, 1057, 609, 161, 553, 105, 49, 2562, 2114, 1666, 1218, 770, 322, 2058, 1610, 1162, 714, 266, 1554, 1106, 658, 210, 1050, 602, 154, 546, 98, 42, 2051, 1603, 1155, 707, 259, 1547, 1099, 651, 203, 1043, 595, 147, 539, 91, 35, 1540, 1092, 644, 196, 1036, 588, 140, 532, 84, 28, 1029, 581, 133, 525, 77, 21, 518, 70, 14, 7};
 
-// is the staged record canonical (see header)?  All 32 lanes must call; warp-uniform result.
-__device__ __forceinline__ bool dog4_canonical_warp(const DogS& s, int lane) {
+// is the staged record canonical (see header)?  Also publishes the pin bitboards s.pbits.  All 32 lanes must call;
+// warp-uniform result.
+__device__ __forceinline__ bool dog4_canonical_warp(DogS& s, int lane) {
   const uint32_t FULL = 0xFFFFFFFFu;
   uint64_t bits[4];
 #pragma unroll
@@ -558,13 +573,17 @@ __device__ __forceinline__ bool dog4_canonical_warp(const DogS& s, int lane) {
       ok = ok && (int)s.board[c] == want;
     }
   }
-  return __all_sync(FULL, ok);
+  if (lane < 4) s.pbits[lane] = bits[lane == 0 ? 0 : lane == 1 ? 1 : lane == 2 ? 2 : 3];
+  const bool all_ok = __all_sync(FULL, ok);
+  __syncwarp();
+  return all_ok;
 }
 
 // board bytes from the pins (set_pins_on_board: later players overwrite earlier ones).  All lanes call.
 __device__ __forceinline__ void dog4_rebuild_board_warp(DogS& s, int lane) {
   __syncwarp();
   if (lane < 16) reinterpret_cast<uint32_t*>(s.board)[lane] = 0xFFFFFFFFu;
+  else if (lane < 20) s.pbits[lane - 16] = dg4_pin_bits(s.pins[lane - 16]);
   __syncwarp();
 #pragma unroll
   for (int p = 0; p < 4; ++p) {
@@ -599,7 +618,7 @@ __device__ __forceinline__ void dog4_build_mask(const Dog4Rules& R, DogS& s, int
     return;
   }
   Dog4View v;
-  dg4_view(R, s.pins, s.cur, v);
+  dg4_view_bits(R, s.pbits, s.pins, s.cur, v);
   const int8_t* hand = s.hands[v.cp];
   const bool joker = hand[0] > 0;
   if (joker || hand[1] > 0) {  // swaps: pin_ok x cell_ok
@@ -644,15 +663,30 @@ __device__ __forceinline__ void dog4_env_step(const Dog4Rules& R, const DogGeom&
                                               int& done_out) {
   __syncwarp();
   const bool play = s.phase != 1;
-  if (!play || action < 0 || action >= 792) {  // swap phase / out-of-range action index: generic path (warp-uniform)
+  if (play && (action < 0 || action >= 792)) {  // a swap-phase index in the play phase: generic path (warp-uniform)
     dog_env_step(g, s, lane, action, reward_out, done_out);
+    dog4_rebuild_board_warp(s, lane);  // refreshes s.pbits
     return;
   }
   if (lane == 0) {
-    int reward, done;
-    s.scratch[0] = dg4_play_phase(R, s, action, reward, done);
-    s.scratch[1] = reward;
-    s.scratch[2] = done;
+    if (play) {
+      int reward, done;
+      s.scratch[0] = dg4_play_phase(R, s, action, reward, done);
+      s.scratch[1] = reward;
+      s.scratch[2] = done;
+    } else {
+      dog_swap_phase(g, s, action);
+      s.scratch[0] = 0;
+      s.scratch[1] = 0;
+      s.scratch[2] = s.done;
+    }
+  }
+  __syncwarp();
+  if (!play) {
+    reward_out = s.scratch[1];
+    done_out = s.scratch[2];
+    __syncwarp();
+    return;
   }
   dog4_rebuild_board_warp(s, lane);
   if (s.scratch[0]) dog_distribute_cards(g, s, lane);

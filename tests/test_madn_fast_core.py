@@ -22,7 +22,7 @@ def hc():
     deps = [SRC, os.path.join(CSRC, "madn_fast.cuh"), os.path.join(CSRC, "madn_core.cuh")]
     if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
         os.makedirs(os.path.dirname(OUT), exist_ok=True)
-        subprocess.run(["/usr/local/cuda/bin/nvcc", "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-Xcompiler", "-fPIC",
+        subprocess.run(["/usr/local/cuda/bin/nvcc", "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC",
                         "-shared", "-o", OUT, SRC], check=True)
     return C.CDLL(OUT)
 
