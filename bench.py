@@ -153,6 +153,30 @@ def measure_extras(dev, key):
                                      "achieved": n * S * bytes_per_sim / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
                                      "frac": n * S * bytes_per_sim / (ms / 1e3) / 1e9 / peak,
                                      "note": "wall time of the whole search incl. the stand-in network and 2 launches per simulation"}}
+    # the same search with precomputed network outputs: the tree kernels alone (select + expand/backup)
+    cfg = mcts._cfg(mcts.STOCHASTIC, mcts.qtransform_by_parent_and_siblings, S, 50, A, Cn, E, dirichlet_fraction=0.0)
+    srch = mcts.Search(cfg, n, dev)
+    R = 8
+    rnd = lambda *shape: torch.randn(*shape, device=dev, generator=g)
+    pl, cl, emb = [rnd(n, A) for _ in range(R)], [rnd(n, Cn) for _ in range(R)], [rnd(n, E) for _ in range(R)]
+    val, rew = [torch.tanh(rnd(n)) for _ in range(R)], [0.1 * rnd(n) for _ in range(R)]
+    disc = [torch.where(rnd(n) > 0, 1.0, -1.0) for _ in range(R)]
+    for rep in range(2):
+        srch.init(keys, root, None, None)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for sim in range(S):
+            srch.select(sim)
+            k = sim % R
+            srch.expand(sim, pl[k], val[k], rew[k], disc[k], emb[k], cl[k], val[(k + 1) % R], emb[(k + 1) % R])
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    out["mcts_cfg3_tree_only"] = {"workload": "cfg3 tree kernels alone (select + expand/backup, precomputed network outputs)",
+                                  "sims": n * S, "ms": ms, "sims_per_s": n * S / (ms / 1e3), "gpu_launches": 2 * S,
+                                  "roofline": {"bound": "hbm", "kernel": "k_mcts_select + k_mcts_expand",
+                                               "algorithmic_bytes_per_sim": bytes_per_sim, "achieved": n * S * bytes_per_sim / (ms / 1e3) / 1e9,
+                                               "peak": peak, "unit": "GB/s", "frac": n * S * bytes_per_sim / (ms / 1e3) / 1e9 / peak}}
     return out
 
 

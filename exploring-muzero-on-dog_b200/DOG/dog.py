@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from .. import _lib, rules as _rules
-from ..MADN._state import BatchedEnv, to_dev
+from ..MADN._state import BatchedEnv, seeds_to_dev, to_dev
 from ..MADN.deterministic_madn import _geometry, _layout_mask, _out
 
 
@@ -72,9 +72,7 @@ def env_reset(_, num_players=4, layout=None, distance=10, starting_player=0, see
               disable_hot_seven=False, disable_joker=False, device="cuda"):
     """env_reset (:83-181), seed scalar or int array [n]."""
     num_players, distance = int(num_players), int(distance)
-    batched = np.ndim(seed.cpu() if isinstance(seed, torch.Tensor) else seed) > 0
-    seeds = to_dev(np.atleast_1d(seed.cpu().numpy() if isinstance(seed, torch.Tensor) else np.asarray(seed)),
-                   torch.int32, device)
+    batched, seeds = seeds_to_dev(seed, device)
     lm = _layout_mask(layout)
     start, target, goal = _geometry(num_players, lm, distance)
     rules = dict(enable_teams=bool(enable_teams) and num_players == 4, enable_initial_free_pin=bool(enable_initial_free_pin),

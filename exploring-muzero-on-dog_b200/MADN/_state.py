@@ -19,6 +19,15 @@ def to_dev(x, dtype, device):
     return torch.as_tensor(a, device=device).to(dtype).contiguous()
 
 
+def seeds_to_dev(seed, device):
+    """(batched?, int32 [n] device tensor) from a scalar / array / tensor seed.  A tensor that already lives on the
+    device is used as is — no host round trip, no synchronisation on the hot path."""
+    if isinstance(seed, torch.Tensor):
+        return seed.dim() > 0, seed.reshape(-1).to(device=device, dtype=torch.int32).contiguous()
+    a = np.asarray(seed)
+    return a.ndim > 0, to_dev(np.atleast_1d(a), torch.int32, device)
+
+
 class BatchedEnv:
     """Leaves: name -> (torch dtype, trailing shape).  Static fields live in `static`."""
 

@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from .. import _lib, rules as _rules
-from ._state import BatchedEnv, to_dev
+from ._state import BatchedEnv, seeds_to_dev, to_dev
 from .deterministic_madn import _geometry, _layout_mask, _out, set_pins_on_board  # noqa: F401  (same function in both files)
 
 
@@ -52,9 +52,7 @@ def env_reset(_, num_players=4, layout=None, distance=10, starting_player=0, see
               enable_bonus_turn_on_6=True, enable_dice_rethrow=False, must_traverse_start=False, device="cuda"):
     """env_reset (:51-131); `seed` scalar (single env) or int array [n] (vmapped)."""
     num_players, distance = int(num_players), int(distance)
-    batched = np.ndim(seed.cpu() if isinstance(seed, torch.Tensor) else seed) > 0
-    seeds = to_dev(np.atleast_1d(seed.cpu().numpy() if isinstance(seed, torch.Tensor) else np.asarray(seed)),
-                   torch.int32, device)
+    batched, seeds = seeds_to_dev(seed, device)
     lm = _layout_mask(layout)
     start, target, goal = _geometry(num_players, lm, distance)
     rules = dict(enable_teams=bool(enable_teams) and num_players == 4,

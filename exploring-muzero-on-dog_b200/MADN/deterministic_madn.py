@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from .. import _lib, rules as _rules
-from ._state import BatchedEnv, to_dev
+from ._state import BatchedEnv, seeds_to_dev, to_dev
 
 RULE_KEYS = ("enable_teams", "enable_initial_free_pin", "enable_circular_board", "enable_start_blocking",
              "enable_jump_in_goal_area", "enable_friendly_fire", "enable_start_on_1", "enable_bonus_turn_on_6",
@@ -89,9 +89,7 @@ def env_reset(_, num_players=4, layout=None, distance=10, starting_player=0, see
     """env_reset (:42-120).  `seed` may be a scalar (single env) or an int array [n] (what
     jax.vmap(env_reset_batched) receives, game_agent.py:24-44)."""
     num_players, distance = int(num_players), int(distance)
-    batched = np.ndim(seed.cpu() if isinstance(seed, torch.Tensor) else seed) > 0
-    seeds = to_dev(np.atleast_1d(seed.cpu().numpy() if isinstance(seed, torch.Tensor) else np.asarray(seed)),
-                   torch.int32, device)
+    batched, seeds = seeds_to_dev(seed, device)
     lm = _layout_mask(layout)
     start, target, goal = _geometry(num_players, lm, distance)
     rules = dict(enable_teams=bool(enable_teams) and num_players == 4,
