@@ -41,7 +41,7 @@ class ClockSampler:
     """SM clock / throttle reasons sampled through NVML DURING the timed region (same fields as the
     nvidia-smi line of B200_PROFILING.md; in-process so that a sub-second region still gets samples)."""
 
-    def __init__(self, index, period=0.01):
+    def __init__(self, index, period=0.002):
         self.index, self.period, self.rows, self._stop, self.th = index, period, [], False, None
         try:
             import pynvml
