@@ -2,6 +2,7 @@
 valid_action_mask :81, policy_function :96, root_fn :121, recurrent_fn :128 — batched over games, one libdogstep.so kernel
 per call.  The env doubles as the search embedding (18 floats), exactly as the reference stores the env pytree in the tree."""
 import ctypes as C
+import functools
 
 import numpy as np
 import torch
@@ -82,6 +83,7 @@ def root_fn(env, rng_key):
     return mcts.RootFnOutput(prior, value, emb)
 
 
+@functools.lru_cache(maxsize=None)
 def make_recurrent_fn(variant=VARIANT):
     def recurrent_fn(params, rng_key, action, embedding):
         """recurrent_fn (:128-140) on the 18-float env embedding"""

@@ -154,34 +154,91 @@ def _run(search, params, root, recurrent_fn, invalid_actions, keys, dirichlet_no
     return search.policy_output()[0]
 
 
+class GraphCache:
+    """Caller-owned cache of searches captured as CUDA graphs.
+
+    A search is 2-3 small launches per simulation (select, the caller's recurrent function, expand); at the batch sizes of
+    the reference's configurations that loop is launch-bound.  Passing the same `GraphCache()` to a policy function on
+    every move makes the first call capture `init -> num_simulations x (select, recurrent_fn, expand) -> policy_output`
+    into one CUDA graph and every later call with the same shapes replay it: inputs are copied into the captured buffers,
+    the returned PolicyOutput tensors are the captured ones (consume them before the next call).  The recurrent function
+    must be capturable (CUDA work on the current stream only, no host synchronisation) and `params` must be updated in
+    place between calls — both hold for torch modules and for the true-env callbacks shipped here."""
+
+    def __init__(self):
+        self.entries = {}
+
+    def run(self, key, inputs, fn):
+        """inputs: dict name -> tensor or None; fn(static_inputs) -> PolicyOutput"""
+        ent = self.entries.get(key)
+        if ent is None:
+            static = {k: (None if v is None else v.detach().clone().contiguous()) for k, v in inputs.items()}
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):  # warm-up outside capture: library handles, allocator pools
+                fn(static)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = fn(static)
+            # `fn` is kept: its closure owns the Search whose work buffers (parent, action, embedding, keys) the captured
+            # kernels write on every replay
+            ent = self.entries[key] = (static, graph, out, fn)
+        static, graph, out, _ = ent
+        for k, v in inputs.items():
+            if v is not None:
+                static[k].copy_(v)
+        graph.replay()
+        return out
+
+
+def _cfg_key(cfg):
+    return tuple(getattr(cfg, f) for f, _ in cfg._fields_)
+
+
+def _run_cached(graph_cache, cfg, n, dev, params, root, recurrent_fn, invalid_actions, keys, dirichlet_noise):
+    if graph_cache is None:
+        return _run(Search(cfg, n, dev), params, root, recurrent_fn, invalid_actions, keys, dirichlet_noise)
+    inputs = dict(keys=keys, prior=root.prior_logits.float(), value=root.value.float(), emb=root.embedding.float().reshape(n, -1),
+                  invalid=None if invalid_actions is None else invalid_actions.reshape(n, -1).to(torch.uint8), noise=dirichlet_noise)
+    key = (_cfg_key(cfg), n, str(dev), id(recurrent_fn), id(params), invalid_actions is None, dirichlet_noise is None)
+    search = Search(cfg, n, dev) if key not in graph_cache.entries else None
+
+    def fn(st):
+        return _run(search, params, RootFnOutput(st["prior"], st["value"], st["emb"]), recurrent_fn, st["invalid"], st["keys"], st["noise"])
+
+    return graph_cache.run(key, inputs, fn)
+
+
 def muzero_policy(params, rng_key, root, recurrent_fn, num_simulations, invalid_actions=None, max_depth=None, *,
                   qtransform=qtransform_by_parent_and_siblings, dirichlet_fraction=0.25, dirichlet_alpha=0.3, pb_c_init=1.25,
-                  pb_c_base=19652, temperature=1.0, dirichlet_noise=None):
-    """mctx.muzero_policy.  rng_key: uint32 [games, 2]."""
+                  pb_c_base=19652, temperature=1.0, dirichlet_noise=None, graph_cache=None):
+    """mctx.muzero_policy.  rng_key: uint32 [games, 2].  graph_cache: optional GraphCache (CUDA-graph replay)."""
     n, A = root.prior_logits.shape
     E = root.embedding.reshape(n, -1).shape[1]
     if dirichlet_noise is None and dirichlet_fraction > 0:
         dirichlet_noise = torch.distributions.Dirichlet(torch.full((A,), float(dirichlet_alpha), device=root.value.device)).sample((n,))
     cfg = _cfg(MUZERO, qtransform, num_simulations, max_depth, A, 0, E, pb_c_init=pb_c_init, pb_c_base=pb_c_base,
                dirichlet_fraction=dirichlet_fraction, temperature=temperature)
-    return _run(Search(cfg, n, root.value.device), params, root, recurrent_fn, invalid_actions, rng_key,
-                dirichlet_noise if dirichlet_fraction > 0 else None)
+    return _run_cached(graph_cache, cfg, n, root.value.device, params, root, recurrent_fn, invalid_actions, rng_key,
+                       dirichlet_noise if dirichlet_fraction > 0 else None)
 
 
 def gumbel_muzero_policy(params, rng_key, root, recurrent_fn, num_simulations, invalid_actions=None, max_depth=None, *,
-                         qtransform=qtransform_completed_by_mix_value, max_num_considered_actions=16, gumbel_scale=1.0):
-    """mctx.gumbel_muzero_policy.  rng_key: uint32 [games, 2]."""
+                         qtransform=qtransform_completed_by_mix_value, max_num_considered_actions=16, gumbel_scale=1.0,
+                         graph_cache=None):
+    """mctx.gumbel_muzero_policy.  rng_key: uint32 [games, 2].  graph_cache: optional GraphCache (CUDA-graph replay)."""
     n, A = root.prior_logits.shape
     E = root.embedding.reshape(n, -1).shape[1]
     cfg = _cfg(GUMBEL, qtransform, num_simulations, max_depth, A, 0, E, max_num_considered_actions=max_num_considered_actions,
                gumbel_scale=gumbel_scale)
-    return _run(Search(cfg, n, root.value.device), params, root, recurrent_fn, invalid_actions, rng_key)
+    return _run_cached(graph_cache, cfg, n, root.value.device, params, root, recurrent_fn, invalid_actions, rng_key, None)
 
 
 def stochastic_muzero_policy(params, rng_key, root, decision_recurrent_fn, chance_recurrent_fn, num_simulations,
                              invalid_actions=None, max_depth=None, *, qtransform=qtransform_by_parent_and_siblings,
                              dirichlet_fraction=0.25, dirichlet_alpha=0.3, pb_c_init=1.25, pb_c_base=19652, temperature=1.0,
-                             dirichlet_noise=None, num_chance_outcomes=None):
+                             dirichlet_noise=None, num_chance_outcomes=None, graph_cache=None):
     """mctx.stochastic_muzero_policy: decision nodes (A actions) alternate with chance nodes (C outcomes).
     Both callbacks are evaluated every simulation (as mctx does) and the kernel picks per game by node type; the stored
     embedding is padded to the wider of the state / afterstate embeddings."""
@@ -197,14 +254,24 @@ def stochastic_muzero_policy(params, rng_key, root, decision_recurrent_fn, chanc
         dirichlet_noise = torch.distributions.Dirichlet(torch.full((A,), float(dirichlet_alpha), device=dev)).sample((n,))
     cfg = _cfg(STOCHASTIC, qtransform, num_simulations, max_depth, A, Cn, E, pb_c_init=pb_c_init, pb_c_base=pb_c_base,
                dirichlet_fraction=dirichlet_fraction, temperature=temperature)
-    s = Search(cfg, n, dev)
-    s.init(rng_key, RootFnOutput(root.prior_logits, root.value, pad(state_emb)), invalid_actions,
-           dirichlet_noise if dirichlet_fraction > 0 else None)
-    for sim in range(num_simulations):
-        _, action, emb, is_dec = s.select(sim)
-        a = action.long()
-        dec, after = decision_recurrent_fn(params, None, a.clamp(max=A - 1), emb[:, :Es])
-        ch, nxt = chance_recurrent_fn(params, None, (a - A).clamp(min=0, max=Cn - 1), emb[:, :Ea])
-        s.expand(sim, ch.action_logits, ch.value, ch.reward, ch.discount, pad(nxt), dec.chance_logits, dec.afterstate_value,
-                 pad(after))
-    return s.policy_output()[0]
+    noise = dirichlet_noise if dirichlet_fraction > 0 else None
+
+    def search_loop(s, st):
+        s.init(st["keys"], RootFnOutput(st["prior"], st["value"], st["emb"]), st["invalid"], st["noise"])
+        for sim in range(num_simulations):
+            _, action, emb, is_dec = s.select(sim)
+            a = action.long()
+            dec, after = decision_recurrent_fn(params, None, a.clamp(max=A - 1), emb[:, :Es])
+            ch, nxt = chance_recurrent_fn(params, None, (a - A).clamp(min=0, max=Cn - 1), emb[:, :Ea])
+            s.expand(sim, ch.action_logits, ch.value, ch.reward, ch.discount, pad(nxt), dec.chance_logits, dec.afterstate_value,
+                     pad(after))
+        return s.policy_output()[0]
+
+    inputs = dict(keys=rng_key, prior=root.prior_logits.float(), value=root.value.float(), emb=pad(state_emb),
+                  invalid=None if invalid_actions is None else invalid_actions.reshape(n, -1).to(torch.uint8), noise=noise)
+    if graph_cache is None:
+        return search_loop(Search(cfg, n, dev), inputs)
+    key = (_cfg_key(cfg), n, str(dev), id(decision_recurrent_fn), id(chance_recurrent_fn), id(params), invalid_actions is None,
+           noise is None)
+    s = Search(cfg, n, dev) if key not in graph_cache.entries else None
+    return graph_cache.run(key, inputs, lambda st: search_loop(s, st))

@@ -152,3 +152,58 @@ def test_mctx_shaped_policies_run():
                                         qtransform=mcts.qtransform_by_parent_and_siblings, temperature=1.0)
     assert (out.search_tree.summary().visit_counts.sum(1) == 64).all()
     assert out.search_tree.children_visits.shape[-1] == 10
+
+
+def test_cuda_graph_replay_equals_eager_search():
+    """mcts.GraphCache: the captured search replayed with new inputs gives bit-identical outputs to the eager loop, for the
+    three policies (launch-bound loops are replayed as one graph)"""
+    import functools
+    from exploring_muzero_on_dog_b200 import mcts
+    n, A, E = 96, 24, 32
+
+    class ElemNet:  # elementwise only: bit-identical in eager and captured execution (cuBLAS may pick other kernels)
+        def __init__(self, A, Cn, E, seed):
+            g = torch.Generator(device="cuda").manual_seed(seed)
+            self.w = torch.randn(A + Cn, E, device="cuda", generator=g)
+            self.A, self.Cn = A, Cn
+
+        def __call__(self, action, emb):
+            nxt = torch.tanh(emb * self.w[action] + 0.1 * torch.roll(emb, 1, 1))
+            return dict(prior=3.0 * nxt[:, :self.A], value=torch.tanh(nxt[:, 0] + nxt[:, 1] - nxt[:, 2]), reward=0.1 * nxt[:, 3],
+                        discount=torch.where(nxt[:, 4] > 0, 1.0, -1.0), emb=nxt, chance=2.0 * nxt[:, 5:5 + max(self.Cn, 1)])
+
+    net = ElemNet(A, 6, E, 3)
+    net4 = ElemNet(4, 6, E, 5)
+
+    def recurrent_fn(params, rng_key, action, embedding):
+        o = net(action, embedding)
+        return mcts.RecurrentFnOutput(o["reward"], o["discount"], o["prior"], o["value"]), o["emb"]
+
+    def dec(params, rng_key, action, embedding):
+        o = net4(action, embedding)
+        return mcts.DecisionRecurrentFnOutput(o["chance"], o["value"]), torch.cat([o["emb"], o["reward"][:, None], o["discount"][:, None]], 1)
+
+    def ch(params, rng_key, outcome, afterstate):
+        o = net4(outcome + 4, afterstate[:, :-2])
+        return mcts.ChanceRecurrentFnOutput(o["prior"], o["value"], afterstate[:, -2], afterstate[:, -1]), o["emb"]
+
+    cache = mcts.GraphCache()
+    qt = functools.partial(mcts.qtransform_completed_by_mix_value, value_scale=0.5)
+    for rep in range(3):  # rep 0 captures, reps 1-2 replay with fresh inputs
+        g = torch.Generator(device="cuda").manual_seed(10 + rep)
+        root = mcts.RootFnOutput(torch.randn(n, A, device="cuda", generator=g), torch.rand(n, device="cuda", generator=g) * 2 - 1,
+                                 torch.randn(n, E, device="cuda", generator=g))
+        keys = torch.randint(0, 2**31, (n, 2), device="cuda", generator=g).to(torch.uint32)
+        invalid = torch.rand(n, A, device="cuda", generator=g) < 0.5
+        invalid[:, 0] = False
+        for run in (lambda gc: mcts.gumbel_muzero_policy(None, keys, root, recurrent_fn, 40, invalid_actions=invalid, max_depth=20, qtransform=qt, graph_cache=gc),
+                    lambda gc: mcts.muzero_policy(None, keys, root, recurrent_fn, 30, invalid_actions=invalid, max_depth=9, dirichlet_fraction=0.0, graph_cache=gc),
+                    lambda gc: mcts.stochastic_muzero_policy(None, keys, mcts.RootFnOutput(root.prior_logits[:, :4].contiguous(), root.value, root.embedding),
+                                                             dec, ch, 32, invalid_actions=invalid[:, :4].contiguous(), max_depth=50,
+                                                             dirichlet_fraction=0.0, graph_cache=gc)):
+            eager, graphed = run(None), run(cache)
+            assert torch.equal(eager.action, graphed.action)
+            assert torch.equal(eager.action_weights, graphed.action_weights)
+            assert torch.equal(eager.search_tree.children_visits, graphed.search_tree.children_visits)
+            assert torch.equal(eager.search_tree.node_values, graphed.search_tree.node_values)
+    assert len(cache.entries) == 3

@@ -150,3 +150,18 @@ def test_config1_lockstep_mcts_selfplay():
     assert st["done"].all() and (plies.cpu().numpy() <= 9).all() and (st["reward"] >= 0).all()
     env, plies = tm.play_mcts_games(512, jaxrand.PRNGKey(1), num_simulations=50, limit=30, variant=1, search=tm.run_gumbel)
     assert (env.numpy()["reward"] >= 0).all() and int(plies.max()) <= 30
+
+
+@pytest.mark.gpu
+def test_config1_graph_replay_plays_the_same_games():
+    """config 1 with the per-move search replayed as one CUDA graph (mcts.GraphCache) == the eager launches"""
+    import torch
+    from exploring_muzero_on_dog_b200 import jaxrand, mcts
+    from exploring_muzero_on_dog_b200.TicTacToe import mcts as tm
+    for variant, search in ((0, tm.run_mcts), (1, tm.run_gumbel)):
+        a, pa = tm.play_mcts_games(256, jaxrand.PRNGKey(3), num_simulations=50, limit=30, variant=variant, search=search)
+        b, pb = tm.play_mcts_games(256, jaxrand.PRNGKey(3), num_simulations=50, limit=30, variant=variant, search=search,
+                                   graph_cache=mcts.GraphCache())
+        assert torch.equal(pa, pb)
+        for k, v in a.numpy().items():
+            assert np.array_equal(v, b.numpy()[k]), k
