@@ -133,10 +133,12 @@ def measure_extras(dev, key):
     root = mcts.RootFnOutput(torch.randn(n, A, device=dev, generator=g), torch.zeros(n, device=dev), torch.randn(n, E, device=dev, generator=g))
     keys = jaxrand.split(key, n, device=dev)
     invalid = torch.zeros(n, A, dtype=torch.bool, device=dev)
-    for rep in range(2):
+    cache = mcts.GraphCache()  # the whole search (init, 64 x (select, both networks, expand), policy) replayed as one CUDA graph
+    for rep in range(3):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        po = mcts.stochastic_muzero_policy(None, keys, root, dec, ch, S, invalid_actions=invalid, max_depth=50, dirichlet_fraction=0.0)
+        po = mcts.stochastic_muzero_policy(None, keys, root, dec, ch, S, invalid_actions=invalid, max_depth=50, dirichlet_fraction=0.0,
+                                           graph_cache=cache)
         e1.record()
         torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
@@ -152,7 +154,7 @@ def measure_extras(dev, key):
                         "roofline": {"bound": "hbm", "kernel": "k_mcts_select + k_mcts_expand", "algorithmic_bytes_per_sim": bytes_per_sim,
                                      "achieved": n * S * bytes_per_sim / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
                                      "frac": n * S * bytes_per_sim / (ms / 1e3) / 1e9 / peak,
-                                     "note": "wall time of the whole search incl. the stand-in network and 2 launches per simulation"}}
+                                     "note": "device time of the whole search incl. the stand-in network (3 small matmuls per simulation), replayed as one CUDA graph"}}
     # the same search with precomputed network outputs: the tree kernels alone (select + expand/backup)
     cfg = mcts._cfg(mcts.STOCHASTIC, mcts.qtransform_by_parent_and_siblings, S, 50, A, Cn, E, dirichlet_fraction=0.0)
     srch = mcts.Search(cfg, n, dev)
