@@ -130,6 +130,109 @@ __global__ void __launch_bounds__(128) k_replay_gather(dogstep_replay_arrays buf
   }
 }
 
+// ---- prioritised sampling (an extension beyond the reference, which samples uniformly with a terminal quota) --------
+// Proportional prioritisation P(e, t) = p[e, t] / sum p over a two-level sum structure: per-(episode, ply) priorities and
+// per-episode row sums.  Priorities are FIXED POINT (uint32, 2^-20 units) and sums uint64, so every sum is exact and
+// independent of the order it is taken in: the parallel scans below and the NumPy oracle agree bit for bit.
+constexpr int kPrioShift = 20;
+
+__device__ __forceinline__ uint32_t prio_to_fixed(float p) {
+  if (!(p > 0.0f)) return 0u;
+  const double v = (double)p * (double)(1u << kPrioShift);
+  return v >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)(v + 0.5);
+}
+
+// rows[i] < 0 is skipped; row = value for t < episode_lengths[row], 0 beyond; row sum recomputed (warp per row)
+__global__ void __launch_bounds__(128) k_replay_prio_fill(uint32_t* __restrict__ prio, unsigned long long* __restrict__ row_sum,
+                                                          const int32_t* __restrict__ episode_lengths, int T,
+                                                          const int32_t* __restrict__ rows, int n_rows, float value) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (i >= n_rows) return;
+  const int row = rows[i];
+  if (row < 0) return;
+  const int len = min(episode_lengths[row], T);
+  const uint32_t v = prio_to_fixed(value);
+  for (int t = lane; t < T; t += 32) prio[(int64_t)row * T + t] = t < len ? v : 0u;
+  if (lane == 0) row_sum[row] = (unsigned long long)v * (unsigned long long)max(len, 0);
+}
+
+// prio[ep[b], t[b]] = value[b]; the row sum follows through atomics, so duplicates in the batch stay consistent
+__global__ void k_replay_prio_update(uint32_t* __restrict__ prio, unsigned long long* __restrict__ row_sum, int T, int B,
+                                     const int32_t* __restrict__ ep, const int32_t* __restrict__ ts, const float* __restrict__ value) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const uint32_t nv = prio_to_fixed(value[b]);
+  const uint32_t old = atomicExch(&prio[(int64_t)ep[b] * T + ts[b]], nv);
+  atomicAdd(&row_sum[ep[b]], (unsigned long long)nv - (unsigned long long)old);  // wraps modulo 2^64: exact
+}
+
+// inclusive scan of row_sum[0..size) -> cdf (one CTA of 1024 threads, chunks of 1024 with a running carry)
+__global__ void __launch_bounds__(1024) k_replay_prio_scan(const unsigned long long* __restrict__ row_sum, int size,
+                                                           unsigned long long* __restrict__ cdf) {
+  __shared__ unsigned long long warp_tot[32];
+  __shared__ unsigned long long carry_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carry_s = 0ull;
+  __syncthreads();
+  for (int base = 0; base < size; base += 1024) {
+    const int i = base + tid;
+    unsigned long long v = i < size ? row_sum[i] : 0ull;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long u = __shfl_up_sync(0xFFFFFFFFu, v, o);
+      if (lane >= o) v += u;
+    }
+    if (lane == 31) warp_tot[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+      unsigned long long w = warp_tot[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long u = __shfl_up_sync(0xFFFFFFFFu, w, o);
+        if (lane >= o) w += u;
+      }
+      warp_tot[lane] = w;
+    }
+    __syncthreads();
+    const unsigned long long before = (warp ? warp_tot[warp - 1] : 0ull) + carry_s;
+    if (i < size) cdf[i] = v + before;
+    __syncthreads();
+    if (tid == 1023) carry_s = v + before;
+    __syncthreads();
+  }
+}
+
+// sample b: target = floor(bits64 * total / 2^64) -> episode by binary search in cdf, ply by a row scan
+__global__ void k_replay_plan_prio(const uint32_t* __restrict__ prio, const unsigned long long* __restrict__ cdf, int size, int T, int B,
+                                   Key2 key, int32_t* __restrict__ ep_indices, int32_t* __restrict__ t_starts,
+                                   double* __restrict__ prob) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const unsigned long long total = cdf[size - 1];
+  const unsigned long long bits = ((unsigned long long)bits_i(key, 2u * b) << 32) | (unsigned long long)bits_i(key, 2u * b + 1u);
+  const unsigned long long target = __umul64hi(bits, total);  // uniform in [0, total)
+  int lo = 0, hi = size - 1;                                   // first episode with cdf > target
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (cdf[mid] > target) hi = mid;
+    else lo = mid + 1;
+  }
+  const int ep = lo;
+  unsigned long long r = target - (ep ? cdf[ep - 1] : 0ull), acc = 0ull;
+  int t = 0;
+  uint32_t pv = 0u;
+  for (int k = 0; k < T; ++k) {
+    pv = prio[(int64_t)ep * T + k];
+    acc += pv;
+    t = k;
+    if (acc > r) break;
+  }
+  ep_indices[b] = ep;
+  t_starts[b] = t;
+  prob[b] = total ? (double)pv / (double)total : 0.0;
+}
+
 static int replay_check(const dogstep_replay_arrays* a) {
   if (!a || a->capacity < 1 || a->max_episode_length < 1 || a->obs_size < 1 || a->action_dim < 1) return DOGSTEP_ERR_INVALID_ARG;
   if (!a->observations || !a->actions || !a->rewards || !a->root_values || !a->child_visits || !a->masks || !a->players ||
@@ -182,6 +285,35 @@ int dogstep_replay_gather(const dogstep_replay_arrays* buf, int32_t batch_size, 
   if (buf->stochastic && (!out->dice_outcomes || !out->dice_probs)) return DOGSTEP_ERR_INVALID_ARG;
   k_replay_gather<<<batch_size, 128, 0, (cudaStream_t)stream>>>(*buf, batch_size, unroll_steps, td_steps, bootstrap_value_target,
                                                                 gamma_pow, ep_indices, t_starts, *out);
+  return check_launch();
+}
+
+int dogstep_replay_prio_fill(uint32_t* prio, unsigned long long* row_sum, const int32_t* episode_lengths, int32_t max_episode_length,
+                             const int32_t* rows, int32_t n_rows, float value, void* stream) {
+  if (!prio || !row_sum || !episode_lengths || !rows || max_episode_length < 1 || n_rows < 0) return DOGSTEP_ERR_INVALID_ARG;
+  if (n_rows == 0) return DOGSTEP_OK;
+  k_replay_prio_fill<<<(n_rows + 3) / 4, 128, 0, (cudaStream_t)stream>>>(prio, row_sum, episode_lengths, max_episode_length, rows, n_rows, value);
+  return check_launch();
+}
+
+int dogstep_replay_prio_update(uint32_t* prio, unsigned long long* row_sum, int32_t max_episode_length, int32_t batch_size,
+                               const int32_t* ep_indices, const int32_t* t_starts, const float* value, void* stream) {
+  if (!prio || !row_sum || !ep_indices || !t_starts || !value || max_episode_length < 1 || batch_size < 0) return DOGSTEP_ERR_INVALID_ARG;
+  if (batch_size == 0) return DOGSTEP_OK;
+  k_replay_prio_update<<<(batch_size + 127) / 128, 128, 0, (cudaStream_t)stream>>>(prio, row_sum, max_episode_length, batch_size, ep_indices,
+                                                                                   t_starts, value);
+  return check_launch();
+}
+
+int dogstep_replay_plan_prioritized(const uint32_t* prio, const unsigned long long* row_sum, unsigned long long* cdf_work, int32_t size,
+                                    int32_t max_episode_length, int32_t batch_size, const uint32_t* host_key, int32_t* ep_indices,
+                                    int32_t* t_starts, double* prob, void* stream) {
+  if (!prio || !row_sum || !cdf_work || !host_key || !ep_indices || !t_starts || !prob || size < 1 || max_episode_length < 1 ||
+      batch_size < 1)
+    return DOGSTEP_ERR_INVALID_ARG;
+  k_replay_prio_scan<<<1, 1024, 0, (cudaStream_t)stream>>>(row_sum, size, cdf_work);
+  k_replay_plan_prio<<<(batch_size + 127) / 128, 128, 0, (cudaStream_t)stream>>>(prio, cdf_work, size, max_episode_length, batch_size,
+                                                                                 Key2{host_key[0], host_key[1]}, ep_indices, t_starts, prob);
   return check_launch();
 }
 

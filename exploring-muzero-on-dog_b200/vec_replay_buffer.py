@@ -8,7 +8,8 @@ libdogstep.so kernels; `sample_batch` returns CUDA tensors (zero-copy to JAX thr
 
 Extras beyond the reference: `seed=` makes sampling reproducible (the reference draws from an unseeded np.random),
 `sample_batch(plan=(ep_indices, t_starts))` replays a given draw, `obs_dtype=torch.int8` stores observations 4x
-smaller, and `sample_batch_global()` all-gathers the per-rank batches over NCCL (the one collective of the design).
+smaller, `sample_batch_global()` all-gathers the per-rank batches over NCCL (the one collective of the design), and
+`prioritized=True` adds proportional prioritised sampling (`sample_batch_prioritized`, `update_priorities`).
 """
 import ctypes as C
 
@@ -27,7 +28,7 @@ class VectorizedReplayBuffer:
     STOCHASTIC = False
 
     def __init__(self, capacity, batch_size, unroll_steps, td_steps, obs_shape=(14, 56), action_dim=24, max_episode_length=500,
-                 bootstrap_value_target=True, device="cuda", obs_dtype=torch.float32, seed=0):
+                 bootstrap_value_target=True, device="cuda", obs_dtype=torch.float32, seed=0, prioritized=False):
         self.capacity, self.batch_size, self.unroll_steps, self.td_steps = capacity, batch_size, unroll_steps, td_steps
         self.obs_shape, self.action_dim, self.max_episode_length = tuple(obs_shape), action_dim, max_episode_length
         self.bootstrap_value_target = bootstrap_value_target
@@ -43,6 +44,11 @@ class VectorizedReplayBuffer:
         self.dice_outcomes = torch.full((capacity, T), -1, dtype=torch.int32, device=dev) if self.STOCHASTIC else None
         self.dice_distributions = z((capacity, T, 6), torch.float32) if self.STOCHASTIC else None
         self.position, self.size = 0, 0
+        self.prioritized, self.max_priority = bool(prioritized), 1.0
+        if self.prioritized:  # fixed-point priorities (2^-20 units) + exact uint64 row sums, see include/dogstep.h
+            self.priorities = z((capacity, T), torch.uint32)
+            self.priority_row_sums = z((capacity,), torch.uint64)
+            self._cdf_work = z((capacity,), torch.uint64)
         self._key = jaxrand.PRNGKey(seed)
         # GAMMA ** k in float64 exactly as NumPy evaluates it in the reference (:228, :234)
         self._gamma_pow = torch.from_numpy(np.float64(GAMMA) ** np.arange(T + 1, dtype=np.int64)).to(dev)
@@ -97,6 +103,11 @@ class VectorizedReplayBuffer:
             traj = self._arrays(src, n_games, T_traj)
             _lib.check(_lib.lib().dogstep_replay_save(C.byref(buf), C.byref(traj), C.c_int64(n_games), _lib.ptr(slot), _lib.stream()),
                        "replay_save")
+            if self.prioritized:  # new episodes enter at the running maximum priority
+                _lib.check(_lib.lib().dogstep_replay_prio_fill(_lib.ptr(self.priorities), _lib.ptr(self.priority_row_sums),
+                                                              _lib.ptr(self.episode_lengths), C.c_int32(self.max_episode_length),
+                                                              _lib.ptr(slot), C.c_int32(n_games), C.c_float(self.max_priority),
+                                                              _lib.stream()), "replay_prio_fill")
             self.position = (self.position + take) % self.capacity
             self.size = min(self.size + take, self.capacity)
             done += take
@@ -133,6 +144,44 @@ class VectorizedReplayBuffer:
                                                    C.c_int32(int(bool(self.bootstrap_value_target))), _lib.ptr(self._gamma_pow),
                                                    _lib.ptr(ep), _lib.ptr(ts), C.byref(cb), _lib.stream()), "replay_gather")
         return out
+
+    # ------------------------------------------------------------------ prioritised sampling (extension)
+    def draw_plan_prioritized(self):
+        """(ep_indices, t_starts, P(e, t) float64) drawn proportionally to the stored priorities"""
+        if not self.prioritized:
+            raise ValueError("buffer was built with prioritized=False")
+        self._key, sub = jaxrand.split_host(self._key)
+        B, dev = self.batch_size, self.device
+        ep, ts = torch.empty(B, dtype=torch.int32, device=dev), torch.empty(B, dtype=torch.int32, device=dev)
+        prob = torch.empty(B, dtype=torch.float64, device=dev)
+        _lib.check(_lib.lib().dogstep_replay_plan_prioritized(_lib.ptr(self.priorities), _lib.ptr(self.priority_row_sums),
+                                                             _lib.ptr(self._cdf_work), C.c_int32(self.size),
+                                                             C.c_int32(self.max_episode_length), C.c_int32(B), _lib.host_key(sub),
+                                                             _lib.ptr(ep), _lib.ptr(ts), _lib.ptr(prob), _lib.stream()),
+                   "replay_plan_prioritized")
+        return ep, ts, prob
+
+    def sample_batch_prioritized(self, beta=1.0):
+        """sample_batch with windows drawn proportionally to priority; adds `ep_indices`, `t_starts` (hand them back to
+        update_priorities) and the importance weights `weights` = (N * P)^-beta / max over the batch."""
+        if self.size < 1:
+            raise ValueError("sample_batch on an empty buffer")
+        ep, ts, prob = self.draw_plan_prioritized()
+        out = self.sample_batch(plan=(ep, ts))
+        n_items = self.episode_lengths[:self.size].sum().clamp(min=1).to(torch.float64)
+        w = (n_items * prob.clamp(min=1e-300)) ** (-float(beta))
+        out["weights"] = (w / w.max()).to(torch.float32)
+        out["ep_indices"], out["t_starts"] = ep, ts
+        return out
+
+    def update_priorities(self, ep_indices, t_starts, priorities):
+        """set the priority of the sampled (episode, ply) pairs (e.g. |search value - target|); float32 >= 0"""
+        pr = self._as(priorities, torch.float32)
+        ep, ts = self._as(ep_indices, torch.int32), self._as(t_starts, torch.int32)
+        self.max_priority = max(self.max_priority, float(pr.max().item()))
+        _lib.check(_lib.lib().dogstep_replay_prio_update(_lib.ptr(self.priorities), _lib.ptr(self.priority_row_sums),
+                                                        C.c_int32(self.max_episode_length), C.c_int32(int(ep.numel())), _lib.ptr(ep),
+                                                        _lib.ptr(ts), _lib.ptr(pr), _lib.stream()), "replay_prio_update")
 
     def sample_batch_global(self, group=None):
         """Every rank samples `batch_size` windows from its own shard; the batches are all-gathered (NCCL over NVLink on

@@ -313,6 +313,23 @@ int dogstep_replay_gather(const dogstep_replay_arrays* buf, int32_t batch_size, 
                           int32_t bootstrap_value_target, const double* gamma_pow, const int32_t* ep_indices,
                           const int32_t* t_starts, const dogstep_replay_batch* out, void* stream);
 
+/* Prioritised sampling — an EXTENSION: the reference samples uniformly with a terminal quota (vec_replay_buffer.py:73-97);
+ * BASELINE's north star asks for prioritised sampling on the per-GPU shard.  Proportional prioritisation
+ * P(e, t) = p[e, t] / sum(p) over fixed-point priorities: prio uint32 [capacity, T] in 2^-20 units, row_sum uint64 [capacity];
+ * every sum is an exact integer, so the result does not depend on summation order.
+ *   prio_fill    rows[i] (int32, -1 = skip) get `value` for t < episode_lengths[row], 0 beyond; row sums recomputed
+ *   prio_update  prio[ep[b], t[b]] = value[b] (float32 [B]); row sums follow atomically
+ *   plan_prioritized  batch_size draws: target = floor(bits64 * total / 2^64) (threefry bits 2b, 2b+1 of host_key), episode
+ *                     by binary search in the scanned row sums (cdf_work: uint64 [capacity] scratch), ply by a row scan;
+ *                     prob[b] = P(e, t) as float64 (for importance weights) */
+int dogstep_replay_prio_fill(uint32_t* prio, unsigned long long* row_sum, const int32_t* episode_lengths, int32_t max_episode_length,
+                             const int32_t* rows, int32_t n_rows, float value, void* stream);
+int dogstep_replay_prio_update(uint32_t* prio, unsigned long long* row_sum, int32_t max_episode_length, int32_t batch_size,
+                               const int32_t* ep_indices, const int32_t* t_starts, const float* value, void* stream);
+int dogstep_replay_plan_prioritized(const uint32_t* prio, const unsigned long long* row_sum, unsigned long long* cdf_work, int32_t size,
+                                    int32_t max_episode_length, int32_t batch_size, const uint32_t* host_key, int32_t* ep_indices,
+                                    int32_t* t_starts, double* prob, void* stream);
+
 /* ---------------------------------------------------------------- self-play bookkeeping
  * One lockstep iteration of play_batch_of_games_jitted AFTER the search (MuZero_det_MADN/game_agent.py:64-148,
  * MuZero_Classic_MADN/game_agent_stochastic.py:86-204): for every game that is not done, env_step(map_action(action)) if a

@@ -107,3 +107,39 @@ class ReplayOracle:
                     target = z
                 out["target_values"][b, k] = np.float32(min(max(target, -1.0), 1.0))
         return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Prioritised sampling (extension beyond the reference; include/dogstep.h "Prioritised sampling").  Fixed-point priorities
+# and Python integers: exact, so the CUDA path must agree bit for bit.
+PRIO_SHIFT = 20
+
+
+def prio_to_fixed(p):
+    p = np.asarray(p, np.float32)
+    v = np.floor(p.astype(np.float64) * float(1 << PRIO_SHIFT) + 0.5)
+    return np.where(p > 0, np.minimum(v, 4294967295.0), 0.0).astype(np.uint64).astype(np.uint32)
+
+
+def plan_prioritized(prio_fixed, size, bits):
+    """prio_fixed uint32 [capacity, T]; bits uint32 [2B] (threefry bits of the draw key) -> ep, t, prob"""
+    prio = np.asarray(prio_fixed, np.uint64)[:size]
+    row_sum = [int(x) for x in prio.sum(1, dtype=np.uint64)]
+    cdf = np.cumsum(np.array(row_sum, dtype=object))
+    total = int(cdf[-1])
+    B = len(bits) // 2
+    ep, ts, prob = np.zeros(B, np.int32), np.zeros(B, np.int32), np.zeros(B, np.float64)
+    for b in range(B):
+        b64 = (int(bits[2 * b]) << 32) | int(bits[2 * b + 1])
+        target = (b64 * total) >> 64
+        e = next(i for i in range(size) if int(cdf[i]) > target)
+        r = target - (int(cdf[e - 1]) if e else 0)
+        acc, t, pv = 0, 0, 0
+        for k in range(prio.shape[1]):
+            pv = int(prio[e, k])
+            acc += pv
+            t = k
+            if acc > r:
+                break
+        ep[b], ts[b], prob[b] = e, t, (pv / total if total else 0.0)
+    return ep, ts, prob
