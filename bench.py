@@ -167,16 +167,17 @@ def measure_extras(dev, key):
         srch.init(keys, root, None, None)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        srch.select(0)
         for sim in range(S):
-            srch.select(sim)
             k = sim % R
-            srch.expand(sim, pl[k], val[k], rew[k], disc[k], emb[k], cl[k], val[(k + 1) % R], emb[(k + 1) % R])
+            step = srch.expand_select if sim + 1 < S else srch.expand  # expand(sim) + select(sim + 1): one launch
+            step(sim, pl[k], val[k], rew[k], disc[k], emb[k], cl[k], val[(k + 1) % R], emb[(k + 1) % R])
         e1.record()
         torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     out["mcts_cfg3_tree_only"] = {"workload": "cfg3 tree kernels alone (select + expand/backup, precomputed network outputs)",
-                                  "sims": n * S, "ms": ms, "sims_per_s": n * S / (ms / 1e3), "gpu_launches": 2 * S,
-                                  "roofline": {"bound": "hbm", "kernel": "k_mcts_select + k_mcts_expand",
+                                  "sims": n * S, "ms": ms, "sims_per_s": n * S / (ms / 1e3), "gpu_launches": S + 1,
+                                  "roofline": {"bound": "hbm", "kernel": "k_mcts_expand_select",
                                                "algorithmic_bytes_per_sim": bytes_per_sim, "achieved": n * S * bytes_per_sim / (ms / 1e3) / 1e9,
                                                "peak": peak, "unit": "GB/s", "frac": n * S * bytes_per_sim / (ms / 1e3) / 1e9 / peak}}
     return out

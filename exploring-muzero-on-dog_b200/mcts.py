@@ -135,6 +135,24 @@ class Search:
                                                  _lib.ptr(f(embedding)), _lib.ptr(f(chance_logits)), _lib.ptr(f(afterstate_value)),
                                                  _lib.ptr(f(afterstate_embedding)), _lib.stream()), "mcts_expand")
 
+    def expand_select(self, sim, prior_logits, value, reward, discount, embedding, chance_logits=None, afterstate_value=None,
+                      afterstate_embedding=None):
+        """expand(sim) followed by select(sim + 1) in one launch; refreshes self.parent / action / embedding / is_decision /
+        expand_key in place and returns them like select()"""
+        f = lambda x: None if x is None else x.float().contiguous()
+        emb, aemb = f(embedding), f(afterstate_embedding)
+        if emb.data_ptr() == self.embedding.data_ptr():
+            emb = emb.clone()
+        if aemb is not None and aemb.data_ptr() == self.embedding.data_ptr():
+            aemb = aemb.clone()
+        _lib.check(_lib.lib().dogstep_mcts_expand_select(C.byref(self._ct), C.c_int64(self.n), C.byref(self.cfg), C.c_int32(sim),
+                                                        _lib.ptr(self.parent), _lib.ptr(self.action), _lib.ptr(f(prior_logits)),
+                                                        _lib.ptr(f(value)), _lib.ptr(f(reward)), _lib.ptr(f(discount)), _lib.ptr(emb),
+                                                        _lib.ptr(f(chance_logits)), _lib.ptr(f(afterstate_value)), _lib.ptr(aemb),
+                                                        _lib.ptr(self.embedding), _lib.ptr(self.is_decision), _lib.ptr(self.expand_key),
+                                                        _lib.stream()), "mcts_expand_select")
+        return self.parent, self.action, self.embedding, self.is_decision
+
     def policy_output(self):
         A = self.cfg.num_actions
         action = torch.empty(self.n, dtype=torch.int32, device=self.device)
@@ -147,10 +165,12 @@ class Search:
 
 def _run(search, params, root, recurrent_fn, invalid_actions, keys, dirichlet_noise=None):
     search.init(keys, root, invalid_actions, dirichlet_noise)
-    for sim in range(search.cfg.num_simulations):
-        _, action, emb, _ = search.select(sim)
+    S = search.cfg.num_simulations
+    _, action, emb, _ = search.select(0)
+    for sim in range(S):
         out, nxt = recurrent_fn(params, search.expand_key, action.long(), emb)
-        search.expand(sim, out.prior_logits, out.value, out.reward, out.discount, nxt.reshape(search.n, -1))
+        step = search.expand_select if sim + 1 < S else search.expand  # expand(sim) + select(sim + 1) fused into one launch
+        step(sim, out.prior_logits, out.value, out.reward, out.discount, nxt.reshape(search.n, -1))
     return search.policy_output()[0]
 
 
@@ -258,13 +278,13 @@ def stochastic_muzero_policy(params, rng_key, root, decision_recurrent_fn, chanc
 
     def search_loop(s, st):
         s.init(st["keys"], RootFnOutput(st["prior"], st["value"], st["emb"]), st["invalid"], st["noise"])
+        _, action, emb, is_dec = s.select(0)
         for sim in range(num_simulations):
-            _, action, emb, is_dec = s.select(sim)
             a = action.long()
             dec, after = decision_recurrent_fn(params, None, a.clamp(max=A - 1), emb[:, :Es])
             ch, nxt = chance_recurrent_fn(params, None, (a - A).clamp(min=0, max=Cn - 1), emb[:, :Ea])
-            s.expand(sim, ch.action_logits, ch.value, ch.reward, ch.discount, pad(nxt), dec.chance_logits, dec.afterstate_value,
-                     pad(after))
+            step = s.expand_select if sim + 1 < num_simulations else s.expand
+            step(sim, ch.action_logits, ch.value, ch.reward, ch.discount, pad(nxt), dec.chance_logits, dec.afterstate_value, pad(after))
         return s.policy_output()[0]
 
     inputs = dict(keys=rng_key, prior=root.prior_logits.float(), value=root.value.float(), emb=pad(state_emb),

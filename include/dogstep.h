@@ -255,6 +255,15 @@ int dogstep_mcts_expand(const dogstep_mcts_tree* t, int64_t n, const dogstep_mct
                         const int32_t* action, const float* prior_logits, const float* value, const float* reward,
                         const float* discount, const float* embedding, const float* chance_logits,
                         const float* afterstate_value, const float* afterstate_embedding, void* stream);
+/* expand + backup of simulation `sim` followed by the descent of simulation sim + 1 in ONE launch (the search loop always
+ * issues them back to back; the caller's network sits between a select and the next expand).  `parent` / `action` are read
+ * (the leaf edge chosen by the previous select) and then overwritten with the next leaf edge; embedding_out must not alias
+ * the expand inputs.  Requires sim + 1 < num_simulations; results identical to expand(sim) then select(sim + 1). */
+int dogstep_mcts_expand_select(const dogstep_mcts_tree* t, int64_t n, const dogstep_mcts_cfg* cfg, int32_t sim, int32_t* parent,
+                               int32_t* action, const float* prior_logits, const float* value, const float* reward,
+                               const float* discount, const float* embedding, const float* chance_logits,
+                               const float* afterstate_value, const float* afterstate_embedding, float* embedding_out,
+                               uint8_t* is_decision_out, uint32_t* expand_key_out, void* stream);
 /* policy epilogue: action i32 [n], action_weights f32 [n,A], root_value f32 [n] (= search_tree.summary().value) */
 int dogstep_mcts_policy_output(const dogstep_mcts_tree* t, int64_t n, const dogstep_mcts_cfg* cfg, int32_t* action,
                                float* action_weights, float* root_value, void* stream);

@@ -28,17 +28,20 @@ for rep in range(3):
     s.init(keys, root, None, None)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * S + 1)]
     ev[0].record()
+    fused = os.environ.get("FUSED", "1") == "1"
+    if fused:
+        s.select(0)
     for sim in range(S):
-        s.select(sim)
+        if not fused:
+            s.select(sim)
         ev[2 * sim + 1].record()
         k = sim % R
+        step = s.expand_select if (fused and sim + 1 < S) else s.expand
         if policy == mcts.STOCHASTIC:
-            s.expand(sim, pl[k], val[k], rew[k], disc[k], emb[k], cl[k], val[(k + 1) % R], emb[(k + 1) % R])
+            step(sim, pl[k], val[k], rew[k], disc[k], emb[k], cl[k], val[(k + 1) % R], emb[(k + 1) % R])
         else:
-            s.expand(sim, pl[k], val[k], rew[k], disc[k], emb[k])
+            step(sim, pl[k], val[k], rew[k], disc[k], emb[k])
         ev[2 * sim + 2].record()
     torch.cuda.synchronize()
-    sel = sum(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(S))
-    exp = sum(ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(S))
     tot = ev[0].elapsed_time(ev[-1])
-    print(f"{shape} n={n} S={S} A'={A+Cn}: total {tot:.2f} ms  select {sel:.2f} ms  expand {exp:.2f} ms  -> {n*S/tot/1e3:.2f} M sims/s (tree kernels only)")
+    print(f"{shape} n={n} S={S} A'={A+Cn} fused={int(fused)}: total {tot:.2f} ms -> {n*S/tot/1e3:.2f} M sims/s (tree kernels only)")
