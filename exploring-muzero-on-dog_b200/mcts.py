@@ -67,6 +67,7 @@ class Tree:
         self.root_invalid_actions = e((n, A), dtype=torch.uint8)
         self.root_gumbel = e((n, A), dtype=f32) if policy == GUMBEL else None
         self.search_key, self.policy_key = e((n, 2), dtype=torch.uint32), e((n, 2), dtype=torch.uint32)
+        self.path = torch.zeros((n, 65), dtype=i32, device=device)  # descent scratch for the parallel backup
         self.num_actions, self.num_chance, self.n = num_actions, num_chance, n
 
     def cstruct(self):

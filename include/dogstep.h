@@ -232,6 +232,9 @@ typedef struct {
   float* root_gumbel;             /* [n, A'] gumbel only (may be NULL otherwise) */
   uint32_t* search_key;           /* [n, 2]  key chain of search(): rng, sim, exp = split(rng, 3) per simulation */
   uint32_t* policy_key;           /* [n, 2]  key of the final categorical draw (muzero / stochastic) */
+  int32_t* path;                  /* [n, 65] optional scratch (NULL allowed): select records the descent (edge count, then
+                                   * (node, action) for the first 32 edges) and expand uses it to fetch every level of the
+                                   * backup at once instead of walking parent pointers; results are identical */
 } dogstep_mcts_tree;
 
 /* policy prologue + instantiate_tree_from_root.  keys: uint32 [n,2] = the rng_key each game hands to the mctx policy.
