@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(kDogThreads) k_dog_random_step(const __grid_co
   if (active_count && lane == 0) atomicAdd(active_count, 1ull);
 }
 
-__global__ void __launch_bounds__(kDogThreads, 8) k_dog_play_random(const __grid_constant__ DogGeom g, DogPtrs p, int64_t n, Key2 rng0,
+__global__ void __launch_bounds__(kDogThreads, 10) k_dog_play_random(const __grid_constant__ DogGeom g, DogPtrs p, int64_t n, Key2 rng0,
                                                                  int64_t game_offset, int max_steps,
                                                                  int32_t* __restrict__ game_len,
                                                                  unsigned long long* __restrict__ total_steps) {
