@@ -74,7 +74,6 @@ struct alignas(16) DogS {
   uint32_t key[2];
   int cur, reward, done, round_starter, phase, hand_size;
   uint32_t mask[kDogMaskWords];
-  uint32_t sortkey[128];
   uint16_t items[2 * (4 * (13 + 64) + 120) + kNCard + 2];
   int scratch[8];
   uint64_t pbits[4];  // bit c of pbits[p]: a pin of player p stands on cell c (kept by the dog_fast.cuh path)
@@ -558,31 +557,37 @@ __device__ __noinline__ void dog_distribute_cards(const DogGeom& g, DogS& s, int
   __syncwarp();
   const Key2 key{s.key[0], s.key[1]};
   const Key2 knew = split_i(key, 0), sub = split_i(key, 1);
-  // slot j of the expanded pool holds card type c iff cum[c] <= j < cum[c+1]; dummies after the real cards
-  int cum = 0, deck_total = 0;
+  // slot j of the expanded pool holds card type c iff cum[c] <= j < cum[c+1]; dummies after the real cards.
+  // argsort(uniform) is only needed for its first n*quantity entries: every lane keeps its four (uniform, index) keys and
+  // card types in registers and the warp extracts the minimum `need` times with redux.sync (stable: the index is in the key)
+  int deck_total = 0;
   for (int k = 0; k < kNCard; ++k) deck_total += s.deck[k];
+  uint32_t sk[4];
+  int ct[4];
+#pragma unroll
   for (int r = 0; r < 4; ++r) {
-    int j = lane + 32 * r;
-    uint32_t sk = 0xFFFFFFFFu;
-    if (j < 120 && j < deck_total) sk = ((bits_i(sub, (uint32_t)j) >> 9) << 7) | (uint32_t)j;  // stable order by (uniform, index)
-    s.sortkey[j] = sk;
+    const int j = lane + 32 * r;
+    sk[r] = 0xFFFFFFFFu;
+    ct[r] = 0;
+    if (j < 120 && j < deck_total) {
+      sk[r] = ((bits_i(sub, (uint32_t)j) >> 9) << 7) | (uint32_t)j;
+      int c = 0, acc = s.deck[0];
+      while (j >= acc) { ++c; acc += s.deck[c]; }
+      ct[r] = c;
+    }
   }
-  (void)cum;
-  __syncwarp();
-  // rank of each real slot among all slots; the first n*quantity ranks are dealt in order
   const int need = n * quantity;
-  for (int r = 0; r < 4; ++r) {
-    int j = lane + 32 * r;
-    uint32_t mine = s.sortkey[j];
-    if (mine != 0xFFFFFFFFu) {
-      int rank = 0;
-#pragma unroll 8
-      for (int k = 0; k < 120; ++k) rank += (s.sortkey[k] < mine);
-      if (rank < need) {
-        int c = 0, acc = s.deck[0];
-        while (j >= acc) { ++c; acc += s.deck[c]; }
-        s.items[rank] = (uint16_t)c;
-      }
+  for (int rank = 0; rank < need; ++rank) {
+    const uint32_t mine = min(min(sk[0], sk[1]), min(sk[2], sk[3]));
+    const uint32_t m = __reduce_min_sync(0xFFFFFFFFu, mine);
+    if (m == 0xFFFFFFFFu) break;  // fewer real cards than seats x hand size
+    if (mine == m) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        if (sk[r] == m) {
+          if (rank < (int)(sizeof(s.items) / sizeof(s.items[0]))) s.items[rank] = (uint16_t)ct[r];
+          sk[r] = 0xFFFFFFFFu;
+        }
     }
   }
   __syncwarp();
