@@ -180,3 +180,20 @@ def test_action_maps_roundtrip():
     assert np.array_equal(back.numpy(), acts)
     assert int(dog.map_move_to_action(env, np.zeros(6, np.int64))) == 739  # DOG/speedtest.ipynb cell 16
     assert dog.get_play_action_size(env) == 792
+
+
+@pytest.mark.parametrize("n", [1, 33, 200])
+def test_play_random_ragged_sizes_caps_and_resume(n):
+    """the persistent phase-synchronous kernel with fewer games than warps / CTAs, a step cap and resumption"""
+    dog = _dog()
+    from exploring_muzero_on_dog_b200 import jaxrand
+    key = jaxrand.split_host(jaxrand.PRNGKey(3))[0]
+    seeds = np.arange(n, dtype=np.int32) * 17 + 1
+    cfg = O.DogCfg(4, 0xF, 10, mask_of(DOG_RULES))
+    env = dog.env_reset(0, seed=seeds, **DOG_RULES)
+    s = O.dog_reset(cfg, seeds, 0)
+    for cap in (0, 25, 700, 2000):
+        _, glen = dog.play_random(env, key, max_steps=cap, game_offset=3)
+        olen, _, _ = O.dog_play_random(s, key, cap, game_offset=3, nthreads=8)
+        assert_state_equal(s, env.numpy())
+        assert np.array_equal(olen, glen.cpu().numpy())

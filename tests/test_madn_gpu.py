@@ -243,3 +243,42 @@ def test_random_helpers_match_oracle():
     assert np.array_equal(jaxrand.uniform(key, 1000, 1.17549435e-38, 1.0).cpu().numpy(), O.uniform(key, 1000, 1.17549435e-38, 1.0))
     assert np.array_equal(jaxrand.randint(key, 1000, 0, 1_000_000).cpu().numpy(), O.randint(key, 1000, 0, 1_000_000))
     assert np.array_equal(jaxrand.randint(key, 1000, -5, 4).cpu().numpy(), O.randint(key, 1000, -5, 4))
+
+
+@pytest.mark.parametrize("n", [1, 31, 33, 449, 1000])
+def test_det_play_random_ragged_sizes_caps_and_resume(n):
+    """the persistent kernel on sizes that leave warps / CTAs partly empty, with a step cap (games stopped mid-way keep
+    their exact intermediate state), resumed from that state (some games already done at load), with a game offset"""
+    dm = _dm()
+    from exploring_muzero_on_dog_b200 import jaxrand
+    key = jaxrand.split_host(jaxrand.PRNGKey(7))[0]
+    seeds = np.arange(n, dtype=np.int32) * 31 + 5
+    cfg = O.MadnCfg(4, 0xF, 10, mask_of(TRAIN_RULES))
+    env = dm.env_reset(0, seed=seeds, **TRAIN_RULES)
+    s = O.madn_reset(cfg, seeds, 0)
+    for cap in (0, 37, 320, 2000):  # resumed again and again: 320 leaves a mix of finished and running games
+        _, glen = dm.play_random(env, key, max_steps=cap, game_offset=11)
+        olen, _, _ = O.madn_det_play_random(s, key, cap, game_offset=11)
+        assert_state_equal(s, env.numpy())
+        assert np.array_equal(olen, glen.cpu().numpy())
+    assert env.numpy()["done"].all()
+
+
+def test_det_play_random_non_canonical_games_take_the_generic_rules():
+    """a CTA that loads a game outside the canonical form (here: two players on one cell, an out-of-range player id)
+    must give the generic kernel's / the oracle's answer for every game it owns"""
+    dm = _dm()
+    from exploring_muzero_on_dog_b200 import jaxrand
+    n = 600
+    key = jaxrand.split_host(jaxrand.PRNGKey(9))[1]
+    cfg = O.MadnCfg(4, 0xF, 10, mask_of(TRAIN_RULES))
+    s = O.madn_reset(cfg, np.arange(n, dtype=np.int32), 0)
+    O.madn_det_play_random(s, key, 60)           # some plies in, so that pins are spread out
+    s.pins[5, 1, 0] = s.pins[5, 0, 0]            # player 1 stacked onto player 0's first pin
+    s.board[5] = O.madn_set_pins_on_board(cfg, s.pins[5:6])[0]
+    s.board[450, 17] = 2                         # board that contradicts the pins
+    env = _upload_det(dm, s, TRAIN_RULES)
+    _, glen = dm.play_random(env, key, max_steps=2000)
+    olen, _, _ = O.madn_det_play_random(s, key, 2000)
+    assert_state_equal(s, env.numpy())
+    assert np.array_equal(olen, glen.cpu().numpy())
