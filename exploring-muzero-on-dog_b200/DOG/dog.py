@@ -62,6 +62,22 @@ class DOG(BatchedEnv):
                                 "round_starter", "phase", "key", "hand_size")])
 
 
+RAW_OBS_SIZE = 56 + 14 + 4
+
+
+def raw_observation(env):
+    """int8 [n, 74]: board | the mover's own hand | phase, hand_size, current_player, round_starter.  NOT a reference function:
+    the reference has no DOG encoder (DOG/dog.py:1264-1272 is a TODO); config 5's self-play slice needs some observation row to
+    record, and this one exposes only what the mover may see.  Plain tensor indexing (plumbing, not a kernel)."""
+    t = env._t
+    n = env.n
+    cur = t["current_player"].reshape(n).long() % env.static["num_players"]
+    own = t["hands"].reshape(n, env.static["num_players"], 14)[torch.arange(n, device=env.device), cur]
+    misc = torch.stack([t["phase"].reshape(n), t["hand_size"].reshape(n), t["current_player"].reshape(n),
+                        t["round_starter"].reshape(n)], 1)
+    return torch.cat([t["board"].reshape(n, -1), own, misc], 1).to(torch.int8).contiguous()
+
+
 def get_play_action_size(env):
     return int(2 * (4 * (12 + 1 + env.static["total_board_size"]) + 120))
 

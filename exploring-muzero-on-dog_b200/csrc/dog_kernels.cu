@@ -233,6 +233,68 @@ __global__ void __launch_bounds__(kDogThreads) k_dog_substep(const __grid_consta
   if (lane < g.n * 4) pins_out[i * g.n * 4 + lane] = s.pins[lane >> 2][lane & 3];
 }
 
+// ---- self-play bookkeeping for DOG (BASELINE config 5): one lockstep iteration after the search ------------------------
+// The reference has no DOG self-play loop (MuZero_DOG/muzero_dog.py:85-99 are stubs), so this is the det-MADN loop
+// (MuZero_det_MADN/game_agent.py:64-148, do_active_step) applied to the DOG env: env_step(action) if a legal action
+// exists else no_step, reward / discount class targets and the trajectory row at traj.episode_lengths[g].  One warp per
+// game; the 806-wide policy row and the observation row are copied by all lanes.
+__global__ void __launch_bounds__(kDogThreads) k_dog_agent_step(const __grid_constant__ DogGeom g, DogPtrs p, int64_t n,
+                                                                const int32_t* __restrict__ action,
+                                                                const float* __restrict__ root_value,
+                                                                const float* __restrict__ weights, const int8_t* __restrict__ obs,
+                                                                dogstep_replay_arrays tr) {
+  DOG_KERNEL_PROLOGUE
+  if (i >= n) return;
+  if (p.done[i] != 0) return;  // do_skip_step: finished games are left untouched (warp-uniform)
+  dog_load(g, p, i, s, lane);
+  dog_build_mask_any(g, s, lane);
+  __syncwarp();
+  uint32_t anyw = 0u;
+  for (int w = lane; w < kDogMaskWords; w += 32) anyw |= s.mask[w];
+  const int has_valid = __any_sync(0xFFFFFFFFu, anyw != 0u);
+  const int teams = DG_RULE(g, DOGSTEP_RULE_TEAMS);
+  const int pid = s.cur;
+  const int team_before = teams ? (((pid % 2) + 2) % 2) : -1;
+  const int idx = tr.episode_lengths[i];
+  __syncwarp();
+  int act = -1, rew_t = 1, disc_t = 1;
+  if (has_valid) {
+    int r, d;
+    act = action[i];
+    dog_env_step_any(g, s, lane, act, r, d);
+    __syncwarp();
+    const int next = s.cur;
+    const int next_team = teams ? (((next % 2) + 2) % 2) : -1;
+    rew_t = (d && r > 0) ? 2 : ((d && r < 0) ? 0 : 1);
+    disc_t = d ? 1 : (teams ? (team_before == next_team ? 2 : 0) : (pid == next ? 2 : 0));
+  } else {
+    dog_no_step(g, s, lane);
+  }
+  dog_store(g, p, i, s, lane);
+  if (lane == 0) tr.episode_lengths[i] = idx + 1;
+  if (idx < 0 || idx >= tr.max_episode_length) return;  // .at[idx].set drops out-of-range rows
+  const int64_t r = i * tr.max_episode_length + idx;
+  if (lane == 0) {
+    tr.actions[r] = act;
+    tr.rewards[r] = rew_t;
+    tr.root_values[r] = has_valid ? root_value[i] : 0.0f;
+    tr.masks[r] = has_valid ? 1.0f : 0.0f;
+    tr.players[r] = pid;
+    tr.teams[r] = team_before;
+    tr.discounts[r] = disc_t;
+  }
+  const int A = tr.action_dim;
+  for (int k = lane; k < A; k += 32) tr.child_visits[r * A + k] = has_valid ? weights[i * A + k] : 0.0f;
+  const int8_t* src = obs + i * tr.obs_size;
+  if (tr.obs_is_int8) {
+    int8_t* d = (int8_t*)tr.observations + r * tr.obs_size;
+    for (int k = lane; k < tr.obs_size; k += 32) d[k] = has_valid ? src[k] : (int8_t)0;
+  } else {
+    float* d = (float*)tr.observations + r * tr.obs_size;
+    for (int k = lane; k < tr.obs_size; k += 32) d[k] = has_valid ? (float)src[k] : 0.0f;
+  }
+}
+
 __device__ __forceinline__ void dog_random_turn(const DogGeom& g, DogS& s, int lane, Key2 key) {
   dog_build_mask_any(g, s, lane);
   int a = dog_categorical(g, s, lane, key);
@@ -424,6 +486,21 @@ int dogstep_dog_play_random(const dogstep_dog_state* s, int64_t n, const dogstep
   cudaFuncSetAttribute(k_dog_play_random, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   k_dog_play_random<<<grid, kSyncWarps * 32, smem, st>>>(g, p, n, Key2{host_rng_key[0], host_rng_key[1]}, game_offset, max_steps,
                                                         game_len, total_steps);
+  return check_launch();
+}
+
+int dogstep_dog_agent_step(const dogstep_dog_state* s, int64_t n, const dogstep_dog_cfg* cfg, const int32_t* action,
+                           const float* root_value, const float* action_weights, const int8_t* obs,
+                           const dogstep_replay_arrays* traj, void* stream) {
+  DOG_PROLOGUE
+  if (!action || !root_value || !action_weights || !traj) return DOGSTEP_ERR_INVALID_ARG;
+  if (traj->capacity < n || traj->action_dim != g.num_actions || traj->stochastic != 0 || traj->obs_size < 0 ||
+      (traj->obs_size > 0 && !obs))
+    return DOGSTEP_ERR_INVALID_ARG;
+  if (!traj->observations || !traj->actions || !traj->rewards || !traj->root_values || !traj->child_visits || !traj->masks ||
+      !traj->players || !traj->teams || !traj->discounts || !traj->episode_lengths)
+    return DOGSTEP_ERR_INVALID_ARG;
+  k_dog_agent_step<<<dog_blocks(n), kDogThreads, 0, st>>>(g, p, n, action, root_value, action_weights, obs, *traj);
   return check_launch();
 }
 

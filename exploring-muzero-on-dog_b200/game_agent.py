@@ -16,12 +16,15 @@ import numpy as np
 import torch
 
 from . import _lib, jaxrand, mcts
+from .DOG import dog as dg
 from .MADN import classic_madn as cm
 from .MADN import deterministic_madn as dm
 
 RULES = dict(enable_teams=True, enable_initial_free_pin=True, enable_circular_board=False, enable_friendly_fire=False,
              enable_start_blocking=False, enable_jump_in_goal_area=True, enable_start_on_1=True, enable_bonus_turn_on_6=True,
              must_traverse_start=False)  # MuZero_det_MADN/game_agent.py:12-22
+DOG_RULES = dict(enable_teams=True, enable_initial_free_pin=False, enable_circular_board=True, enable_friendly_fire=True,
+                 enable_start_blocking=True, enable_jump_in_goal_area=False, must_traverse_start=True)  # MuZero_DOG/game_agent.py:12-23
 
 
 def _split_each(keys, index):
@@ -87,8 +90,10 @@ class Trajectories:
 
 def agent_step(envs, traj, action, root_value, action_weights, obs):
     """the post-search part of one lockstep iteration (fused kernel), in place"""
-    det = isinstance(envs, dm.deterministic_MADN)
-    fn = _lib.lib().dogstep_madn_det_agent_step if det else _lib.lib().dogstep_madn_cls_agent_step
+    if isinstance(envs, dg.DOG):
+        fn = _lib.lib().dogstep_dog_agent_step
+    else:
+        fn = _lib.lib().dogstep_madn_det_agent_step if isinstance(envs, dm.deterministic_MADN) else _lib.lib().dogstep_madn_cls_agent_step
     cfg, st, tr = envs.cfg(), envs.cstate(), traj.carrays()
     _lib.check(fn(C.byref(st), C.c_int64(envs.n), C.byref(cfg), _lib.ptr(action.to(torch.int32).contiguous()),
                   _lib.ptr(root_value.float().contiguous()), _lib.ptr(action_weights.float().contiguous()),
@@ -100,10 +105,12 @@ def play_batch_of_games(envs, num_envs, input_shape, params, rng_key, num_simula
     """play_batch_of_games_jitted (game_agent.py:50-183 / game_agent_stochastic.py:52-218).
     search_fn(params, step_keys [n,2], obs int8 [n,C,T], invalid bool [n,A]) -> (action [n], action_weights [n,A], root_value [n]).
     `envs` is stepped in place.  Returns the buffers dict the reference returns."""
-    det = isinstance(envs, dm.deterministic_MADN)
+    dog = isinstance(envs, dg.DOG)
+    det = dog or isinstance(envs, dm.deterministic_MADN)
     mod = dm if det else cm
     dev = envs.device
-    traj = Trajectories(num_envs, max_steps, input_shape, 24 if det else 4, not det, dev, obs_dtype)
+    action_dim = dg.get_play_action_size(envs) + 14 if dog else (24 if det else 4)
+    traj = Trajectories(num_envs, max_steps, input_shape, action_dim, not det, dev, obs_dtype)
     key = np.asarray(rng_key, dtype=np.uint32)
     step = 0
     while step < max_steps and not bool(envs.raw("done").all()):
@@ -114,8 +121,10 @@ def play_batch_of_games(envs, num_envs, input_shape, params, rng_key, num_simula
             cfg, st = envs.cfg(), envs.cstate()
             _lib.check(_lib.lib().dogstep_madn_cls_throw_die_active(C.byref(st), C.c_int64(envs.n), C.byref(cfg), _lib.stream()),
                        "throw_die_active")
-        obs = mod.encode_board(envs)
-        valid = mod.valid_action(envs).reshape(num_envs, -1)
+        if dog:  # the reference has no DOG encoder (DOG/dog.py:1264-1272): raw mover-view leaves stand in for it
+            obs, valid = dg.raw_observation(envs), dg.valid_actions(envs)
+        else:
+            obs, valid = mod.encode_board(envs), mod.valid_action(envs).reshape(num_envs, -1)
         action, weights, value = search_fn(params, step_keys, obs, ~valid)
         agent_step(envs, traj, action, value, weights, obs)
         step += 1
@@ -136,3 +145,24 @@ def play_n_games_v3(params, rng_key, input_shape, num_envs, num_simulation, max_
 
     return play_batch_of_games(envs, num_envs, input_shape, params, subkey, num_simulation, max_depth, max_steps, temp,
                                search_fn=search_fn, obs_dtype=obs_dtype)
+
+
+def play_n_dog_games(params, rng_key, num_envs, num_simulation, max_depth, max_steps, temp, *, root_fn, recurrent_fn, rules=DOG_RULES,
+                     obs_dtype=torch.int8, device="cuda", max_num_considered_actions=16):
+    """BASELINE config 5: play_n_games_v3's shape (game_agent.py:185-192) on the DOG env (MuZero_DOG/game_agent.py:12-44 rules and
+    batch_reset), Gumbel MuZero search over the 806 DOG actions (MuZero_DOG/muzero_dog.py:101-136).  The reference's DOG
+    networks are stubs, so root_fn / recurrent_fn are the caller's."""
+    rng_key, subkey = jaxrand.split_host(rng_key)
+    seeds = jaxrand.randint(subkey, num_envs, 0, 1000000, device=device)
+    envs = dg.env_reset(0, num_players=4, distance=10, starting_player=0, seed=seeds, device=device, **rules)
+
+    def search_fn(p, keys, obs, invalid):
+        key2 = _split_each(keys, 1)
+        out = mcts.gumbel_muzero_policy(p, key2, root_fn(p, obs.to(torch.float32)), recurrent_fn, num_simulation,
+                                        invalid_actions=invalid, max_depth=max_depth,
+                                        qtransform=functools.partial(mcts.qtransform_completed_by_mix_value, value_scale=0.5),
+                                        gumbel_scale=temp, max_num_considered_actions=max_num_considered_actions)
+        return out.action, out.action_weights, out.search_tree.summary().value
+
+    return envs, play_batch_of_games(envs, num_envs, (dg.RAW_OBS_SIZE,), params, subkey, num_simulation, max_depth, max_steps, temp,
+                                     search_fn=search_fn, obs_dtype=obs_dtype)

@@ -356,6 +356,14 @@ int dogstep_madn_cls_agent_step(const dogstep_madn_cls_state* s, int64_t n, cons
                                 const dogstep_replay_arrays* traj, void* stream);
 /* throw_die for the games that are not done (game_agent_stochastic.py:90 runs inside do_active_step) */
 int dogstep_madn_cls_throw_die_active(const dogstep_madn_cls_state* s, int64_t n, const dogstep_madn_cfg* cfg, void* stream);
+/* The same iteration on the DOG env (BASELINE config 5).  The reference has no DOG self-play loop — MuZero_DOG/muzero_dog.py:85-99
+ * are stubs and DOG/dog.py:1264-1272 has no observation encoder — so this applies do_active_step of
+ * MuZero_det_MADN/game_agent.py:64-148 to DOG/dog.py's env_step (:1117) / no_step (:713) / valid_actions (:693):
+ * traj.action_dim = dogstep_dog_num_actions(cfg) (806), obs: int8 [n, traj.obs_size] supplied by the caller (may be NULL
+ * when traj.obs_size == 0). */
+int dogstep_dog_agent_step(const dogstep_dog_state* s, int64_t n, const dogstep_dog_cfg* cfg, const int32_t* action,
+                           const float* root_value, const float* action_weights, const int8_t* obs,
+                           const dogstep_replay_arrays* traj, void* stream);
 
 /* ---------------------------------------------------------------- TicTacToe (BASELINE config 1)
  * Batched leaves of `TicTacToe` / `TicTacToeV2` (TicTacToe/TicTacToe.py:12-17, TicTacToeV2.py:14-20).

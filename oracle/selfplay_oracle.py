@@ -76,3 +76,57 @@ def play_batch_of_games(state, max_steps, rng_key, search_fn, teams):
                 getattr(state, f)[g] = v[g]
         step += 1
     return buf
+
+
+def dog_raw_observation(state):
+    """NumPy twin of DOG.dog.raw_observation (not a reference function: the reference has no DOG encoder)"""
+    n, P = state.n, state.cfg.num_players
+    own = state.hands[np.arange(n), state.current_player.astype(np.int64) % P]
+    misc = np.stack([state.phase, state.hand_size, state.current_player, state.round_starter], 1)
+    return np.concatenate([state.board, own, misc], 1).astype(np.int8)
+
+
+def play_batch_of_games_dog(state, max_steps, rng_key, search_fn, teams):
+    """do_active_step of MuZero_det_MADN/game_agent.py:64-148 applied to the DOG env oracle (BASELINE config 5; the reference
+    has no DOG self-play loop, MuZero_DOG/muzero_dog.py:85-99).  state: O.DogState."""
+    n = state.n
+    A = state.cfg.num_actions
+    buf = dict(obs=np.zeros((n, max_steps, 74), np.float32), act=np.zeros((n, max_steps), np.int32),
+               rew=np.zeros((n, max_steps), np.int32), val=np.zeros((n, max_steps), np.float32), pol=np.zeros((n, max_steps, A), np.float32),
+               mask=np.zeros((n, max_steps), np.float32), player=np.zeros((n, max_steps), np.int32),
+               team=np.full((n, max_steps), -1, np.int32), discount=np.zeros((n, max_steps), np.int32), idx=np.zeros(n, np.int32))
+    key = np.asarray(rng_key, np.uint32)
+    step = 0
+    while step < max_steps and not state.done.all():
+        keys = O.split(key, n + 1)
+        key, step_keys = keys[0], keys[1:]
+        live = state.done == 0
+        obs = dog_raw_observation(state)
+        valid = O.dog_valid_actions(state)
+        action, weights, value = search_fn(step_keys, obs, ~valid)
+        stepped, skipped = state.copy(), state.copy()
+        r, d = O.dog_step(stepped, np.where(valid.any(1), action, 0))
+        O.dog_no_step(skipped)
+        for g in range(n):
+            if not live[g]:
+                continue
+            i = buf["idx"][g]
+            has_valid = valid[g].any()
+            pid = int(state.current_player[g])
+            team = pid % 2 if teams else -1
+            src = stepped if has_valid else skipped
+            if i < max_steps:
+                buf["player"][g, i], buf["team"][g, i] = pid, team
+                if has_valid:
+                    nxt, nd, rw = int(stepped.current_player[g]), bool(d[g]), int(r[g])
+                    same = (team == nxt % 2) if teams else (pid == nxt)
+                    buf["obs"][g, i], buf["act"][g, i], buf["val"][g, i], buf["pol"][g, i] = obs[g], int(action[g]), value[g], weights[g]
+                    buf["rew"][g, i] = 2 if (nd and rw > 0) else (0 if (nd and rw < 0) else 1)
+                    buf["mask"][g, i], buf["discount"][g, i] = 1.0, (1 if nd else (2 if same else 0))
+                else:
+                    buf["act"][g, i], buf["rew"][g, i], buf["discount"][g, i] = -1, 1, 1
+            buf["idx"][g] = i + 1
+            for f, v in src.fields().items():
+                getattr(state, f)[g] = v[g]
+        step += 1
+    return buf

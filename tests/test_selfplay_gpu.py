@@ -102,3 +102,71 @@ def test_full_selfplay_with_tree_search_is_replay_consistent():
             cur = getattr(s, f)
             cur[live & has] = getattr(stepped, f)[live & has]
             cur[live & ~has] = getattr(skipped, f)[live & ~has]
+
+
+def test_dog_loop_bookkeeping_matches_oracle():
+    """config 5's loop on the DOG env (806 actions, swap phase, re-deals, no_step discards) with a supplied search"""
+    from helpers import DOG_RULES
+    from exploring_muzero_on_dog_b200 import game_agent, jaxrand
+    from exploring_muzero_on_dog_b200.DOG import dog as dg
+    n, max_steps = 64, 1300
+    key = jaxrand.split_host(jaxrand.PRNGKey(5))[1]
+    seeds = O.randint(key, n, 0, 1_000_000)
+    cfg = O.DogCfg(4, 0xF, 10, mask_of(DOG_RULES))
+    host_fn, dev_fn = _fake_search(cfg.num_actions)
+    s = O.dog_reset(cfg, seeds, 0)
+    exp = selfplay_oracle.play_batch_of_games_dog(s, max_steps, key, host_fn, teams=True)
+    envs = dg.env_reset(0, seed=seeds, **DOG_RULES)
+    got = game_agent.play_batch_of_games(envs, n, (dg.RAW_OBS_SIZE,), None, key, 0, 0, max_steps, 1.0, search_fn=dev_fn)
+    assert_state_equal(s, envs.numpy())
+    assert (exp["mask"] == 0).any() and (exp["rew"] != 1).any() and s.done.any()   # no_step and game ends are exercised
+    for k, v in exp.items():
+        assert np.array_equal(got[k].cpu().numpy(), v), k
+
+
+def test_dog_selfplay_with_gumbel_search_plays_legal_moves():
+    """config-5-shaped slice: Gumbel search over DOG's 806 actions with a torch stand-in network; the recorded actions replayed
+    through the CPU oracle must be legal and reproduce players / masks / reward classes and the final state"""
+    from helpers import DOG_RULES
+    from exploring_muzero_on_dog_b200 import game_agent, jaxrand, mcts
+    n, max_steps, E, A = 64, 40, 32, 806
+    g = torch.Generator(device="cuda").manual_seed(2)
+    Wr = torch.randn(74, E, device="cuda", generator=g) * 0.2
+    Wp, Wv = torch.randn(E, A, device="cuda", generator=g), torch.randn(E, device="cuda", generator=g)
+    Wa, Wd = torch.randn(A, E, device="cuda", generator=g), torch.randn(E, E, device="cuda", generator=g) * 0.4
+
+    def root_fn(params, obs):
+        e = torch.tanh(obs.reshape(obs.shape[0], -1) @ Wr)
+        return mcts.RootFnOutput(e @ Wp, torch.tanh(e @ Wv), e)
+
+    def recurrent_fn(params, rng, action, emb):
+        e = torch.tanh(emb @ Wd + Wa[action])
+        return mcts.RecurrentFnOutput(0.1 * e[:, 0], torch.where(e[:, 1] > 0, 1.0, -1.0), e @ Wp, torch.tanh(e @ Wv)), e
+
+    key = jaxrand.PRNGKey(13)
+    envs, buf = game_agent.play_n_dog_games(None, key, n, 12, 6, max_steps, 1.0, root_fn=root_fn, recurrent_fn=recurrent_fn)
+    b = {k: v.cpu().numpy() for k, v in buf.items()}
+    sub = jaxrand.split_host(key)[1]
+    seeds = O.randint(sub, n, 0, 1_000_000)
+    s = O.dog_reset(O.DogCfg(4, 0xF, 10, mask_of(DOG_RULES)), seeds, 0)
+    for t in range(int(b["idx"].max())):
+        live = (s.done == 0) & (t < b["idx"])
+        valid = O.dog_valid_actions(s)
+        has = valid.any(1)
+        act = b["act"][:, t]
+        assert (b["mask"][live, t] == has[live]).all() and (act[live & ~has] == -1).all()
+        assert valid[live & has, act[live & has]].all()
+        assert (b["player"][live, t] == s.current_player[live]).all()
+        assert np.array_equal(b["obs"][live & has, t], selfplay_oracle.dog_raw_observation(s)[live & has])
+        assert np.allclose(b["pol"][live & has, t].sum(1), 1.0, atol=1e-4) and (b["pol"][live & has, t][~valid[live & has]] < 1e-30).all()
+        stepped, skipped = s.copy(), s.copy()
+        r, d = O.dog_step(stepped, np.where(has, act, 0))
+        O.dog_no_step(skipped)
+        rew_t = np.where(d & (r > 0), 2, np.where(d & (r < 0), 0, 1))
+        sel = live & has
+        assert (b["rew"][sel, t] == rew_t[sel]).all()
+        for f in s.fields():
+            cur = getattr(s, f)
+            cur[live & has] = getattr(stepped, f)[live & has]
+            cur[live & ~has] = getattr(skipped, f)[live & ~has]
+    assert_state_equal(s, envs.numpy())
