@@ -89,7 +89,7 @@ class MctsCfg(C.Structure):
 
 MCTS_TREE_FIELDS = ("node_visits", "raw_values", "node_values", "parents", "action_from_parent", "children_index",
                     "children_prior_logits", "children_visits", "children_rewards", "children_discounts", "children_values",
-                    "embeddings", "is_decision", "root_invalid_actions", "root_gumbel", "search_key", "policy_key", "path")
+                    "embeddings", "is_decision", "root_invalid_actions", "root_gumbel", "search_key", "policy_key", "path", "select_aux")
 
 
 class MctsTree(C.Structure):

@@ -68,6 +68,9 @@ class Tree:
         self.root_gumbel = e((n, A), dtype=f32) if policy == GUMBEL else None
         self.search_key, self.policy_key = e((n, 2), dtype=torch.uint32), e((n, 2), dtype=torch.uint32)
         self.path = torch.zeros((n, 65), dtype=i32, device=device)  # descent scratch for the parallel backup
+        # per-node select cache of the wide Gumbel path (DOG's 806 actions): 144 B per node
+        self.select_aux = (torch.zeros((n, N + 1, 36), dtype=torch.uint32, device=device)
+                           if policy == GUMBEL and num_chance == 0 and 32 < A <= 832 else None)
         self.num_actions, self.num_chance, self.n = num_actions, num_chance, n
 
     def cstruct(self):
