@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdogstep.so")
+LIB_PATH = os.environ.get("DOGSTEP_LIB") or os.path.join(_HERE, "libdogstep.so")  # DOGSTEP_LIB: an alternative build (profiling)
 _lib = None
 
 ERRORS = {-1: "invalid argument", -2: "unsupported configuration", -3: "CUDA failure"}

@@ -273,6 +273,11 @@ int dogstep_mcts_expand_select(const dogstep_mcts_tree* t, int64_t n, const dogs
                                const float* discount, const float* embedding, const float* chance_logits,
                                const float* afterstate_value, const float* afterstate_embedding, float* embedding_out,
                                uint8_t* is_decision_out, uint32_t* expand_key_out, void* stream);
+/* The exp of the float contract above, out[i] = (float)exp((double)x[i]), as the tree kernels evaluate it.  Exposed so
+ * that the parity tests can check the device function itself against the oracle's libm expression (the two double
+ * libraries may differ in the last bit; the float results differ only when that straddles a float rounding boundary,
+ * about one argument in 2^29). */
+int dogstep_exp_f32(const float* x, int64_t n, float* out, void* stream);
 /* policy epilogue: action i32 [n], action_weights f32 [n,A], root_value f32 [n] (= search_tree.summary().value) */
 int dogstep_mcts_policy_output(const dogstep_mcts_tree* t, int64_t n, const dogstep_mcts_cfg* cfg, int32_t* action,
                                float* action_weights, float* root_value, void* stream);

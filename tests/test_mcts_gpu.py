@@ -207,3 +207,20 @@ def test_cuda_graph_replay_equals_eager_search():
             assert torch.equal(eager.search_tree.children_visits, graphed.search_tree.children_visits)
             assert torch.equal(eager.search_tree.node_values, graphed.search_tree.node_values)
     assert len(cache.entries) == 3
+
+
+def test_device_exp_matches_libm():
+    """the exp of the float contract, (float)exp((double)x), evaluated on the device against libm (math.exp) on softmax-like,
+    uniform and boundary arguments"""
+    import ctypes as C
+    import math
+    from exploring_muzero_on_dog_b200 import _lib
+    rng = np.random.default_rng(0)
+    x = np.concatenate([-np.abs(rng.standard_normal(1 << 19)).astype(np.float32) * 8, rng.uniform(-150, 5, 1 << 18).astype(np.float32),
+                        np.array([0.0, -0.0, -np.inf, -87.4, -100.0, -103.9, -104.0, -150.0, -3.4028235e38, 80.0, 88.7], np.float32)])
+    want = np.array([math.exp(float(v)) for v in x], np.float64).astype(np.float32)
+    xd = torch.from_numpy(x).cuda()
+    out = torch.empty_like(xd)
+    _lib.check(_lib.lib().dogstep_exp_f32(_lib.ptr(xd), C.c_int64(x.size), _lib.ptr(out), _lib.stream()), "exp_f32")
+    got = out.cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
