@@ -180,6 +180,89 @@ def measure_extras(dev, key):
                                   "roofline": {"bound": "hbm", "kernel": "k_mcts_expand_select",
                                                "algorithmic_bytes_per_sim": bytes_per_sim, "achieved": n * S * bytes_per_sim / (ms / 1e3) / 1e9,
                                                "peak": peak, "unit": "GB/s", "frac": n * S * bytes_per_sim / (ms / 1e3) / 1e9 / peak}}
+    out.update(measure_cfg5(dev, key, peak))
+    return out
+
+
+def measure_cfg5(dev, key, peak):
+    """BASELINE config 5 (8,192 DOG games per GPU x 100 Gumbel simulations over 806 actions, latent 256): the tree kernels alone
+    with precomputed network outputs, and a short slice of the whole self-play loop (DOG env + search with a random-init
+    stand-in network + trajectory rows + replay save / sample) — the reference has no DOG networks (muzero_dog.py:85-99)."""
+    import torch
+    from exploring_muzero_on_dog_b200 import game_agent, jaxrand, mcts, vec_replay_buffer
+    out = {}
+    n, S, A, E, R = 8192, 100, 806, 256, 4
+    g = torch.Generator(device=dev).manual_seed(0)
+    rnd = lambda *shape: torch.randn(*shape, device=dev, generator=g)
+    cfg = mcts._cfg(mcts.GUMBEL, mcts.qtransform_completed_by_mix_value(value_scale=0.5), S, 50, A, 0, E)
+    srch = mcts.Search(cfg, n, dev)
+    keys = jaxrand.split(key, n, device=dev)
+    root = mcts.RootFnOutput(rnd(n, A), torch.zeros(n, device=dev), rnd(n, E))
+    pl, emb = [rnd(n, A) for _ in range(R)], [rnd(n, E) for _ in range(R)]
+    val, rew = [torch.tanh(rnd(n)) for _ in range(R)], [0.1 * rnd(n) for _ in range(R)]
+    disc = [torch.where(rnd(n) > 0, 1.0, -1.0) for _ in range(R)]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    for rep in range(2):
+        ev[0].record()
+        srch.init(keys, root, None, None)
+        ev[1].record()
+        srch.select(0)
+        for sim in range(S):
+            k = sim % R
+            (srch.expand_select if sim + 1 < S else srch.expand)(sim, pl[k], val[k], rew[k], disc[k], emb[k])
+        ev[2].record()
+        torch.cuda.synchronize()
+    ms_init, ms = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
+    t = srch.tree
+    depth = torch.zeros_like(t.parents)
+    for node in range(1, S + 1):
+        par = t.parents[:, node].long().clamp(min=0)
+        depth[:, node] = torch.where(t.parents[:, node] >= 0, depth.gather(1, par[:, None])[:, 0] + 1, 0)
+    dbar = float(depth[:, 1:].float().mean().item())
+    bps = 5300 + 16200 * dbar  # SURVEY.md 8(d) cfg 5: five dense 806-wide child rows per visited level
+    out["mcts_cfg5_tree_only"] = {
+        "workload": "cfg5 tree kernels alone: Gumbel MuZero, 8,192 games x 100 sims, A=806, E=256, precomputed network outputs",
+        "sims": n * S, "ms": ms, "init_ms": ms_init, "sims_per_s": n * S / (ms / 1e3), "mean_expansion_depth": dbar, "gpu_launches": S + 1,
+        "tree_bytes": int(sum(getattr(t, k).numel() * getattr(t, k).element_size() for k in
+                              ("children_index", "children_prior_logits", "children_visits", "children_rewards", "children_discounts",
+                               "children_values", "embeddings"))),
+        "roofline": {"bound": "hbm", "kernel": "k_mcts_expand_select<8,2>", "algorithmic_bytes_per_sim": bps,
+                     "achieved": n * S * bps / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s", "frac": n * S * bps / (ms / 1e3) / 1e9 / peak,
+                     "note": "algorithmic bytes of the reference dataflow (5 dense child rows per level); the kernel reads one dense "
+                             "row per level plus the visited children (select cache), so its DRAM traffic is about a third of that"}}
+    del srch, t, depth, pl, emb
+    torch.cuda.empty_cache()
+    # a slice of the whole loop
+    plies = 4
+    Wr, Wp, Wv = rnd(74, E) * 0.2, rnd(E, A), rnd(E)
+    Wa, Wd = rnd(A, E), rnd(E, E) * 0.06
+
+    def root_fn(params, obs):
+        e = torch.tanh(obs.reshape(obs.shape[0], -1) @ Wr)
+        return mcts.RootFnOutput(e @ Wp, torch.tanh(e @ Wv), e)
+
+    def recurrent_fn(params, rng, action, e0):
+        e = torch.tanh(e0 @ Wd + Wa[action])
+        return mcts.RecurrentFnOutput(0.1 * e[:, 0], torch.where(e[:, 1] > 0, 1.0, -1.0), e @ Wp, torch.tanh(e @ Wv)), e
+
+    buf = vec_replay_buffer.VectorizedReplayBuffer(n, 128, 10, 50, obs_shape=(74,), action_dim=A, max_episode_length=64, device=dev,
+                                                   obs_dtype=torch.int8)
+    for rep in range(2):
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        envs, traj = game_agent.play_n_dog_games(None, jaxrand.PRNGKey(rep), n, S, 50, plies, 1.0, root_fn=root_fn, recurrent_fn=recurrent_fn,
+                                                 device=dev)
+        e1.record()
+        buf.save_games_from_buffers(traj)
+        batch = buf.sample_batch()
+        e2.record()
+        torch.cuda.synchronize()
+    ms_play, ms_rep = e0.elapsed_time(e1), e1.elapsed_time(e2)
+    out["selfplay_cfg5_slice"] = {
+        "workload": f"cfg5 loop slice: 8,192 DOG games x {plies} plies x 100 sims (env + Gumbel search + stand-in latent-256 network + "
+                    "trajectory rows), then replay save + sample(batch 128, unroll 10, td 50)",
+        "plies": plies, "play_ms": ms_play, "replay_ms": ms_rep, "sims_per_s": n * plies * S / (ms_play / 1e3),
+        "env_steps_per_s": n * plies / (ms_play / 1e3), "batch_keys": sorted(batch.keys())}
     return out
 
 
