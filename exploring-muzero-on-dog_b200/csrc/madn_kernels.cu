@@ -428,33 +428,40 @@ __global__ void __launch_bounds__(kThreads) k_madn_det_play_random(const __grid_
 //   4. each lane applies its game's move (incremental bitboard update); a finished game is written back at once.
 // Games end at different plies (mean 403, max ~850 in config 2), so a warp that kept its 32 games to the end would idle
 // 30 % of its lane-iterations: every kPlayRound iterations the live games of the CTA are packed into the lowest warps
-// through shared memory (23 words per game) and the emptied warps only wait at the barriers.  The key chain value
-// travels through shared memory too, because a warp that ran empty and is refilled has not advanced it.
+// through shared memory (23 words per game) and the emptied warps only wait at the barriers.  The loop key chain
+// (rng <- split(rng, N + 1)[0], the same for every game) is produced a round ahead by one extra warp per CTA into a
+// double-buffered shared ring, so a warp that ran empty and is refilled finds the current value there.
 // A CTA that loaded a non-canonical game (see madn_fast.cuh) runs the generic rules of madn_core.cuh instead.
 #ifdef DOGSTEP_TRACE
 __device__ unsigned long long g_play_trace[128];
 #endif
 constexpr int kPlayRound = 32;
-constexpr int kPlayMaxThreads = 512;
+constexpr int kPlayMaxThreads = 512;  // game threads per CTA (+ 32: the producer warp)
 constexpr int kXWords = 23;  // occ 8, pins 4, action set 8, cur|reward, len, game index
 
+constexpr int kRingMax = 64;  // longest round the key ring holds
+// `threads` = game threads (the CTA has one more warp, the key-chain producer)
 static size_t play_smem_bytes(int threads) {
-  return (size_t)(threads / 32) * (24 * 32 * 2 + 32 * 4 + 32 * 8) + (size_t)kXWords * threads * 4 + 2 * 34 * 4;
+  return (size_t)(threads / 32) * (24 * 32 * 2 + 32 * 4 + 32 * 8) + (size_t)kXWords * threads * 4 + 2 * 34 * 4 +
+         2 * (kRingMax + 1) * 8;
 }
 
 template <uint32_t CT>
-__global__ void __launch_bounds__(kPlayMaxThreads) k_madn_det_play_cta(const __grid_constant__ MadnGeom g, MadnPtrs p, int64_t n,
+__global__ void __launch_bounds__(kPlayMaxThreads + 32) k_madn_det_play_cta(const __grid_constant__ MadnGeom g, MadnPtrs p, int64_t n,
                                                                       Key2 rng0, int64_t game_offset, int max_steps,
                                                                       int32_t* __restrict__ game_len,
                                                                       unsigned long long* __restrict__ total_steps, int round_len) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int T = blockDim.x, W = T >> 5;
+  const int T = blockDim.x - 32, W = T >> 5;  // game threads / warps; the CTA's last warp produces the key chain
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint2* s_key = reinterpret_cast<uint2*>(smem_raw) + warp * 32;                                  // [W][32]
-  uint32_t* s_best = reinterpret_cast<uint32_t*>(smem_raw + (size_t)W * 256) + warp * 32;         // [W][32]
-  uint16_t* s_items = reinterpret_cast<uint16_t*>(smem_raw + (size_t)W * 384) + warp * (24 * 32);  // [W][768]
-  uint32_t* s_x = reinterpret_cast<uint32_t*>(smem_raw + (size_t)W * 1920);                       // [kXWords][T]
-  uint32_t* s_cnt = s_x + (size_t)kXWords * T;                                                    // 2 x ([32] counts, key[2])
+  const bool producer = warp == W;
+  const int pw = producer ? 0 : warp;  // the producer never touches the per-warp arrays
+  uint2* s_key = reinterpret_cast<uint2*>(smem_raw) + pw * 32;                                  // [W][32]
+  uint32_t* s_best = reinterpret_cast<uint32_t*>(smem_raw + (size_t)W * 256) + pw * 32;         // [W][32]
+  uint16_t* s_items = reinterpret_cast<uint16_t*>(smem_raw + (size_t)W * 384) + pw * (24 * 32);  // [W][768]
+  uint32_t* s_x = reinterpret_cast<uint32_t*>(smem_raw + (size_t)W * 1920);                     // [kXWords][T]
+  uint32_t* s_cnt = s_x + (size_t)kXWords * T;                                                  // 2 x [34] counts
+  uint2* s_ring = reinterpret_cast<uint2*>(s_cnt + 2 * 34);                                     // 2 x [kRingMax + 1] keys
   const uint32_t FULL = 0xFFFFFFFFu;
   const int64_t cta_base = (int64_t)blockIdx.x * T;
   int gi = threadIdx.x;  // game held by this lane, relative to cta_base
@@ -463,27 +470,34 @@ __global__ void __launch_bounds__(kPlayMaxThreads) k_madn_det_play_cta(const __g
   unsigned steps_done = 0;
   MadnRegs s;
   bool alive = false, canon = true;
-  if (cta_base + gi < n) {
+  if (producer) {
+    // The loop key chain rng_{t+1} = split(rng_t, N + 1)[0] (game_agent.py:60) is the same for every game: one warp per CTA
+    // computes it, a round ahead, into a double-buffered ring (ring[i] = rng_{t0 + i}, i = 0..round_len) instead of
+    // every lane of every warp repeating it each iteration (it was one Threefry in seven, and sat on the critical path
+    // of the next step key).
+    Key2 r = rng0;
+    if (lane == 0) s_ring[0] = make_uint2(r.a, r.b);
+    for (int i = 1; i <= round_len; ++i) {
+      r = split_i(r, 0u);
+      if (lane == 0) s_ring[i] = make_uint2(r.a, r.b);
+    }
+  } else if (cta_base + gi < n) {
     load_state<true>(g, p, cta_base + gi, s);
     canon = is_canonical4(s, s.occ);
     alive = !s.done;
     if (!alive && game_len) game_len[cta_base + gi] = 0;
   }
   const bool fast = !__syncthreads_or(!canon);
-  Key2 rng = rng0;
   const uint32_t lane_hi = (uint32_t)lane << 8;
-  s_best[lane] = 0u;
-  bool rng_current = true;  // this warp's copy of the key chain is the one for iteration t
+  if (!producer) s_best[lane] = 0u;
   int t = 0, round = 0;
   while (true) {
     // ---- compaction point
-    // (counts and key are double-buffered by round parity: an empty warp can reach the next point while others still read)
+    // (counts and ring are double-buffered by round parity: an empty warp can reach the next point while others still read)
     const uint32_t ab = __ballot_sync(FULL, alive);
-    uint32_t* cnt = s_cnt + (round & 1) * 34;
-    if (lane == 0) {
-      cnt[warp] = (uint32_t)__popc(ab);
-      if (rng_current) { cnt[32] = rng.a; cnt[33] = rng.b; }
-    }
+    const int par = round & 1;
+    uint32_t* cnt = s_cnt + par * 34;
+    if (lane == 0 && !producer) cnt[warp] = (uint32_t)__popc(ab);
     ++round;
     __syncthreads();
     int before = 0, live = 0, nonempty = 0;
@@ -502,8 +516,6 @@ __global__ void __launch_bounds__(kPlayMaxThreads) k_madn_det_play_cta(const __g
     }
 #endif
     if (live == 0 || t >= max_steps) break;
-    rng = Key2{cnt[32], cnt[33]};
-    rng_current = true;
     if (((live + 31) >> 5) < nonempty) {  // CTA-uniform: packing frees at least one warp
       if (alive) {
         const int slot = before + __popc(ab & ((1u << lane) - 1u));
@@ -542,12 +554,27 @@ __global__ void __launch_bounds__(kPlayMaxThreads) k_madn_det_play_cta(const __g
     }
     // ---- kPlayRound lockstep iterations
     const int tend = min(t + round_len, max_steps);
+    const uint2* rk = s_ring + par * (kRingMax + 1);  // rk[i] = the loop key of iteration t + i
+    if (producer) {  // next round's keys
+      uint2* nk = s_ring + (par ^ 1) * (kRingMax + 1);
+      const uint2 r0 = rk[round_len];
+      Key2 r{r0.x, r0.y};
+      if (lane == 0) nk[0] = r0;
+      for (int i = 1; i <= round_len; ++i) {
+        r = split_i(r, 0u);
+        if (lane == 0) nk[i] = make_uint2(r.a, r.b);
+      }
+      t = tend;
+      continue;
+    }
     const uint32_t my = (uint32_t)(game_offset + cta_base + gi + 1);
-    Key2 key = split_i(rng, my);  // split(rng, N+1)[j+1]   (game_agent.py:60 / evaluate_agent.py:336)
+    Key2 key = split_i(Key2{rk[0].x, rk[0].y}, my);  // split(rng, N+1)[j+1]   (game_agent.py:60 / evaluate_agent.py:336)
+    int ri = 0;
 #pragma unroll 1
     for (; t < tend; ++t) {
-      if (!__any_sync(FULL, alive)) { rng_current = false; break; }
-      const Key2 rng_next = split_i(rng, 0u);  // split(rng, N+1)[0]
+      if (!__any_sync(FULL, alive)) break;
+      ++ri;
+      const uint2 rn = rk[ri];  // split(rng, N+1)[0] of this iteration = the loop key of the next
       int cp = 0;
       uint32_t m = 0u;
       if (alive) m = fast ? det_valid_mask4(R, g, s, cp) : madn_det_valid_mask(g, s);
@@ -576,7 +603,7 @@ __global__ void __launch_bounds__(kPlayMaxThreads) k_madn_det_play_cta(const __g
         const uint32_t o0 = it0 >> 8, a0 = it0 & 0xFFu, o1 = it1 >> 8, a1 = it1 & 0xFFu;
         const uint2 k0 = s_key[o0], k1 = s_key[o1];
         const uint32_t v0 = bits_i(Key2{k0.x, k0.y}, a0) >> 9, v1 = bits_i(Key2{k1.x, k1.y}, a1) >> 9;
-        key_next = split_i(rng_next, my);
+        key_next = split_i(Key2{rn.x, rn.y}, my);
         if (h0) atomicMax(&s_best[o0], (v0 << 5) | (23u - a0));
         if (h1) atomicMax(&s_best[o1], (v1 << 5) | (23u - a1));
       }
@@ -617,7 +644,6 @@ __global__ void __launch_bounds__(kPlayMaxThreads) k_madn_det_play_cta(const __g
       }
       s_best[lane] = 0u;
       key = key_next;
-      rng = rng_next;
       __syncwarp();
     }
     t = tend;
@@ -929,13 +955,13 @@ int dogstep_madn_det_play_random(const dogstep_madn_det_state* s, int64_t n, con
     if (threads > kPlayMaxThreads) threads = kPlayMaxThreads;
     const size_t smem = play_smem_bytes(threads);
     const unsigned blocks = blocks_for(n, threads);
-    const int round_len = kPlayRound;
+    const int round_len = kPlayRound;  // <= kRingMax
     if (g.rules == kTrainRules) {
       cudaFuncSetAttribute(k_madn_det_play_cta<kTrainRules>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      k_madn_det_play_cta<kTrainRules><<<blocks, threads, smem, st>>>(g, p, n, rng, game_offset, max_steps, game_len, total_steps, round_len);
+      k_madn_det_play_cta<kTrainRules><<<blocks, threads + 32, smem, st>>>(g, p, n, rng, game_offset, max_steps, game_len, total_steps, round_len);
     } else {
       cudaFuncSetAttribute(k_madn_det_play_cta<kRulesRuntime>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      k_madn_det_play_cta<kRulesRuntime><<<blocks, threads, smem, st>>>(g, p, n, rng, game_offset, max_steps, game_len, total_steps, round_len);
+      k_madn_det_play_cta<kRulesRuntime><<<blocks, threads + 32, smem, st>>>(g, p, n, rng, game_offset, max_steps, game_len, total_steps, round_len);
     }
   } else {
     k_madn_det_play_random<<<blocks_for(n, kThreads), kThreads, 0, st>>>(g, p, n, rng, game_offset, max_steps, game_len,
