@@ -491,13 +491,14 @@ __global__ void __launch_bounds__(kPlayMaxThreads + 32) k_madn_det_play_cta(cons
   const uint32_t lane_hi = (uint32_t)lane << 8;
   if (!producer) s_best[lane] = 0u;
   int t = 0, round = 0;
+  bool tail = false;  // CTA-uniform: one game per WARP from here on (see below)
   while (true) {
     // ---- compaction point
     // (counts and ring are double-buffered by round parity: an empty warp can reach the next point while others still read)
     const uint32_t ab = __ballot_sync(FULL, alive);
     const int par = round & 1;
     uint32_t* cnt = s_cnt + par * 34;
-    if (lane == 0 && !producer) cnt[warp] = (uint32_t)__popc(ab);
+    if (lane == 0 && !producer) cnt[warp] = tail ? (ab != 0u) : (uint32_t)__popc(ab);
     ++round;
     __syncthreads();
     int before = 0, live = 0, nonempty = 0;
@@ -516,7 +517,12 @@ __global__ void __launch_bounds__(kPlayMaxThreads + 32) k_madn_det_play_cta(cons
     }
 #endif
     if (live == 0 || t >= max_steps) break;
-    if (((live + 31) >> 5) < nonempty) {  // CTA-uniform: packing frees at least one warp
+    // Tail: once the CTA is down to one game per warp or fewer, the lockstep iteration is bound by the latency of ONE warp's
+    // instruction stream (~1.2 us), not by issue slots.  From then on every warp holds ONE game, replicated in all lanes:
+    // lane a draws action a's Threefry bits one iteration ahead (they do not depend on the state), the legal mask and
+    // the move are computed redundantly by all lanes, and the argmax is one redux — no scan, no item list, no atomics.
+    const bool enter_tail = fast && !tail && live <= W;
+    if (enter_tail || (!tail && ((live + 31) >> 5) < nonempty)) {  // CTA-uniform: packing frees at least one warp
       if (alive) {
         const int slot = before + __popc(ab & ((1u << lane) - 1u));
         uint32_t* x = s_x + slot;
@@ -533,9 +539,10 @@ __global__ void __launch_bounds__(kPlayMaxThreads + 32) k_madn_det_play_cta(cons
         x[22 * T] = (uint32_t)gi;
       }
       __syncthreads();
-      alive = (int)threadIdx.x < live;
+      tail = tail || enter_tail;
+      alive = (tail ? warp : (int)threadIdx.x) < live && !producer;
       if (alive) {
-        const uint32_t* x = s_x + threadIdx.x;
+        const uint32_t* x = s_x + (tail ? warp : (int)threadIdx.x);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           s.occ[q] = (uint64_t)x[(2 * q) * T] | ((uint64_t)x[(2 * q + 1) * T] << 32);
@@ -570,6 +577,38 @@ __global__ void __launch_bounds__(kPlayMaxThreads + 32) k_madn_det_play_cta(cons
     const uint32_t my = (uint32_t)(game_offset + cta_base + gi + 1);
     Key2 key = split_i(Key2{rk[0].x, rk[0].y}, my);  // split(rng, N+1)[j+1]   (game_agent.py:60 / evaluate_agent.py:336)
     int ri = 0;
+    if (tail) {
+      uint32_t mant = bits_i(key, (uint32_t)lane) >> 9;  // lane a: the draw of action a (lanes >= 24 unused)
+      const uint32_t tag = lane < 24 ? 23u - (uint32_t)lane : 0u;
+#pragma unroll 1
+      for (; t < tend && alive; ++t) {
+        ++ri;
+        const uint2 rn = rk[ri];
+        const Key2 key_next = split_i(Key2{rn.x, rn.y}, my);           // next iteration's draws: independent of the state,
+        const uint32_t mant_next = bits_i(key_next, (uint32_t)lane) >> 9;  // they overlap the dependent chain below
+        int cp = 0;
+        const uint32_t m = det_valid_mask4(R, g, s, cp);
+        if (m) {
+          const uint32_t v = ((m >> lane) & 1u) ? ((mant << 5) | tag) : 0u;  // m has 24 bits: lanes >= 24 contribute 0
+          const int a = 23 - (int)(__reduce_max_sync(FULL, v) & 31u);
+          det_step4(R, s, cp, a);
+        } else {
+          det_no_step4(s);
+        }
+        ++len;
+        steps_done += (lane == 0);
+        if (s.done) {
+          alive = false;
+          if (lane == 0) {
+            store_det_all(g, p, cta_base + gi, s);
+            if (game_len) game_len[cta_base + gi] = len;
+          }
+        }
+        mant = mant_next;
+      }
+      t = tend;
+      continue;
+    }
 #pragma unroll 1
     for (; t < tend; ++t) {
       if (!__any_sync(FULL, alive)) break;
@@ -648,7 +687,7 @@ __global__ void __launch_bounds__(kPlayMaxThreads + 32) k_madn_det_play_cta(cons
     }
     t = tend;
   }
-  if (alive) {  // max_steps reached with the game still running
+  if (alive && (!tail || lane == 0)) {  // max_steps reached with the game still running
     store_det_all(g, p, cta_base + gi, s);
     if (game_len) game_len[cta_base + gi] = len;
   }
