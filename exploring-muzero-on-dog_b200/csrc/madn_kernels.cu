@@ -334,6 +334,112 @@ __global__ void __launch_bounds__(kThreads) k_madn_det_random_step(const __grid_
   }
 }
 
+// ---- evaluation loop: one lockstep iteration of play_eval_loop_jitted (MuZero_det_MADN/evaluate_agent.py:733-930) -------
+// Every seat is played by an agent type (params['type']): 3 = random legal policy, 2 = the rule-based scorer, anything
+// else = tree search (the caller's search supplies the action).  Thread per game.
+__device__ __forceinline__ float eval_log_f(float x) { return (float)log((double)x); }
+
+// do_rule_based (:780-878), literally — including that it scores env.pins[env.current_player] (NOT the team proxy the
+// legal mask was computed for), that the candidate distances are arange(6) = 0..5 (one less than the move an action
+// plays), and that base_score = repeat(action_abundance, 4) indexes the six abundances by a // 4.
+__device__ int madn_rule_based_action(const MadnGeom& g, const MadnRegs& s, uint32_t m, Key2 key) {
+  const int cur = s.cur;
+  const uint32_t pw = pick4(s.pins, cur);
+  const int start = g.start[cur], target = g.target[cur], goal0 = g.goal0[cur];
+  const int mts = DS_RULE(g, DOGSTEP_RULE_MUST_TRAVERSE_START) ? 1 : 0;
+  const int mate = DS_RULE(g, DOGSTEP_RULE_TEAMS) ? ((cur + 2) & 3) : -1;
+  int pins_in_home = 0;
+#pragma unroll
+  for (int p = 0; p < 4; ++p) pins_in_home += byte_s(pw, p) < 0;
+  const float out_w = pins_in_home >= 2 ? 3.0f : 2.0f;
+  const float denom = fmaxf((float)__popc(m), 1.0f);
+  float abundance[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    int c = 0;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) c += (m >> (6 * p + k)) & 1u;
+    abundance[k] = __fdiv_rn((float)c, denom);
+  }
+  float best = 0.0f;
+  int best_a = -1;
+#pragma unroll 1
+  for (int a = 0; a < 24; ++a) {
+    const int p = a / 6, k = a - 6 * p;
+    const int cur_pos = byte_s(pw, p);
+    const int moved = cur_pos + k, fitted = floormod(moved, g.bs);
+    const int x = moved - target - mts;
+    int new_pos = fitted;
+    if (x <= 4 && x > 0 && cur_pos <= target) new_pos = goal0 + x - 1;
+    if (cur_pos >= g.bs) new_pos = moved;
+    if (cur_pos < 0) new_pos = start;
+    const bool into_goal = (unsigned)(new_pos - goal0) <= 3u && cur_pos < g.bs;
+    const bool leaves_home = cur_pos < 0 && new_pos == start;
+    bool hits = false;
+    for (int q = 0; q < g.n; ++q) {
+      if (q == cur || q == mate) continue;
+      const uint32_t ow = pick4(s.pins, q);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) hits = hits || byte_s(ow, j) == new_pos;
+    }
+    hits = hits && new_pos != cur_pos;
+    float score = abundance[a >> 2];
+    score = __fadd_rn(score, into_goal ? 5.0f : 0.0f);
+    score = __fadd_rn(score, leaves_home ? out_w : 0.0f);
+    score = __fadd_rn(score, hits ? 2.0f : 0.0f);
+    const float logit = ((m >> a) & 1u) ? __fdiv_rn(score, 0.25f) : __int_as_float(0xFF800000);
+    const float u = uniform_i(key, (uint32_t)a, 1.17549435e-38f, 1.0f);
+    const float v = __fadd_rn(-eval_log_f(-eval_log_f(u)), logit);  // jax.random.categorical: argmax(gumbel + logits)
+    if (best_a < 0 || v > best) { best = v; best_a = a; }
+  }
+  return best_a;
+}
+
+__global__ void __launch_bounds__(kThreads) k_madn_det_eval_step(const __grid_constant__ MadnGeom g, MadnPtrs p, int64_t n,
+                                                                 int4 agent_type, const int32_t* __restrict__ search_action,
+                                                                 Key2 rng, int64_t game_offset, int32_t* __restrict__ winners,
+                                                                 unsigned long long* __restrict__ active_count) {
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  int active = 0;
+  if (i < n && p.done[i] == 0) {
+    MadnRegs s;
+    load_state<true>(g, p, i, s);
+    const Key2 key = split_i(rng, (uint32_t)(game_offset + i + 1));  // rng_key, *step_keys = split(rng_key, num_envs + 1)
+    const uint32_t m = madn_det_valid_mask(g, s);
+    if (m) {
+      const int cur = s.cur;
+      const int type = cur == 0 ? agent_type.x : cur == 1 ? agent_type.y : cur == 2 ? agent_type.z : agent_type.w;
+      int a;
+      if (type == 3) a = categorical_masked(key, m);
+      else if (type == 2) a = madn_rule_based_action(g, s, m, key);
+      else a = search_action[i];
+      madn_det_step(g, s, a / 6, a % 6 + 1, m);  // map_action
+    } else {
+      madn_det_no_step(g, s);
+    }
+    store_det_all(g, p, i, s);
+    if (s.done && winners) {  // manual_get_winner (:16-45) on the new board
+      const uint64_t any = s.occ[0] | s.occ[1] | s.occ[2] | s.occ[3];
+      int w[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) w[q] = player_done(g, any, q);
+      if (DS_RULE(g, DOGSTEP_RULE_TEAMS)) {
+        const int t0 = w[0] & w[2], t1 = w[1] & w[3];
+        const int none = (t0 & t1) | !(t0 | t1);
+        w[0] = w[2] = !none && t0;
+        w[1] = w[3] = !none && !t0;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) winners[4 * i + q] += w[q];
+    }
+    active = 1;
+  }
+  if (active_count) {
+    const unsigned b = __ballot_sync(0xFFFFFFFFu, active);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(active_count, (unsigned long long)__popc(b));
+  }
+}
+
 // Persistent lockstep loop.  One game per lane, but the expensive part of a turn — one
 // Threefry-2x32-20 per LEGAL action for the categorical draw — is pooled per warp: the (game, action)
 // pairs of all 32 games are compacted into a shared list and dealt out evenly to the lanes, so a game
@@ -1093,6 +1199,19 @@ int dogstep_madn_cls_agent_step(const dogstep_madn_cls_state* s, int64_t n, cons
   if (!action || !root_value || !action_weights || !obs) return DOGSTEP_ERR_INVALID_ARG;
   if (int rc = traj_check(traj, n, (2 * g.n + 3) * g.total, 4, 1)) return rc;
   k_madn_agent_step<false><<<blocks_for(n, kThreads / 32), kThreads, 0, st>>>(g, p, n, action, root_value, action_weights, obs, *traj);
+  return check_launch();
+}
+
+int dogstep_madn_det_eval_step(const dogstep_madn_det_state* s, int64_t n, const dogstep_madn_cfg* cfg, const int32_t* agent_type,
+                               const int32_t* search_action, const uint32_t* host_rng_key, int64_t game_offset, int32_t* winners,
+                               unsigned long long* active_count, void* stream) {
+  DS_PROLOGUE(det_ptrs)
+  if (!agent_type || !host_rng_key) return DOGSTEP_ERR_INVALID_ARG;
+  for (int q = 0; q < g.n; ++q)
+    if (agent_type[q] != 2 && agent_type[q] != 3 && !search_action) return DOGSTEP_ERR_INVALID_ARG;  // a search seat needs actions
+  const int4 at = make_int4(agent_type[0], agent_type[1], agent_type[2], agent_type[3]);
+  k_madn_det_eval_step<<<blocks_for(n, kThreads), kThreads, 0, st>>>(g, p, n, at, search_action, Key2{host_rng_key[0], host_rng_key[1]},
+                                                                     game_offset, winners, active_count);
   return check_launch();
 }
 

@@ -376,6 +376,19 @@ int dogstep_dog_agent_step(const dogstep_dog_state* s, int64_t n, const dogstep_
                            const float* root_value, const float* action_weights, const int8_t* obs,
                            const dogstep_replay_arrays* traj, void* stream);
 
+/* ---------------------------------------------------------------- evaluation loop
+ * One lockstep iteration of play_eval_loop_jitted (MuZero_det_MADN/evaluate_agent.py:733-930) for every game that is not
+ * done: the seat to move is played by agent_type[current_player] (host int32[4], the reference's params['type']):
+ * 3 = random legal policy (do_random :774-778), 2 = the rule-based scorer (do_rule_based :780-878, categorical over
+ * score / 0.25), anything else = tree search, whose action for this game is read from search_action[g] (device int32 [n];
+ * may be NULL when no seat searches).  No legal action -> no_step.  Per-game step key = split(rng_key, n + 1)[g + 1] with
+ * the global game index g = game_offset + local index, as in the other lockstep drivers.  winners int32 [n,4] (may be NULL)
+ * accumulates manual_get_winner (:16-45) when a game ends.  Float contract of the scorer: IEEE float32 add / div in the
+ * reference's order, gumbel = -log(-log(u)) with each log rounded once from double. */
+int dogstep_madn_det_eval_step(const dogstep_madn_det_state* s, int64_t n, const dogstep_madn_cfg* cfg, const int32_t* agent_type,
+                               const int32_t* search_action, const uint32_t* host_rng_key, int64_t game_offset, int32_t* winners,
+                               unsigned long long* active_count, void* stream);
+
 /* ---------------------------------------------------------------- TicTacToe (BASELINE config 1)
  * Batched leaves of `TicTacToe` / `TicTacToeV2` (TicTacToe/TicTacToe.py:12-17, TicTacToeV2.py:14-20).
  * variant 0 = TicTacToe.py, 1 = TicTacToeV2.py (last three moves per player persist; `memory`). */
