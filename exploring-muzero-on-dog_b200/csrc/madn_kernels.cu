@@ -912,14 +912,17 @@ __global__ void __launch_bounds__(kThreads) k_madn_agent_step(const __grid_const
   const int idx = row[0], has_valid = row[1];
   if (idx < 0 || idx >= tr.max_episode_length) return;
   const int64_t r = i * tr.max_episode_length + idx;
-  for (int k = lane; k < A; k += 32) tr.child_visits[r * A + k] = has_valid ? weights[i * A + k] : 0.0f;
+  if (has_valid) coop_copy_bytes(tr.child_visits + r * A, weights + i * A, (int64_t)A * 4, lane, 32);
+  else coop_zero_bytes(tr.child_visits + r * A, (int64_t)A * 4, lane, 32);
   const int8_t* src = obs + i * tr.obs_size;
   if (tr.obs_is_int8) {
     int8_t* d = (int8_t*)tr.observations + r * tr.obs_size;
-    for (int k = lane; k < tr.obs_size; k += 32) d[k] = has_valid ? src[k] : (int8_t)0;
+    if (has_valid) coop_copy_bytes(d, src, tr.obs_size, lane, 32);
+    else coop_zero_bytes(d, tr.obs_size, lane, 32);
   } else {
     float* d = (float*)tr.observations + r * tr.obs_size;
-    for (int k = lane; k < tr.obs_size; k += 32) d[k] = has_valid ? (float)src[k] : 0.0f;
+    if (has_valid) coop_widen_i8_f32(d, src, tr.obs_size, lane, 32);
+    else coop_zero_bytes(d, (int64_t)tr.obs_size * 4, lane, 32);
   }
 }
 

@@ -22,29 +22,33 @@ __global__ void __launch_bounds__(256) k_replay_save(dogstep_replay_arrays buf, 
   const int Tb = buf.max_episode_length, Tt = traj.max_episode_length;
   const int t0 = blockIdx.x * 8, t1 = min(t0 + 8, length);  // 8 plies per CTA
   const int tid = threadIdx.x;
-  for (int t = t0; t < t1; ++t) {
-    const int64_t src = game * Tt + t, dst = (int64_t)pos * Tb + t;
-    if (buf.obs_is_int8) {
-      const int8_t* s = (const int8_t*)traj.observations + src * buf.obs_size;
+  if (t1 > t0) {
+    // the plies t0..t1-1 of one episode are contiguous in the trajectory and in the ring slot: one vectorised chunk per leaf
+    const int np = t1 - t0;
+    const int64_t src = game * Tt + t0, dst = (int64_t)pos * Tb + t0;
+    const int64_t ne = (int64_t)np * buf.obs_size;
+    if (buf.obs_is_int8 == traj.obs_is_int8) {
+      const int es = buf.obs_is_int8 ? 1 : 4;
+      coop_copy_bytes((char*)buf.observations + dst * buf.obs_size * es, (const char*)traj.observations + src * buf.obs_size * es, ne * es, tid, 256);
+    } else if (buf.obs_is_int8) {
+      const float* sf = (const float*)traj.observations + src * buf.obs_size;
       int8_t* d = (int8_t*)buf.observations + dst * buf.obs_size;
-      if (traj.obs_is_int8) for (int k = tid; k < buf.obs_size; k += 256) d[k] = s[k];
-      else { const float* sf = (const float*)traj.observations + src * buf.obs_size; for (int k = tid; k < buf.obs_size; k += 256) d[k] = (int8_t)sf[k]; }
+      for (int64_t k = tid; k < ne; k += 256) d[k] = (int8_t)sf[k];
     } else {
-      float* d = (float*)buf.observations + dst * buf.obs_size;
-      if (traj.obs_is_int8) { const int8_t* s = (const int8_t*)traj.observations + src * buf.obs_size; for (int k = tid; k < buf.obs_size; k += 256) d[k] = (float)s[k]; }
-      else { const float* s = (const float*)traj.observations + src * buf.obs_size; for (int k = tid; k < buf.obs_size; k += 256) d[k] = s[k]; }
+      coop_widen_i8_f32((float*)buf.observations + dst * buf.obs_size, (const int8_t*)traj.observations + src * buf.obs_size, ne, tid, 256);
     }
-    for (int k = tid; k < buf.action_dim; k += 256) buf.child_visits[dst * buf.action_dim + k] = traj.child_visits[src * buf.action_dim + k];
-    if (buf.stochastic && tid < 6) buf.dice_distributions[dst * 6 + tid] = traj.dice_distributions[src * 6 + tid];
-    if (tid == 0) {
-      buf.actions[dst] = traj.actions[src];
-      buf.rewards[dst] = traj.rewards[src];
-      buf.root_values[dst] = traj.root_values[src];
-      buf.masks[dst] = traj.masks[src];
-      buf.players[dst] = traj.players[src];
-      buf.teams[dst] = traj.teams[src];
-      buf.discounts[dst] = traj.discounts[src];
-      if (buf.stochastic) buf.dice_outcomes[dst] = traj.dice_outcomes[src];
+    coop_copy_bytes(buf.child_visits + dst * buf.action_dim, traj.child_visits + src * buf.action_dim, (int64_t)np * buf.action_dim * 4, tid, 256);
+    if (buf.stochastic && tid < 6 * np) buf.dice_distributions[dst * 6 + tid] = traj.dice_distributions[src * 6 + tid];
+    if (tid < np) {
+      const int64_t a = src + tid, b = dst + tid;
+      buf.actions[b] = traj.actions[a];
+      buf.rewards[b] = traj.rewards[a];
+      buf.root_values[b] = traj.root_values[a];
+      buf.masks[b] = traj.masks[a];
+      buf.players[b] = traj.players[a];
+      buf.teams[b] = traj.teams[a];
+      buf.discounts[b] = traj.discounts[a];
+      if (buf.stochastic) buf.dice_outcomes[b] = traj.dice_outcomes[a];
     }
   }
   if (blockIdx.x == 0 && tid == 0) buf.episode_lengths[pos] = length;
