@@ -336,7 +336,18 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL may print its version banner on stdout while the communicator is created: keep stdout for the one JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     n = args.games
     offset = rank * n                                    # rank r owns global games [r*n, (r+1)*n)
     key = jaxrand.split_host(jaxrand.PRNGKey(0))[1]      # subkey = split(PRNGKey(0))[1]  (game_agent.py:187)
