@@ -181,7 +181,57 @@ def measure_extras(dev, key):
                                                "algorithmic_bytes_per_sim": bytes_per_sim, "achieved": n * S * bytes_per_sim / (ms / 1e3) / 1e9,
                                                "peak": peak, "unit": "GB/s", "frac": n * S * bytes_per_sim / (ms / 1e3) / 1e9 / peak}}
     out.update(measure_cfg5(dev, key, peak))
+    # config 1: TicTacToeV2, 512 lockstep games x 50 simulations per ply, true-env callbacks with rollout, PUCT (TicTacToe/mcts.py:9-23)
+    from exploring_muzero_on_dog_b200.TicTacToe import mcts as tm
+    cache = mcts.GraphCache()
+    for rep in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _, plies = tm.play_mcts_games(512, jaxrand.PRNGKey(rep), num_simulations=50, limit=30, variant=1, device=dev, graph_cache=cache)
+        e1.record()
+        torch.cuda.synchronize()
+    ms, moves = e0.elapsed_time(e1), int(plies.sum().item())
+    out["ttt_cfg1"] = {"workload": "cfg1: TicTacToeV2 self-play, 512 lockstep games x 50 sims per ply (muzero_policy on the true env with rollouts), "
+                                   "to termination; each ply's search replayed as one CUDA graph",
+                       "searched_moves": moves, "ms": ms, "sims_per_s": moves * 50 / (ms / 1e3), "env_steps_per_s": moves / (ms / 1e3)}
     return out
+
+
+def measure_replay_exchange(dev, rank, world):
+    """N > 1 only: the one collective of the design — every rank samples a batch from its own replay shard and the batches are
+    all-gathered over NCCL (VectorizedReplayBuffer.sample_batch_global).  Off the stepping path; reported as a side number."""
+    import torch
+    import torch.distributed as dist
+    from exploring_muzero_on_dog_b200 import vec_replay_buffer
+    n, T, A = 2048, 64, 24
+    g = torch.Generator(device=dev).manual_seed(rank)
+    traj = dict(obs=torch.randint(-1, 4, (n, T, 34, 56), device=dev, generator=g, dtype=torch.int8),
+                act=torch.randint(0, A, (n, T), device=dev, generator=g, dtype=torch.int32),
+                rew=torch.randint(0, 3, (n, T), device=dev, generator=g, dtype=torch.int32),
+                val=torch.rand(n, T, device=dev, generator=g), pol=torch.rand(n, T, A, device=dev, generator=g),
+                mask=torch.ones(n, T, device=dev), player=torch.randint(0, 4, (n, T), device=dev, generator=g, dtype=torch.int32),
+                team=torch.randint(0, 2, (n, T), device=dev, generator=g, dtype=torch.int32),
+                discount=torch.randint(0, 3, (n, T), device=dev, generator=g, dtype=torch.int32),
+                idx=torch.full((n,), T, device=dev, dtype=torch.int32))
+    buf = vec_replay_buffer.VectorizedReplayBuffer(n, 128, 10, 50, obs_shape=(34, 56), action_dim=A, max_episode_length=T, device=dev,
+                                                   obs_dtype=torch.int8, seed=rank)
+    buf.save_games_from_buffers(traj)
+    ms = []
+    for rep in range(6):
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        batch = buf.sample_batch_global()
+        e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    t = torch.tensor([sorted(ms[1:])[len(ms[1:]) // 2]], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    nbytes = sum(v.numel() * v.element_size() for v in batch.values())
+    return {"replay_exchange": {"workload": "sample_batch(128, unroll 10, td 50) on every rank + NCCL all-gather of the batch leaves",
+                                "ms": float(t.item()), "global_batch": int(batch["actions"].shape[0]), "gathered_bytes_per_rank": int(nbytes),
+                                "collective": "one ncclAllGather of the %d packed leaves" % len(batch)}}
 
 
 def measure_cfg5(dev, key, peak):
@@ -434,6 +484,8 @@ def main():
     extras = None
     if world == 1 and not args.no_extras:
         extras = measure_extras(dev, key)
+    elif world > 1 and not args.no_extras:
+        extras = measure_replay_exchange(dev, rank, world)
 
     if rank == 0:
         peak, peak_src = _peaks()
