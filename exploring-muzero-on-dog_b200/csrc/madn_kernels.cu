@@ -549,7 +549,7 @@ constexpr int kRingMax = 64;  // longest round the key ring holds
 // `threads` = game threads (the CTA has one more warp, the key-chain producer)
 static size_t play_smem_bytes(int threads) {
   return (size_t)(threads / 32) * (24 * 32 * 2 + 32 * 4 + 32 * 8) + (size_t)kXWords * threads * 4 + 2 * 34 * 4 +
-         2 * (kRingMax + 1) * 8;
+         2 * (kRingMax + 2) * 8;
 }
 
 template <uint32_t CT>
@@ -567,7 +567,7 @@ __global__ void __launch_bounds__(kPlayMaxThreads + 32) k_madn_det_play_cta(cons
   uint16_t* s_items = reinterpret_cast<uint16_t*>(smem_raw + (size_t)W * 384) + pw * (24 * 32);  // [W][768]
   uint32_t* s_x = reinterpret_cast<uint32_t*>(smem_raw + (size_t)W * 1920);                     // [kXWords][T]
   uint32_t* s_cnt = s_x + (size_t)kXWords * T;                                                  // 2 x [34] counts
-  uint2* s_ring = reinterpret_cast<uint2*>(s_cnt + 2 * 34);                                     // 2 x [kRingMax + 1] keys
+  uint2* s_ring = reinterpret_cast<uint2*>(s_cnt + 2 * 34);                                     // 2 x [kRingMax + 2] keys
   const uint32_t FULL = 0xFFFFFFFFu;
   const int64_t cta_base = (int64_t)blockIdx.x * T;
   int gi = threadIdx.x;  // game held by this lane, relative to cta_base
@@ -578,12 +578,12 @@ __global__ void __launch_bounds__(kPlayMaxThreads + 32) k_madn_det_play_cta(cons
   bool alive = false, canon = true;
   if (producer) {
     // The loop key chain rng_{t+1} = split(rng_t, N + 1)[0] (game_agent.py:60) is the same for every game: one warp per CTA
-    // computes it, a round ahead, into a double-buffered ring (ring[i] = rng_{t0 + i}, i = 0..round_len) instead of
+    // computes it, a round ahead, into a double-buffered ring (ring[i] = rng_{t0 + i}, i = 0..round_len + 1) instead of
     // every lane of every warp repeating it each iteration (it was one Threefry in seven, and sat on the critical path
     // of the next step key).
     Key2 r = rng0;
     if (lane == 0) s_ring[0] = make_uint2(r.a, r.b);
-    for (int i = 1; i <= round_len; ++i) {
+    for (int i = 1; i <= round_len + 1; ++i) {
       r = split_i(r, 0u);
       if (lane == 0) s_ring[i] = make_uint2(r.a, r.b);
     }
@@ -667,13 +667,13 @@ __global__ void __launch_bounds__(kPlayMaxThreads + 32) k_madn_det_play_cta(cons
     }
     // ---- kPlayRound lockstep iterations
     const int tend = min(t + round_len, max_steps);
-    const uint2* rk = s_ring + par * (kRingMax + 1);  // rk[i] = the loop key of iteration t + i
+    const uint2* rk = s_ring + par * (kRingMax + 2);  // rk[i] = the loop key of iteration t + i
     if (producer) {  // next round's keys
-      uint2* nk = s_ring + (par ^ 1) * (kRingMax + 1);
+      uint2* nk = s_ring + (par ^ 1) * (kRingMax + 2);
       const uint2 r0 = rk[round_len];
       Key2 r{r0.x, r0.y};
       if (lane == 0) nk[0] = r0;
-      for (int i = 1; i <= round_len; ++i) {
+      for (int i = 1; i <= round_len + 1; ++i) {
         r = split_i(r, 0u);
         if (lane == 0) nk[i] = make_uint2(r.a, r.b);
       }
@@ -685,13 +685,17 @@ __global__ void __launch_bounds__(kPlayMaxThreads + 32) k_madn_det_play_cta(cons
     int ri = 0;
     if (tail) {
       uint32_t mant = bits_i(key, (uint32_t)lane) >> 9;  // lane a: the draw of action a (lanes >= 24 unused)
+      Key2 key1 = split_i(Key2{rk[1].x, rk[1].y}, my);   // step key of the NEXT iteration
       const uint32_t tag = lane < 24 ? 23u - (uint32_t)lane : 0u;
 #pragma unroll 1
       for (; t < tend && alive; ++t) {
         ++ri;
-        const uint2 rn = rk[ri];
-        const Key2 key_next = split_i(Key2{rn.x, rn.y}, my);           // next iteration's draws: independent of the state,
-        const uint32_t mant_next = bits_i(key_next, (uint32_t)lane) >> 9;  // they overlap the dependent chain below
+        // two independent Threefry chains per iteration, both with inputs known at the top of the loop: the draws of
+        // iteration t + 1 (from its key) and the key of iteration t + 2 — they overlap each other and the state-dependent
+        // chain below (mask -> argmax -> move)
+        const uint2 rn = rk[ri + 1];
+        const uint32_t mant_next = bits_i(key1, (uint32_t)lane) >> 9;
+        const Key2 key2 = split_i(Key2{rn.x, rn.y}, my);
         int cp = 0;
         const uint32_t m = det_valid_mask4(R, g, s, cp);
         if (m) {
@@ -711,6 +715,7 @@ __global__ void __launch_bounds__(kPlayMaxThreads + 32) k_madn_det_play_cta(cons
           }
         }
         mant = mant_next;
+        key1 = key2;
       }
       t = tend;
       continue;
