@@ -176,7 +176,9 @@ int dogstep_dog_substep(const dogstep_dog_state* s, int64_t n, const dogstep_dog
  * derivation as dogstep_madn_det_random_step) */
 int dogstep_dog_random_step(const dogstep_dog_state* s, int64_t n, const dogstep_dog_cfg* cfg, const uint32_t* host_rng_key,
                             int64_t game_offset, unsigned long long* active_count, void* stream);
-/* the whole random-policy loop as one persistent launch (cap MuZero_DOG/evaluate_agent.py:518) */
+/* the whole random-policy loop as one persistent launch (cap MuZero_DOG/evaluate_agent.py:518).  Games are handed to the
+ * warps through a device-side queue counter; the library keeps one 256-byte scratch allocation for these counters (made at
+ * the first call, never freed) — its only allocation. */
 int dogstep_dog_play_random(const dogstep_dog_state* s, int64_t n, const dogstep_dog_cfg* cfg, const uint32_t* host_rng_key,
                             int64_t game_offset, int32_t max_steps, int32_t* game_len, unsigned long long* total_steps,
                             void* stream);
