@@ -502,14 +502,15 @@ int dogstep_dog_play_random(const dogstep_dog_state* s, int64_t n, const dogstep
   const size_t smem = sizeof(DogS) * kSyncWarps;
   cudaFuncSetAttribute(k_dog_play_random, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   // per-launch game queue: a rotating pool of counters so that launches in flight on different streams do not share one
-  static unsigned int* pool = nullptr;
+  static unsigned int* pools[64] = {};  // one pool per device ordinal
   static std::atomic<unsigned> ticket{0};
   static std::mutex pool_mu;
+  if (dev < 0 || dev >= 64) return DOGSTEP_ERR_UNSUPPORTED;
   {
     std::lock_guard<std::mutex> lock(pool_mu);
-    if (!pool && cudaMalloc(&pool, 64 * sizeof(unsigned int)) != cudaSuccess) return check_launch();
+    if (!pools[dev] && cudaMalloc(&pools[dev], 64 * sizeof(unsigned int)) != cudaSuccess) return check_launch();
   }
-  unsigned int* queue = pool + (ticket.fetch_add(1) & 63u);
+  unsigned int* queue = pools[dev] + (ticket.fetch_add(1) & 63u);
   cudaMemsetAsync(queue, 0, sizeof(unsigned int), st);
   k_dog_play_random<<<grid, kSyncWarps * 32, smem, st>>>(g, p, n, Key2{host_rng_key[0], host_rng_key[1]}, game_offset, max_steps,
                                                         game_len, total_steps, queue);
