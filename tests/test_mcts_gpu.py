@@ -26,7 +26,8 @@ def _mk_cfgs(policy, qt, S, depth, A, Cn, E, **kw):
 class Net:
     """deterministic stand-in for dynamics+prediction: emb' = tanh(W[a] emb), heads are linear maps of emb'"""
 
-    def __init__(self, A, Cn, E, seed):
+    def __init__(self, A, Cn, E, seed, quantize=False):
+        self.quantize = quantize  # priors / values on a coarse grid: many exactly equal scores, the first index must win
         g = torch.Generator(device="cuda").manual_seed(seed)
         self.W = torch.randn(A + Cn, E, E, device="cuda", generator=g) * 0.7
         self.P = torch.randn(E, A, device="cuda", generator=g)
@@ -34,6 +35,9 @@ class Net:
 
     def __call__(self, action, emb):
         nxt = torch.tanh(torch.einsum("nij,nj->ni", self.W[action], emb))
+        if self.quantize:
+            return dict(prior=torch.round(nxt @ self.P), value=torch.round(torch.tanh(nxt.sum(1)) * 2) / 2, reward=torch.zeros_like(nxt[:, 0]),
+                        discount=torch.where(nxt[:, 1] > 0, 1.0, -1.0), emb=nxt, chance=torch.round(nxt @ self.Pc))
         return dict(prior=nxt @ self.P, value=torch.tanh(nxt.sum(1)), reward=0.1 * nxt[:, 0],
                     discount=torch.where(nxt[:, 1] > 0, 1.0, -1.0), emb=nxt, chance=nxt @ self.Pc)
 
@@ -61,24 +65,32 @@ CASES = [
     (0, 1, 24, 0, 40, 5),      # muzero_policy, depth cut revisits
     (1, 2, 806, 0, 100, 50),   # DOG-wide action space (config 5)
     (0, 2, 806, 0, 30, 8),
+    (1, 2, 806, 0, 100, 50, "ties"),   # quantised priors and values: exact ties everywhere (argmax keeps the FIRST maximum)
+    (1, 2, 100, 0, 60, 50, "ties"),
+    (1, 2, 33, 0, 40, 50),             # the narrowest wide tree
+    (1, 2, 832, 0, 20, 50),            # the widest register-path tree
 ]
 
 
-@pytest.mark.parametrize("policy,qt,A,Cn,S,depth", CASES)
-def test_cuda_search_equals_oracle(policy, qt, A, Cn, S, depth):
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "-".join(str(x) for x in c))
+def test_cuda_search_equals_oracle(case):
     from exploring_muzero_on_dog_b200 import mcts
+    policy, qt, A, Cn, S, depth = case[:6]
+    ties = len(case) > 6
     n, E = 96, 16
     ccfg, ocfg = _mk_cfgs(policy, qt, S, depth, A, Cn, E)
     rng = np.random.default_rng(1000 * policy + A)
     keys = rng.integers(0, 2**32, (n, 2), dtype=np.uint64).astype(np.uint32)
     prior = rng.standard_normal((n, A)).astype(np.float32) * 2
+    if ties:
+        prior = np.round(prior)
     value = rng.uniform(-1, 1, n).astype(np.float32)
     emb = rng.standard_normal((n, E)).astype(np.float32)
     invalid = (rng.random((n, A)) < 0.4).astype(np.uint8)
     invalid[np.arange(n), rng.integers(0, A, n)] = 0
     invalid[:4] = 0
     noise = rng.dirichlet(np.full(A, 0.3), n).astype(np.float32)
-    net = Net(A, Cn, E, 7)
+    net = Net(A, Cn, E, 7, quantize=ties)
 
     s = mcts.Search(ccfg, n)
     dev = lambda x: torch.as_tensor(x, device="cuda")
