@@ -148,7 +148,7 @@ def play_n_games_v3(params, rng_key, input_shape, num_envs, num_simulation, max_
 
 
 def play_n_dog_games(params, rng_key, num_envs, num_simulation, max_depth, max_steps, temp, *, root_fn, recurrent_fn, rules=DOG_RULES,
-                     obs_dtype=torch.int8, device="cuda", max_num_considered_actions=16):
+                     obs_dtype=torch.int8, device="cuda", max_num_considered_actions=16, graph_cache=None):
     """BASELINE config 5: play_n_games_v3's shape (game_agent.py:185-192) on the DOG env (MuZero_DOG/game_agent.py:12-44 rules and
     batch_reset), Gumbel MuZero search over the 806 DOG actions (MuZero_DOG/muzero_dog.py:101-136).  The reference's DOG
     networks are stubs, so root_fn / recurrent_fn are the caller's."""
@@ -161,7 +161,8 @@ def play_n_dog_games(params, rng_key, num_envs, num_simulation, max_depth, max_s
         out = mcts.gumbel_muzero_policy(p, key2, root_fn(p, obs.to(torch.float32)), recurrent_fn, num_simulation,
                                         invalid_actions=invalid, max_depth=max_depth,
                                         qtransform=functools.partial(mcts.qtransform_completed_by_mix_value, value_scale=0.5),
-                                        gumbel_scale=temp, max_num_considered_actions=max_num_considered_actions)
+                                        gumbel_scale=temp, max_num_considered_actions=max_num_considered_actions,
+                                        **({} if graph_cache is None else {"graph_cache": graph_cache}))
         return out.action, out.action_weights, out.search_tree.summary().value
 
     return envs, play_batch_of_games(envs, num_envs, (dg.RAW_OBS_SIZE,), params, subkey, num_simulation, max_depth, max_steps, temp,
