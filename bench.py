@@ -181,6 +181,32 @@ def measure_extras(dev, key):
                                                "algorithmic_bytes_per_sim": bytes_per_sim, "achieved": n * S * bytes_per_sim / (ms / 1e3) / 1e9,
                                                "peak": peak, "unit": "GB/s", "frac": n * S * bytes_per_sim / (ms / 1e3) / 1e9 / peak}}
     out.update(measure_cfg5(dev, key, peak))
+    # config 2 driven per call: one fused lockstep iteration (legal mask + categorical draw + env_step / no_step) per launch,
+    # i.e. what a jitted loop body that calls the drop-in functions every iteration pays; 842 iterations = the longest game
+    from exploring_muzero_on_dog_b200.MADN import deterministic_madn as dm
+    n2 = 65536
+    seeds2 = jaxrand.randint(key, n2, 0, 1_000_000, device=dev)
+    iters = 842
+    for rep in range(2):
+        env2 = dm.env_reset(0, seed=seeds2, device=dev, **RULES)
+        act = torch.zeros(1, dtype=torch.int64, device=dev)
+        import numpy as np
+        k = np.asarray(key, dtype=np.uint32)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for t in range(iters):
+            dm.random_step(env2, k, active_count=act)
+            k = jaxrand.split_host(k)[0]
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    steps2 = int(act.item())
+    out["madn_cfg2_per_call"] = {"workload": "cfg2 through one launch per lockstep iteration (k_madn_det_random_step), 65,536 games, 842 iterations",
+                                 "env_steps": steps2, "ms": ms, "env_steps_per_s": steps2 / (ms / 1e3), "gpu_launches": iters,
+                                 "all_done": bool(env2.raw("done").all()),
+                                 "roofline": {"bound": "hbm", "kernel": "k_madn_det_random_step", "algorithmic_bytes_per_env_step": BYTES_PER_STEP,
+                                              "achieved": steps2 * BYTES_PER_STEP / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                                              "frac": steps2 * BYTES_PER_STEP / (ms / 1e3) / 1e9 / peak}}
     # config 1: TicTacToeV2, 512 lockstep games x 50 simulations per ply, true-env callbacks with rollout, PUCT (TicTacToe/mcts.py:9-23)
     from exploring_muzero_on_dog_b200.TicTacToe import mcts as tm
     cache = mcts.GraphCache()
