@@ -59,6 +59,15 @@ class BatchedEnv:
     def __setattr__(self, name, value):
         raise AttributeError("envs are immutable like the reference's dataclasses; use .replace()")
 
+    def memo(self, key, make):
+        """per-env cache of the ctypes structs handed to the C-ABI (leaves are never rebound after alloc(), static fields
+        only change through replace(), which builds a new env): keeps the per-call host cost of the drop-in functions low"""
+        c = self.__dict__.setdefault("_memo", {})
+        v = c.get(key)
+        if v is None:
+            v = c[key] = make()
+        return v
+
     def raw(self, name):
         """leaf WITH the game axis, whatever `batched` says"""
         return self._t[name]

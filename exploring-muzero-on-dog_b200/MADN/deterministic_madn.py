@@ -73,10 +73,16 @@ class deterministic_MADN(BatchedEnv):
         return self._const("goal")
 
     def cfg(self):
+        return self.memo("cfg", self._make_cfg)
+
+    def _make_cfg(self):
         s = self.static
         return _lib.MadnCfg(s["num_players"], s["layout_mask"], s["board_size"] // 4, _rules.to_mask(s["rules"]))
 
     def cstate(self):
+        return self.memo("cstate", self._make_cstate)
+
+    def _make_cstate(self):
         t = self._t
         return _lib.MadnDetState(*[C.c_void_p(t[k].data_ptr()) for k in
                                    ("board", "current_player", "pins", "reward", "done", "action_set", "key")])
