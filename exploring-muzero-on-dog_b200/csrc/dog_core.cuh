@@ -556,7 +556,10 @@ __device__ __noinline__ void dog_distribute_cards(const DogGeom& g, DogS& s, int
   }
   __syncwarp();
   const Key2 key{s.key[0], s.key[1]};
-  const Key2 knew = split_i(key, 0), sub = split_i(key, 1);
+  // key, sub = split(env.key): one Threefry pass, even lanes take element 0 and odd lanes element 1
+  const Key2 both = split_i(key, (uint32_t)(lane & 1));
+  const Key2 knew{__shfl_sync(0xFFFFFFFFu, both.a, 0), __shfl_sync(0xFFFFFFFFu, both.b, 0)};
+  const Key2 sub{__shfl_sync(0xFFFFFFFFu, both.a, 1), __shfl_sync(0xFFFFFFFFu, both.b, 1)};
   // slot j of the expanded pool holds card type c iff cum[c] <= j < cum[c+1]; dummies after the real cards.
   // argsort(uniform) is only needed for its first n*quantity entries: every lane keeps its four (uniform, index) keys and
   // card types in registers and the warp extracts the minimum `need` times with redux.sync (stable: the index is in the key)
@@ -591,16 +594,32 @@ __device__ __noinline__ void dog_distribute_cards(const DogGeom& g, DogS& s, int
     }
   }
   __syncwarp();
-  if (lane == 0) {
-    for (int p = 0; p < n; ++p)
-      for (int slot = 0; slot < quantity && slot < 6; ++slot) {
-        int idx = p * quantity + slot;
-        if (idx < deck_total) {
-          int c = s.items[idx];
-          s.hands[p][c] = (int8_t)(s.hands[p][c] + 1);
-          s.deck[c] = (int8_t)(s.deck[c] - 1);
-        }
+  // deal: seat p receives the cards of ranks p * quantity .. p * quantity + quantity - 1.  Lanes own (seat, card type) pairs
+  // and count their cards among the seat's ranks (the scalar loop over the 24 ranks on lane 0 was the longest serial
+  // stretch of a turn); lanes 0..13 then take the dealt cards off the deck.
+  {
+    const int q6 = quantity < 6 ? quantity : 6;
+    for (int pc = lane; pc < n * kNCard; pc += 32) {
+      const int p = pc / kNCard, c = pc - p * kNCard;
+      int cnt = 0;
+      for (int slot = 0; slot < q6; ++slot) {
+        const int idx = p * quantity + slot;
+        cnt += (idx < deck_total && (int)s.items[idx] == c) ? 1 : 0;
       }
+      if (cnt) s.hands[p][c] = (int8_t)(s.hands[p][c] + cnt);
+    }
+    if (lane < kNCard) {
+      int cnt = 0;
+      for (int p = 0; p < n; ++p)
+        for (int slot = 0; slot < q6; ++slot) {
+          const int idx = p * quantity + slot;
+          cnt += (idx < deck_total && (int)s.items[idx] == lane) ? 1 : 0;
+        }
+      if (cnt) s.deck[lane] = (int8_t)(s.deck[lane] - cnt);
+    }
+  }
+  __syncwarp();
+  if (lane == 0) {
     int rs = (s.round_starter == -1) ? s.cur : d_fmod(s.round_starter + 1, n);
     s.cur = rs;
     s.round_starter = rs;

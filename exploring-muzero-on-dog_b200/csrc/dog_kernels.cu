@@ -112,15 +112,11 @@ __device__ __forceinline__ int dog_categorical(const DogGeom& g, DogS& s, int la
     uint32_t m = bits_i(key, (uint32_t)a) >> 9;
     if (best_a == 0x7FFFFFFF || m > best_m) { best_m = m; best_a = a; }  // items ascend, so ties keep the first
   }
-#pragma unroll
-  for (int o = 16; o; o >>= 1) {
-    uint32_t om = __shfl_xor_sync(FULL, best_m, o);
-    int oa = __shfl_xor_sync(FULL, best_a, o);
-    bool take = (oa != 0x7FFFFFFF) && (best_a == 0x7FFFFFFF || om > best_m || (om == best_m && oa < best_a));
-    if (take) { best_m = om; best_a = oa; }
-  }
+  // largest mantissa, lowest action among equals: two redux instead of a five-step shuffle butterfly
+  const uint32_t top = __reduce_max_sync(FULL, best_a == 0x7FFFFFFF ? 0u : best_m);
+  const int first = (int)__reduce_min_sync(FULL, (best_a != 0x7FFFFFFF && best_m == top) ? (uint32_t)best_a : 0x7FFFFFFFu);
   __syncwarp();
-  return best_a;
+  return first;
 }
 
 #define DOG_KERNEL_PROLOGUE                                            \
@@ -377,8 +373,10 @@ __global__ void __launch_bounds__(kSyncWarps * 32, 1) k_dog_play_random(const __
     __syncthreads();
     int a = -1;
     if (have) {                                                     // phase B
-      const Key2 key = split_i(rng, (uint32_t)(game_offset + i + 1));
-      rng = split_i(rng, 0u);
+      // one Threefry pass for both keys of the turn: lane 0 takes split(rng, N + 1)[0], the others the game's step key
+      const Key2 both = split_i(rng, lane == 0 ? 0u : (uint32_t)(game_offset + i + 1));
+      const Key2 key{__shfl_sync(0xFFFFFFFFu, both.a, 1), __shfl_sync(0xFFFFFFFFu, both.b, 1)};
+      rng = Key2{__shfl_sync(0xFFFFFFFFu, both.a, 0), __shfl_sync(0xFFFFFFFFu, both.b, 0)};
       a = dog_categorical(g, s, lane, key);
     }
     if (have) {                                                     // phase C
