@@ -119,6 +119,54 @@ __device__ __forceinline__ int dog_categorical(const DogGeom& g, DogS& s, int la
   return first;
 }
 
+// dog_categorical for the persistent play kernel, with the NEXT turn's two key derivations riding in the idle lanes of the
+// last item pass (a game has 10-40 legal actions, so the last pass of 32 usually has room): `key` is this turn's step key,
+// `rng1` the loop key of the next turn; on return key = split(rng1, N + 1)[g + 1] (the next step key) and
+// rng1 = split(rng1, N + 1)[0] (the loop key after that).  Saves the separate Threefry pass per turn.
+__device__ __forceinline__ int dog_categorical_pipelined(const DogGeom& g, DogS& s, int lane, Key2& key, Key2& rng1, uint32_t my) {
+  const uint32_t FULL = 0xFFFFFFFFu;
+  const int nwords = (g.num_actions + 31) >> 5;
+  const uint32_t w = (lane < nwords) ? s.mask[lane] : 0u;
+  const int cnt = __popc(w);
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(FULL, incl, o);
+    if (lane >= o) incl += v;
+  }
+  const int total = __shfl_sync(FULL, incl, 31);
+  int off = incl - cnt;
+  for (uint32_t m = w; m; m &= m - 1) s.items[off++] = (uint16_t)(lane * 32 + __ffs(m) - 1);
+  __syncwarp();
+  // slots total and total + 1 of the padded item list carry the two key derivations
+  const int slots = total + 2;
+  uint32_t best_m = 0;
+  int best_a = 0x7FFFFFFF;
+  Key2 nkey{0u, 0u}, nrng{0u, 0u};
+  for (int base = 0; base < slots; base += 32) {
+    const int j = base + lane;
+    const bool item = j < total, kslot = j == total, rslot = j == total + 1;
+    const int a = item ? (int)s.items[j] : 0;
+    const Key2 k = item ? key : rng1;
+    const uint32_t c = item ? (uint32_t)a : (kslot ? my : 0u);
+    const Key2 o = threefry2x32(k, 0u, c);
+    if (item) {
+      const uint32_t m = (o.a ^ o.b) >> 9;
+      if (best_a == 0x7FFFFFFF || m > best_m) { best_m = m; best_a = a; }  // items ascend, so ties keep the first
+    }
+    const uint32_t kb = __ballot_sync(FULL, kslot), rb = __ballot_sync(FULL, rslot);
+    if (kb) { const int src = __ffs(kb) - 1; nkey = Key2{__shfl_sync(FULL, o.a, src), __shfl_sync(FULL, o.b, src)}; }
+    if (rb) { const int src = __ffs(rb) - 1; nrng = Key2{__shfl_sync(FULL, o.a, src), __shfl_sync(FULL, o.b, src)}; }
+  }
+  key = nkey;
+  rng1 = nrng;
+  if (total == 0) return -1;
+  const uint32_t top = __reduce_max_sync(FULL, best_a == 0x7FFFFFFF ? 0u : best_m);
+  const int first = (int)__reduce_min_sync(FULL, (best_a != 0x7FFFFFFF && best_m == top) ? (uint32_t)best_a : 0x7FFFFFFFu);
+  __syncwarp();
+  return first;
+}
+
 #define DOG_KERNEL_PROLOGUE                                            \
   __shared__ DogS sh[kDogWarps];                                       \
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;          \
@@ -354,7 +402,7 @@ __global__ void __launch_bounds__(kSyncWarps * 32, 1) k_dog_play_random(const __
   bool have = false;
   int len = 0;
   unsigned long long steps = 0;
-  Key2 rng = rng0;
+  Key2 rng = rng0, key = rng0;  // rng: loop key of the NEXT turn, key: step key of this turn (see dog_categorical_pipelined)
   while (true) {
     while (!have && i < n) {  // next game of this warp (games that are already over cost nothing)
       dog_load(g, p, i, s, lane);
@@ -365,20 +413,17 @@ __global__ void __launch_bounds__(kSyncWarps * 32, 1) k_dog_play_random(const __
       } else {
         have = true;
         len = 0;
-        rng = rng0;
+        // first step key and the loop key of the second turn, in one Threefry pass (lane 0: split(rng0, N + 1)[0])
+        const Key2 both = split_i(rng0, lane == 0 ? 0u : (uint32_t)(game_offset + i + 1));
+        key = Key2{__shfl_sync(0xFFFFFFFFu, both.a, 1), __shfl_sync(0xFFFFFFFFu, both.b, 1)};
+        rng = Key2{__shfl_sync(0xFFFFFFFFu, both.a, 0), __shfl_sync(0xFFFFFFFFu, both.b, 0)};
       }
     }
     if (!__syncthreads_or(have)) break;
     if (have) dog_build_mask_any(g, s, lane);                       // phase A
     __syncthreads();
     int a = -1;
-    if (have) {                                                     // phase B
-      // one Threefry pass for both keys of the turn: lane 0 takes split(rng, N + 1)[0], the others the game's step key
-      const Key2 both = split_i(rng, lane == 0 ? 0u : (uint32_t)(game_offset + i + 1));
-      const Key2 key{__shfl_sync(0xFFFFFFFFu, both.a, 1), __shfl_sync(0xFFFFFFFFu, both.b, 1)};
-      rng = Key2{__shfl_sync(0xFFFFFFFFu, both.a, 0), __shfl_sync(0xFFFFFFFFu, both.b, 0)};
-      a = dog_categorical(g, s, lane, key);
-    }
+    if (have) a = dog_categorical_pipelined(g, s, lane, key, rng, (uint32_t)(game_offset + i + 1));  // phase B
     if (have) {                                                     // phase C
       if (a >= 0) {
         int r, d;
