@@ -236,3 +236,46 @@ def test_device_exp_matches_libm():
     _lib.check(_lib.lib().dogstep_exp_f32(_lib.ptr(xd), C.c_int64(x.size), _lib.ptr(out), _lib.stream()), "exp_f32")
     got = out.cpu().numpy()
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_wide_select_cache_is_consistent_at_scale():
+    """config-5-shaped search (806 actions, 100 simulations) on 1,024 games with random network outputs: the per-node select
+    cache the wide Gumbel kernels maintain (select_aux) must describe the dense tree arrays exactly — bitmap of the children
+    with visits, visit sum / maximum, prior softmax statistics — and the usual search invariants hold."""
+    from exploring_muzero_on_dog_b200 import jaxrand, mcts
+    n, S, A, E = 1024, 100, 806, 32
+    g = torch.Generator(device="cuda").manual_seed(5)
+    rnd = lambda *shape: torch.randn(*shape, device="cuda", generator=g)
+    cfg = mcts._cfg(mcts.GUMBEL, mcts.qtransform_completed_by_mix_value(value_scale=0.5), S, 50, A, 0, E)
+    srch = mcts.Search(cfg, n)
+    keys = jaxrand.split(jaxrand.PRNGKey(9), n)
+    invalid = torch.rand(n, A, device="cuda", generator=g) < 0.3
+    invalid[:, 0] = False
+    srch.init(keys, mcts.RootFnOutput(rnd(n, A) * 2, torch.zeros(n, device="cuda"), rnd(n, E)), invalid, None)
+    srch.select(0)
+    for sim in range(S):
+        step = srch.expand_select if sim + 1 < S else srch.expand
+        step(sim, rnd(n, A) * 2, torch.tanh(rnd(n)), 0.1 * rnd(n), torch.where(rnd(n) > 0, 1.0, -1.0), rnd(n, E))
+    t = srch.tree
+    vc = t.children_visits                                            # [n, N, A]
+    aux = t.select_aux.view(torch.int32)                              # [n, N + 1, 36]
+    N = S + 1
+    assert (vc[:, 0].sum(1) == S).all() and (vc[:, 0][invalid] == 0).all()
+    assert (t.node_visits[:, 1:] >= 1).all() and (t.node_visits[:, 0] == S + 1).all()
+    # visit sum / maximum per node
+    assert torch.equal(aux[:, :N, 34], vc.sum(2).to(torch.int32)) and torch.equal(aux[:, :N, 35], vc.max(2).values.to(torch.int32))
+    # bitmap: word l, bit j <-> child l + 32 j
+    a = torch.arange(A, device="cuda")
+    words = aux[:, :N, :32].to(torch.int64) & 0xFFFFFFFF
+    bit = (words[:, :, a % 32] >> (a // 32)) & 1
+    assert torch.equal(bit.bool(), vc > 0)
+    # prior statistics of every expanded node: max and softmax denominator (float32 sums in a different order: tolerance)
+    lg = t.children_prior_logits
+    m1 = aux[:, :N, 32].view(torch.float32)
+    s1 = aux[:, :N, 33].view(torch.float32)
+    assert torch.equal(m1, lg.max(2).values)
+    assert torch.allclose(s1, torch.exp(lg.double() - m1.double().unsqueeze(2)).sum(2).float(), rtol=1e-5)
+    # root_invalid bitmap and valid count in the extra slot
+    rwords = aux[:, N, :32].to(torch.int64) & 0xFFFFFFFF
+    rbit = (rwords[:, a % 32] >> (a // 32)) & 1
+    assert torch.equal(rbit.bool(), invalid) and torch.equal(aux[:, N, 32], (~invalid).sum(1).to(torch.int32))
