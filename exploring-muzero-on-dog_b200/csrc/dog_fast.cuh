@@ -656,6 +656,61 @@ __device__ __forceinline__ void dog4_build_mask(const Dog4Rules& R, DogS& s, int
   __syncwarp();
 }
 
+// The same mask cut into tasks that ANY warp of the CTA can run on a record (bits are OR-ed into s.mask atomically), so that
+// the four 32-split chunks of the hot seven — the heavy part, needed only when the hand holds a seven or a joker — can be
+// shared out to warps whose own game has a light hand (k_dog_play_random).  sub 0..3 = the hot-seven chunks, 4..5 = the normal
+// moves (the second chunk also carries the four -4 moves), 6 = swaps.  `flags` (dog4_mask_flags): bit 0 swaps, bit 1 hot
+// seven, bit 2 moves.  s must be a canonical record in the play phase with s.mask zeroed.
+__device__ __forceinline__ int dog4_mask_flags(const Dog4Rules& R, const DogS& s) {
+  Dog4View v;
+  dg4_view_bits(R, s.pbits, s.pins, s.cur, v);
+  const int8_t* hand = s.hands[v.cp];
+  const bool joker = hand[0] > 0;
+  return ((joker || hand[1] > 0) ? 1 : 0) | ((joker || hand[7] > 0) ? 2 : 0) | 4;
+}
+
+__device__ __forceinline__ void dog4_mask_task(const Dog4Rules& R, DogS& s, int sub, int lane) {
+  Dog4View v;
+  dg4_view_bits(R, s.pbits, s.pins, s.cur, v);
+  const int8_t* hand = s.hands[v.cp];
+  const bool joker = hand[0] > 0;
+  if (sub < 4) {  // hot seven: splits 32 sub .. 32 sub + 31
+    const int it = 32 * sub + lane;
+    if (it < 120) {
+      const uint32_t e = g_dog_splits7[it];
+      const int d[4] = {(int)(e & 7u), (int)((e >> 3) & 7u), (int)((e >> 6) & 7u), (int)((e >> 9) & 7u)};
+      if (dg4_val_7(R, v, d)) dog4_set_pair(s, 224 + it, joker, hand[7] > 0);
+    }
+  } else if (sub < 6) {  // normal moves: pin x {1..6, 8..13}; then the -4 move of each pin
+    const int it = 32 * (sub - 4) + lane;
+    if (it < 48) {
+      const int i = (it * 43) >> 9, k = it - 12 * i;
+      int move = k + 1;
+      move += (move >= 7);
+      const int cid = (k == 0) ? 11 : move;  // move 1 is the low face of card 11 (dog.py:660-670)
+      const bool card = hand[cid] > 0;
+      if ((joker || card) && dg4_val_normal(R, v, i, move)) dog4_set_pair(s, 344 + it, joker, card);
+    } else if (it < 52) {
+      const int i = it - 48;
+      if ((joker || hand[4] > 0) && dg4_val_neg(R, v, i, -4)) dog4_set_pair(s, 392 + i, joker, hand[4] > 0);
+    }
+  } else {  // swaps: pin_ok x cell_ok
+    uint32_t pin_ok;
+    uint64_t cell_ok;
+    dg4_val_swap(R, v, pin_ok, cell_ok);
+    const bool card = hand[1] > 0;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int c = lane + 32 * r;
+      if (c < 40 && ((cell_ok >> c) & 1ull)) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if ((pin_ok >> i) & 1u) dog4_set_pair(s, 56 * i + c, joker, card);
+      }
+    }
+  }
+}
+
 // env_step (dog.py:1117-1131) for a canonical record: the swap phase and the deal are the generic code (they do not
 // touch the board), the play phase runs on the bitboards; the board bytes are rebuilt from the pins afterwards.
 // All lanes call; lane 0 applies the move, all lanes deal if needed.

@@ -395,8 +395,14 @@ __global__ void __launch_bounds__(kSyncWarps * 32, 1) k_dog_play_random(const __
                                                                       unsigned int* __restrict__ queue) {
   extern __shared__ __align__(16) unsigned char dog_smem_raw[];
   DogS* sh = reinterpret_cast<DogS*>(dog_smem_raw);
+  // hot-seven task queues, double-buffered by turn parity: [head, tail, 128 x (slot * 4 + chunk)]
+  int* s_q = reinterpret_cast<int*>(dog_smem_raw + sizeof(DogS) * kSyncWarps);
+  const Dog4Rules R4 = dg4_rules(g.rules);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   DogS& s = sh[warp];
+  int turn = 0;
+  if (threadIdx.x < 4) s_q[(threadIdx.x >> 1) * 130 + (threadIdx.x & 1)] = 0;
+  __syncthreads();
   const int64_t stride = (int64_t)gridDim.x * kSyncWarps;
   int64_t i = (int64_t)blockIdx.x * kSyncWarps + warp;
   bool have = false;
@@ -419,8 +425,43 @@ __global__ void __launch_bounds__(kSyncWarps * 32, 1) k_dog_play_random(const __
         rng = Key2{__shfl_sync(0xFFFFFFFFu, both.a, 0), __shfl_sync(0xFFFFFFFFu, both.b, 0)};
       }
     }
+    // phase A, legal masks.  A hand with a seven or a joker needs the 120 hot-seven splits on top of the moves every hand has
+    // (11 k cycles for the slowest warp of a turn against a mean of 4.7 k): its four 32-split chunks go to a CTA queue and
+    // are taken by whichever warp has finished its own mask.
+    int* q = s_q + (turn & 1) * 130;
+    int flags = 0;
+    bool shared_mask = false;
+    if (have) {
+      shared_mask = s.phase == 0 && s.scratch[7] != 0;
+      if (shared_mask) {
+        for (int w = lane; w < kDogMaskWords; w += 32) s.mask[w] = 0u;
+        flags = dog4_mask_flags(R4, s);
+        if (lane == 0 && (flags & 2)) {
+          const int pos = atomicAdd(&q[1], 4);
+          for (int k = 0; k < 4; ++k) q[2 + pos + k] = warp * 4 + k;
+        }
+      }
+    }
     if (!__syncthreads_or(have)) break;
-    if (have) dog_build_mask_any(g, s, lane);                       // phase A
+    if (threadIdx.x == 0) { int* qn = s_q + ((turn + 1) & 1) * 130; qn[0] = 0; qn[1] = 0; }  // next turn's queue (see parity note)
+    if (have) {
+      if (shared_mask) {
+        dog4_mask_task(R4, s, 4, lane);
+        dog4_mask_task(R4, s, 5, lane);
+        if (flags & 1) dog4_mask_task(R4, s, 6, lane);
+      } else {
+        dog_build_mask_any(g, s, lane);  // swap phase (14 card bits) or a non-canonical record: the owner alone
+      }
+    }
+    for (;;) {
+      int t = 0;
+      if (lane == 0) t = atomicAdd(&q[0], 1);
+      t = __shfl_sync(0xFFFFFFFFu, t, 0);
+      if (t >= *(volatile int*)&q[1]) break;
+      const int task = q[2 + t];
+      dog4_mask_task(R4, sh[task >> 2], task & 3, lane);
+    }
+    ++turn;
     __syncthreads();
     int a = -1;
     if (have) a = dog_categorical_pipelined(g, s, lane, key, rng, (uint32_t)(game_offset + i + 1));  // phase B
@@ -542,7 +583,7 @@ int dogstep_dog_play_random(const dogstep_dog_state* s, int64_t n, const dogstep
   if (sms <= 0) sms = 148;
   const int64_t ctas_needed = (n + kSyncWarps - 1) / kSyncWarps;
   const unsigned grid = (unsigned)(ctas_needed < sms ? ctas_needed : sms);  // one persistent CTA per SM
-  const size_t smem = sizeof(DogS) * kSyncWarps;
+  const size_t smem = sizeof(DogS) * kSyncWarps + 2 * 130 * sizeof(int);
   cudaFuncSetAttribute(k_dog_play_random, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   // per-launch game queue: a rotating pool of counters so that launches in flight on different streams do not share one
   static unsigned int* pools[64] = {};  // one pool per device ordinal
