@@ -632,6 +632,110 @@ __device__ __noinline__ void dog_distribute_cards(const DogGeom& g, DogS& s, int
   __syncwarp();
 }
 
+// distribute_cards in three parts for the persistent play kernel, which shares the 120 Threefry draws of a deal among the
+// warps of its CTA: begin (owner: deck reset, key split), draw (ANY warp: 32 pool slots per call), finish (owner: selection
+// of the first n * hand_size cards, dealing, round bookkeeping).  Same arithmetic as dog_distribute_cards above.  The
+// slot keys / card types travel through the record's item list (unused while a game deals): bytes 64.. of s.items.
+__device__ __forceinline__ uint32_t* dog_deal_keys(DogS& s) { return reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(s.items) + 64); }
+__device__ __forceinline__ uint8_t* dog_deal_types(DogS& s) { return reinterpret_cast<unsigned char*>(s.items) + 64 + 512; }
+
+__device__ __forceinline__ void dog_deal_begin(const DogGeom& g, DogS& s, int lane) {
+  const int n = g.n, quantity = s.hand_size;
+  __syncwarp();
+  if (lane == 0) {
+    int deck_sum = 0;
+    for (int k = 0; k < kNCard; ++k) deck_sum += s.deck[k];
+    if (deck_sum < (int)(int8_t)(quantity * n)) {  // reset_deck (:183-186) with the joker enabled
+      for (int k = 0; k < kNCard; ++k) s.deck[k] = 8;
+    }
+  }
+  __syncwarp();
+  const Key2 key{s.key[0], s.key[1]};
+  const Key2 both = split_i(key, (uint32_t)(lane & 1));  // key, sub = split(env.key)
+  int deck_total = 0;
+  for (int k = 0; k < kNCard; ++k) deck_total += s.deck[k];
+  if (lane < 2) {
+    s.scratch[1 + 2 * lane] = (int)both.a;  // [1],[2] = new key, [3],[4] = sub
+    s.scratch[2 + 2 * lane] = (int)both.b;
+  }
+  if (lane == 0) s.scratch[5] = deck_total;
+  __syncwarp();
+}
+
+__device__ __forceinline__ void dog_deal_draw(DogS& s, int r, int lane) {
+  const int j = lane + 32 * r, deck_total = s.scratch[5];
+  const Key2 sub{(uint32_t)s.scratch[3], (uint32_t)s.scratch[4]};
+  uint32_t k = 0xFFFFFFFFu;
+  int c = 0;
+  if (j < 120 && j < deck_total) {
+    k = ((bits_i(sub, (uint32_t)j) >> 9) << 7) | (uint32_t)j;
+    int acc = s.deck[0];
+    while (j >= acc) { ++c; acc += s.deck[c]; }
+  }
+  dog_deal_keys(s)[j] = k;
+  dog_deal_types(s)[j] = (uint8_t)c;
+}
+
+__device__ __forceinline__ void dog_deal_finish(const DogGeom& g, DogS& s, int lane) {
+  const int n = g.n, quantity = s.hand_size, deck_total = s.scratch[5];
+  __syncwarp();
+  uint32_t sk[4];
+  int ct[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    sk[r] = dog_deal_keys(s)[lane + 32 * r];
+    ct[r] = dog_deal_types(s)[lane + 32 * r];
+  }
+  const int need = n * quantity;
+  for (int rank = 0; rank < need; ++rank) {
+    const uint32_t mine = min(min(sk[0], sk[1]), min(sk[2], sk[3]));
+    const uint32_t m = __reduce_min_sync(0xFFFFFFFFu, mine);
+    if (m == 0xFFFFFFFFu) break;  // fewer real cards than seats x hand size
+    if (mine == m) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        if (sk[r] == m) {
+          if (rank < 32) s.items[rank] = (uint16_t)ct[r];
+          sk[r] = 0xFFFFFFFFu;
+        }
+    }
+  }
+  __syncwarp();
+  {
+    const int q6 = quantity < 6 ? quantity : 6;
+    for (int pc = lane; pc < n * kNCard; pc += 32) {
+      const int p = pc / kNCard, c = pc - p * kNCard;
+      int cnt = 0;
+      for (int slot = 0; slot < q6; ++slot) {
+        const int idx = p * quantity + slot;
+        cnt += (idx < deck_total && (int)s.items[idx] == c) ? 1 : 0;
+      }
+      if (cnt) s.hands[p][c] = (int8_t)(s.hands[p][c] + cnt);
+    }
+    if (lane < kNCard) {
+      int cnt = 0;
+      for (int p = 0; p < n; ++p)
+        for (int slot = 0; slot < q6; ++slot) {
+          const int idx = p * quantity + slot;
+          cnt += (idx < deck_total && (int)s.items[idx] == lane) ? 1 : 0;
+        }
+      if (cnt) s.deck[lane] = (int8_t)(s.deck[lane] - cnt);
+    }
+  }
+  __syncwarp();
+  if (lane == 0) {
+    int rs = (s.round_starter == -1) ? s.cur : d_fmod(s.round_starter + 1, n);
+    s.cur = rs;
+    s.round_starter = rs;
+    for (int q = 0; q < 4; ++q) s.swap_choices[q] = -1;
+    s.phase = (DG_RULE(g, DOGSTEP_RULE_TEAMS) && n == 4) ? 1 : 0;
+    s.key[0] = (uint32_t)s.scratch[1];
+    s.key[1] = (uint32_t)s.scratch[2];
+    s.hand_size = (quantity == 2) ? 6 : quantity - 1;
+  }
+  __syncwarp();
+}
+
 // env_step_swap_phase (dog.py:1078-1114) on the staged record: scalar, no board access
 DS_FN void dog_swap_phase(const DogGeom& g, DogS& s, int action) {
   int card_idx = action - g.play_actions;
@@ -702,7 +806,7 @@ __device__ __noinline__ void dog_env_step(const DogGeom& g, DogS& s, int lane, i
     s.scratch[2] = done;
   }
   __syncwarp();
-  if (s.scratch[0]) dog_distribute_cards(g, s, lane);
+  if (s.scratch[0] && !s.scratch[6]) dog_distribute_cards(g, s, lane);  // scratch[6]: the caller deals (k_dog_play_random)
   reward_out = s.scratch[1];
   done_out = s.scratch[2];
   __syncwarp();
@@ -722,7 +826,7 @@ __device__ __noinline__ void dog_no_step(const DogGeom& g, DogS& s, int lane) {
     s.scratch[0] = !cont;
   }
   __syncwarp();
-  if (s.scratch[0]) dog_distribute_cards(g, s, lane);
+  if (s.scratch[0] && !s.scratch[6]) dog_distribute_cards(g, s, lane);  // scratch[6]: the caller deals (k_dog_play_random)
   __syncwarp();
 }
 

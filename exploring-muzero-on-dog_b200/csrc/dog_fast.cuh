@@ -744,7 +744,7 @@ __device__ __forceinline__ void dog4_env_step(const Dog4Rules& R, const DogGeom&
     return;
   }
   dog4_rebuild_board_warp(s, lane);
-  if (s.scratch[0]) dog_distribute_cards(g, s, lane);
+  if (s.scratch[0] && !s.scratch[6]) dog_distribute_cards(g, s, lane);  // scratch[6]: the caller deals (k_dog_play_random)
   reward_out = s.scratch[1];
   done_out = s.scratch[2];
   __syncwarp();

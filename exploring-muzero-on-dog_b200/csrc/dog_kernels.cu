@@ -52,7 +52,7 @@ __device__ __forceinline__ void dog_load(const DogGeom& g, const DogPtrs& p, int
   __syncwarp();
   // canonical 4-player / distance-10 records take the bitboard rules of dog_fast.cuh (warp-uniform flag)
   const bool fast = g.n == 4 && g.d == 10 && dog4_canonical_warp(s, lane);
-  if (lane == 0) s.scratch[7] = fast;
+  if (lane == 0) { s.scratch[7] = fast; s.scratch[6] = 0; }
   __syncwarp();
 }
 
@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(kSyncWarps * 32, 1) k_dog_play_random(const __
   __syncthreads();
   const int64_t stride = (int64_t)gridDim.x * kSyncWarps;
   int64_t i = (int64_t)blockIdx.x * kSyncWarps + warp;
-  bool have = false;
+  bool have = false, dealing = false;  // dealing: the game sits this turn out and is dealt (see below)
   int len = 0;
   unsigned long long steps = 0;
   Key2 rng = rng0, key = rng0;  // rng: loop key of the NEXT turn, key: step key of this turn (see dog_categorical_pipelined)
@@ -431,7 +431,17 @@ __global__ void __launch_bounds__(kSyncWarps * 32, 1) k_dog_play_random(const __
     int* q = s_q + (turn & 1) * 130;
     int flags = 0;
     bool shared_mask = false;
-    if (have) {
+    if (have && dealing) {
+      // The previous transition ended a round.  A deal is 120 Threefry draws plus a 24-step selection — 11 k cycles against
+      // 5 k for a plain transition, and with 26 live games one of them deals in four turns out of five — so it is not done
+      // inline: the game sits THIS turn out, its four 32-slot draw passes go to the task queue next to the hot-seven
+      // chunks, and its owner selects and deals while the other games draw and move.
+      dog_deal_begin(g, s, lane);
+      if (lane == 0) {
+        const int pos = atomicAdd(&q[1], 4);
+        for (int k = 0; k < 4; ++k) q[2 + pos + k] = 0x100 | (warp * 4 + k);
+      }
+    } else if (have) {
       shared_mask = s.phase == 0 && s.scratch[7] != 0;
       if (shared_mask) {
         for (int w = lane; w < kDogMaskWords; w += 32) s.mask[w] = 0u;
@@ -444,7 +454,7 @@ __global__ void __launch_bounds__(kSyncWarps * 32, 1) k_dog_play_random(const __
     }
     if (!__syncthreads_or(have)) break;
     if (threadIdx.x == 0) { int* qn = s_q + ((turn + 1) & 1) * 130; qn[0] = 0; qn[1] = 0; }  // next turn's queue (see parity note)
-    if (have) {
+    if (have && !dealing) {
       if (shared_mask) {
         dog4_mask_task(R4, s, 4, lane);
         dog4_mask_task(R4, s, 5, lane);
@@ -459,13 +469,18 @@ __global__ void __launch_bounds__(kSyncWarps * 32, 1) k_dog_play_random(const __
       t = __shfl_sync(0xFFFFFFFFu, t, 0);
       if (t >= *(volatile int*)&q[1]) break;
       const int task = q[2 + t];
-      dog4_mask_task(R4, sh[task >> 2], task & 3, lane);
+      if (task & 0x100) dog_deal_draw(sh[(task & 0xFF) >> 2], task & 3, lane);
+      else dog4_mask_task(R4, sh[task >> 2], task & 3, lane);
     }
     ++turn;
     __syncthreads();
-    int a = -1;
-    if (have) a = dog_categorical_pipelined(g, s, lane, key, rng, (uint32_t)(game_offset + i + 1));  // phase B
-    if (have) {                                                     // phase C
+    if (have && dealing) {                                          // the draws are in the record: select, deal, next round
+      dog_deal_finish(g, s, lane);
+      dealing = false;
+    } else if (have) {
+      const int a = dog_categorical_pipelined(g, s, lane, key, rng, (uint32_t)(game_offset + i + 1));  // phase B
+      if (lane == 0) s.scratch[6] = 1;                              // phase C: transition, a deal that falls due is held back
+      __syncwarp();
       if (a >= 0) {
         int r, d;
         dog_env_step_any(g, s, lane, a, r, d);
@@ -475,12 +490,20 @@ __global__ void __launch_bounds__(kSyncWarps * 32, 1) k_dog_play_random(const __
       ++len;
       ++steps;
       __syncwarp();
-      if (s.done || len >= max_steps) {
+      const bool need_deal = s.scratch[0] != 0;
+      const bool finished = s.done || len >= max_steps;
+      __syncwarp();
+      if (lane == 0) s.scratch[6] = 0;
+      __syncwarp();
+      if (finished) {
+        if (need_deal) dog_distribute_cards(g, s, lane);            // the state written back is the reference's: dealt
         dog_store(g, p, i, s, lane);
         if (lane == 0 && game_len) game_len[i] = len;
         __syncwarp();
         have = false;
         i = dog_next_game(queue, stride, lane);
+      } else {
+        dealing = need_deal;
       }
     }
   }
