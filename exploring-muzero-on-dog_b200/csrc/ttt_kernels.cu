@@ -84,28 +84,39 @@ __device__ void ttt_policy(int variant, const Ttt& e, float logits[9]) {
 // variant run for > 100 plies).
 __device__ float ttt_rollout_group(int variant, const Ttt& e0, Key2 key, int sub, uint32_t gmask) {
   Ttt e = e0;
+  // key chain of the rollout: key_{t+1}, sub_t = split(key_t).  The group keeps sub_t and key_{t+1}; every iteration is ONE
+  // Threefry pass over the lanes: lanes 0..8 draw their action's uniform from sub_t, lane 9 derives key_{t+2} and lane 10
+  // sub_{t+1} from key_{t+1} (three dependent Threefry calls per ply otherwise).
+  const int base = (threadIdx.x & 31) & 16;  // first lane of this group inside the warp
+  Key2 sk = split_i(key, 1), kn = split_i(key, 0);
   for (int it = 0; it < 100000 && !e.done; ++it) {
-    const Key2 nk = split_i(key, 0), sk = split_i(key, 1);
-    key = nk;
+    const Key2 k = sub < 9 ? sk : kn;
+    const uint32_t ctr = sub < 9 ? (uint32_t)sub : (sub == 10 ? 1u : 0u);
+    const Key2 o = threefry2x32(k, 0u, ctr);
+    const Key2 kn2{__shfl_sync(gmask, o.a, base + 9), __shfl_sync(gmask, o.b, base + 9)};
+    const Key2 sk1{__shfl_sync(gmask, o.a, base + 10), __shfl_sync(gmask, o.b, base + 10)};
     float v = 0.0f;
     int a = sub;
     if (sub < 9) {
       const float lg = ttt_policy_a(variant, e, sub);
-      const float u = uniform_i(sk, (uint32_t)sub, 1.17549435e-38f, 1.0f);
+      const float f = bits_to_unit_float(o.a ^ o.b);  // uniform(sub_t, minval = tiny, maxval = 1)[sub], as uniform_i
+      const float u = fmaxf(1.17549435e-38f, __fadd_rn(__fmul_rn(f, __fsub_rn(1.0f, 1.17549435e-38f)), 1.17549435e-38f));
       v = __fadd_rn(-t_log(-t_log(u)), lg);
     } else {
       a = 0x7FFF;  // never wins: handled by the validity flag below
     }
     bool has = sub < 9;
 #pragma unroll
-    for (int o = 8; o; o >>= 1) {
-      const float ov = __shfl_xor_sync(gmask, v, o);
-      const int oa = __shfl_xor_sync(gmask, a, o);
-      const bool oh = __shfl_xor_sync(gmask, (int)has, o) != 0;
+    for (int o2 = 8; o2; o2 >>= 1) {
+      const float ov = __shfl_xor_sync(gmask, v, o2);
+      const int oa = __shfl_xor_sync(gmask, a, o2);
+      const bool oh = __shfl_xor_sync(gmask, (int)has, o2) != 0;
       const bool take = oh && (!has || ov > v || (ov == v && oa < a));
       if (take) { v = ov; a = oa; has = true; }
     }
     ttt_step(variant, e, a);
+    sk = sk1;
+    kn = kn2;
   }
   return (float)(int8_t)(e.reward * e.cur * e0.cur);
 }
