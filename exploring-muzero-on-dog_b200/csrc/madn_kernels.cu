@@ -556,7 +556,8 @@ template <uint32_t CT>
 __global__ void __launch_bounds__(kPlayMaxThreads + 32) k_madn_det_play_cta(const __grid_constant__ MadnGeom g, MadnPtrs p, int64_t n,
                                                                       Key2 rng0, int64_t game_offset, int max_steps,
                                                                       int32_t* __restrict__ game_len,
-                                                                      unsigned long long* __restrict__ total_steps, int round_len) {
+                                                                      unsigned long long* __restrict__ total_steps, int round_len,
+                                                                      int games_per_cta) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int T = blockDim.x - 32, W = T >> 5;  // game threads / warps; the CTA's last warp produces the key chain
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -569,7 +570,7 @@ __global__ void __launch_bounds__(kPlayMaxThreads + 32) k_madn_det_play_cta(cons
   uint32_t* s_cnt = s_x + (size_t)kXWords * T;                                                  // 2 x [34] counts
   uint2* s_ring = reinterpret_cast<uint2*>(s_cnt + 2 * 34);                                     // 2 x [kRingMax + 2] keys
   const uint32_t FULL = 0xFFFFFFFFu;
-  const int64_t cta_base = (int64_t)blockIdx.x * T;
+  const int64_t cta_base = (int64_t)blockIdx.x * games_per_cta;  // games_per_cta <= T: the games are spread over ALL SMs
   int gi = threadIdx.x;  // game held by this lane, relative to cta_base
   const RuleSet<CT> R{g.rules};
   int len = 0;
@@ -587,7 +588,7 @@ __global__ void __launch_bounds__(kPlayMaxThreads + 32) k_madn_det_play_cta(cons
       r = split_i(r, 0u);
       if (lane == 0) s_ring[i] = make_uint2(r.a, r.b);
     }
-  } else if (cta_base + gi < n) {
+  } else if (gi < games_per_cta && cta_base + gi < n) {
     load_state<true>(g, p, cta_base + gi, s);
     canon = is_canonical4(s, s.occ);
     alive = !s.done;
@@ -1108,23 +1109,24 @@ int dogstep_madn_det_play_random(const dogstep_madn_det_state* s, int64_t n, con
   if (!host_rng_key || max_steps < 0) return DOGSTEP_ERR_INVALID_ARG;
   Key2 rng{host_rng_key[0], host_rng_key[1]};
   if (g.n == 4 && g.d == 10) {
-    // one CTA per SM when the games fit (config 2: 65,536 games -> 147 CTAs of 448), else CTAs of 512
+    // the games are spread evenly over the SMs (config 2: 65,536 games -> 148 CTAs of 443), at most 512 per CTA
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms <= 0) sms = 148;
     int64_t per = (n + sms - 1) / sms;
-    int threads = (int)(((per + 31) / 32) * 32);
-    if (threads > kPlayMaxThreads) threads = kPlayMaxThreads;
+    if (per > kPlayMaxThreads) per = kPlayMaxThreads;
+    const int gpc = (int)per;                          // games per CTA (config 2: 443 on each of the 148 SMs)
+    const int threads = ((gpc + 31) / 32) * 32;
     const size_t smem = play_smem_bytes(threads);
-    const unsigned blocks = blocks_for(n, threads);
+    const unsigned blocks = blocks_for(n, gpc);
     const int round_len = kPlayRound;  // <= kRingMax
     if (g.rules == kTrainRules) {
       cudaFuncSetAttribute(k_madn_det_play_cta<kTrainRules>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      k_madn_det_play_cta<kTrainRules><<<blocks, threads + 32, smem, st>>>(g, p, n, rng, game_offset, max_steps, game_len, total_steps, round_len);
+      k_madn_det_play_cta<kTrainRules><<<blocks, threads + 32, smem, st>>>(g, p, n, rng, game_offset, max_steps, game_len, total_steps, round_len, gpc);
     } else {
       cudaFuncSetAttribute(k_madn_det_play_cta<kRulesRuntime>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      k_madn_det_play_cta<kRulesRuntime><<<blocks, threads + 32, smem, st>>>(g, p, n, rng, game_offset, max_steps, game_len, total_steps, round_len);
+      k_madn_det_play_cta<kRulesRuntime><<<blocks, threads + 32, smem, st>>>(g, p, n, rng, game_offset, max_steps, game_len, total_steps, round_len, gpc);
     }
   } else {
     k_madn_det_play_random<<<blocks_for(n, kThreads), kThreads, 0, st>>>(g, p, n, rng, game_offset, max_steps, game_len,
