@@ -22,12 +22,28 @@ __host__ __device__ __forceinline__ uint32_t rotl32(uint32_t x, int r) {
 #endif
 }
 
-// Threefry-2x32, 20 rounds.  Fully unrolled: 20 x (IADD, SHF, LOP) + 5 key injections.
+// x0 + x1 of a Threefry round.  On the device it is written as  x1 * 1 + x0  with the 1 read from the constant bank, so that
+// ptxas keeps it an IMAD on the fma pipe: shift and xor of a round already fill the integer-alu pipe (half rate), which is what
+// bounds the play kernels.  Measured (scripts/microbench/threefry_variants.cu, V3): 349 -> 381 G Threefry/s at 16 warps per SM.
+#ifdef __CUDACC__
+static __constant__ uint32_t c_dogstep_one = 1u;
+#endif
+__host__ __device__ __forceinline__ uint32_t tf_add(uint32_t x0, uint32_t x1) {
+#ifdef __CUDA_ARCH__
+  uint32_t r;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(x1), "r"(c_dogstep_one), "r"(x0));
+  return r;
+#else
+  return x0 + x1;
+#endif
+}
+
+// Threefry-2x32, 20 rounds.  Fully unrolled: 20 x (IMAD, SHF, LOP) + 5 key injections.
 __host__ __device__ __forceinline__ Key2 threefry2x32(Key2 k, uint32_t c0, uint32_t c1) {
   const uint32_t ks0 = k.a, ks1 = k.b, ks2 = k.a ^ k.b ^ 0x1BD11BDAu;
   uint32_t x0 = c0 + ks0, x1 = c1 + ks1;
 #define DOGSTEP_TF_ROUND(r) \
-  x0 += x1;                 \
+  x0 = tf_add(x0, x1);      \
   x1 = rotl32(x1, r);       \
   x1 ^= x0;
   DOGSTEP_TF_ROUND(13) DOGSTEP_TF_ROUND(15) DOGSTEP_TF_ROUND(26) DOGSTEP_TF_ROUND(6)

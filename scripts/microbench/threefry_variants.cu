@@ -9,13 +9,20 @@
 #include <cstdio>
 #include <cuda_runtime.h>
 
-struct Mults { uint32_t m[8]; };  // 2^13, 2^15, 2^26, 2^6, 2^17, 2^29, 2^16, 2^24
+struct Mults { uint32_t m[8]; uint32_t one; };  // 2^13, 2^15, 2^26, 2^6, 2^17, 2^29, 2^16, 2^24; one = 1 (from the constant bank)
 
 __device__ __forceinline__ uint32_t rotx_shf(uint32_t x1, uint32_t x0, int r) { return __funnelshift_l(x1, x1, r) ^ x0; }
 __device__ __forceinline__ uint32_t rotx_mul(uint32_t x1, uint32_t x0, uint32_t mult) {
   uint32_t lo, hi;
   asm("{ .reg .u64 t; mul.wide.u32 t, %2, %3; mov.b64 {%0, %1}, t; }" : "=r"(lo), "=r"(hi) : "r"(x1), "r"(mult));
   return lo ^ hi ^ x0;
+}
+
+// V3: x0 += x1 as  mad.lo.u32 x0 = x1 * 1 + x0  with the 1 read from the constant bank (fma pipe) — the adds are a third of a round
+__device__ __forceinline__ uint32_t add_mad(uint32_t a, uint32_t b, uint32_t one) {
+  uint32_t r;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(b), "r"(one), "r"(a));
+  return r;
 }
 
 template <int V>
@@ -28,8 +35,8 @@ __device__ __forceinline__ uint2 threefry(uint32_t k0, uint32_t k1, uint32_t c0,
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int ri = (g & 1) * 4 + j;
-      x0 += x1;
-      const bool mul = (V == 1) || (V == 2 && (j & 1));
+      x0 = (V == 3) ? add_mad(x0, x1, M.one) : x0 + x1;
+      const bool mul = (V == 1) || (V == 2 && (j & 1));  // V3 keeps the shf rotate
       x1 = mul ? rotx_mul(x1, x0, M.m[ri]) : rotx_shf(x1, x0, R[ri]);
     }
     const uint32_t ka = (g % 3 == 0) ? ks1 : (g % 3 == 1) ? ks2 : ks0;
@@ -58,7 +65,7 @@ __global__ void __launch_bounds__(256) k(const __grid_constant__ Mults M, uint32
 
 template <int V, int ILP>
 void run(const char* name, int blocks_per_sm) {
-  Mults M{{1u << 13, 1u << 15, 1u << 26, 1u << 6, 1u << 17, 1u << 29, 1u << 16, 1u << 24}};
+  Mults M{{1u << 13, 1u << 15, 1u << 26, 1u << 6, 1u << 17, 1u << 29, 1u << 16, 1u << 24}, 1u};
   int sms = 148, iters = 2000, blocks = sms * blocks_per_sm;
   uint32_t* out;
   cudaMalloc(&out, (size_t)blocks * 256 * 4);
@@ -82,6 +89,7 @@ int main() {
     run<0, 1>("V0 shf", bps); run<1, 1>("V1 mul.wide", bps); run<2, 1>("V2 alternate", bps);
     run<0, 2>("V0 shf", bps); run<1, 2>("V1 mul.wide", bps); run<2, 2>("V2 alternate", bps);
     run<0, 4>("V0 shf", bps); run<2, 4>("V2 alternate", bps);
+    run<3, 1>("V3 add via mad", bps); run<3, 2>("V3 add via mad", bps); run<3, 4>("V3 add via mad", bps);
   }
   return 0;
 }
