@@ -47,15 +47,15 @@ __host__ __device__ __forceinline__ Key2 threefry2x32(Key2 k, uint32_t c0, uint3
   x1 = rotl32(x1, r);       \
   x1 ^= x0;
   DOGSTEP_TF_ROUND(13) DOGSTEP_TF_ROUND(15) DOGSTEP_TF_ROUND(26) DOGSTEP_TF_ROUND(6)
-  x0 += ks1; x1 += ks2 + 1u;
+  x0 = tf_add(x0, ks1); x1 = tf_add(x1, ks2 + 1u);
   DOGSTEP_TF_ROUND(17) DOGSTEP_TF_ROUND(29) DOGSTEP_TF_ROUND(16) DOGSTEP_TF_ROUND(24)
-  x0 += ks2; x1 += ks0 + 2u;
+  x0 = tf_add(x0, ks2); x1 = tf_add(x1, ks0 + 2u);
   DOGSTEP_TF_ROUND(13) DOGSTEP_TF_ROUND(15) DOGSTEP_TF_ROUND(26) DOGSTEP_TF_ROUND(6)
-  x0 += ks0; x1 += ks1 + 3u;
+  x0 = tf_add(x0, ks0); x1 = tf_add(x1, ks1 + 3u);
   DOGSTEP_TF_ROUND(17) DOGSTEP_TF_ROUND(29) DOGSTEP_TF_ROUND(16) DOGSTEP_TF_ROUND(24)
-  x0 += ks1; x1 += ks2 + 4u;
+  x0 = tf_add(x0, ks1); x1 = tf_add(x1, ks2 + 4u);
   DOGSTEP_TF_ROUND(13) DOGSTEP_TF_ROUND(15) DOGSTEP_TF_ROUND(26) DOGSTEP_TF_ROUND(6)
-  x0 += ks2; x1 += ks0 + 5u;
+  x0 = tf_add(x0, ks2); x1 = tf_add(x1, ks0 + 5u);
 #undef DOGSTEP_TF_ROUND
   return Key2{x0, x1};
 }
