@@ -35,8 +35,8 @@ __device__ __forceinline__ uint2 threefry(uint32_t k0, uint32_t k1, uint32_t c0,
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int ri = (g & 1) * 4 + j;
-      x0 = (V == 3) ? add_mad(x0, x1, M.one) : x0 + x1;
-      const bool mul = (V == 1) || (V == 2 && (j & 1));  // V3 keeps the shf rotate
+      x0 = (V >= 3) ? add_mad(x0, x1, M.one) : x0 + x1;
+      const bool mul = (V == 1) || (V == 4) || ((V == 2 || V == 5) && (j & 1)) || (V == 6 && j == 3);  // V3 keeps the shf rotate; V4/V5/V6 = V3 + mul rotates (all / every second / every fourth round)
       x1 = mul ? rotx_mul(x1, x0, M.m[ri]) : rotx_shf(x1, x0, R[ri]);
     }
     const uint32_t ka = (g % 3 == 0) ? ks1 : (g % 3 == 1) ? ks2 : ks0;
@@ -90,6 +90,8 @@ int main() {
     run<0, 2>("V0 shf", bps); run<1, 2>("V1 mul.wide", bps); run<2, 2>("V2 alternate", bps);
     run<0, 4>("V0 shf", bps); run<2, 4>("V2 alternate", bps);
     run<3, 1>("V3 add via mad", bps); run<3, 2>("V3 add via mad", bps); run<3, 4>("V3 add via mad", bps);
+    run<4, 2>("V4 mad + mul all", bps); run<5, 2>("V5 mad + mul alternate", bps); run<6, 2>("V6 mad + mul every 4th", bps);
+    run<5, 4>("V5 mad + mul alternate", bps); run<6, 4>("V6 mad + mul every 4th", bps);
   }
   return 0;
 }
