@@ -395,7 +395,52 @@ __device__ int madn_rule_based_action(const MadnGeom& g, const MadnRegs& s, uint
   return best_a;
 }
 
-__global__ void __launch_bounds__(kThreads) k_madn_det_eval_step(const __grid_constant__ MadnGeom g, MadnPtrs p, int64_t n,
+// do_rule_based of the dice game (MuZero_Classic_MADN/evaluate_agent_stochastic.py:782-872): four actions (the pin to move by
+// env.die), scores = goal bonus 5 + leaving-home bonus 3 / 2 + hit bonus 2.5, categorical over score / 0.25
+__device__ int madn_cls_rule_based_action(const MadnGeom& g, const MadnRegs& s, uint32_t m, Key2 key) {
+  const int cur = s.cur;
+  const uint32_t pw = pick4(s.pins, cur);
+  const int start = g.start[cur], target = g.target[cur], goal0 = g.goal0[cur];
+  const int mts = DS_RULE(g, DOGSTEP_RULE_MUST_TRAVERSE_START) ? 1 : 0;
+  const int mate = DS_RULE(g, DOGSTEP_RULE_TEAMS) ? ((cur + 2) & 3) : -1;
+  int pins_in_home = 0;
+#pragma unroll
+  for (int p = 0; p < 4; ++p) pins_in_home += byte_s(pw, p) < 0;
+  const float out_w = pins_in_home >= 2 ? 3.0f : 2.0f;
+  float best = 0.0f;
+  int best_a = -1;
+#pragma unroll 1
+  for (int a = 0; a < 4; ++a) {
+    const int cur_pos = byte_s(pw, a);
+    const int moved = cur_pos + s.die, fitted = floormod(moved, g.bs);
+    const int x = moved - target - mts;
+    int new_pos = fitted;
+    if (x <= 4 && x > 0 && cur_pos <= target) new_pos = goal0 + x - 1;
+    if (cur_pos >= g.bs) new_pos = moved;
+    if (cur_pos < 0) new_pos = start;
+    const bool into_goal = (unsigned)(new_pos - goal0) <= 3u && cur_pos < g.bs;
+    const bool leaves_home = cur_pos < 0 && new_pos == start;
+    bool hits = false;
+    for (int q = 0; q < g.n; ++q) {
+      if (q == cur || q == mate) continue;
+      const uint32_t ow = pick4(s.pins, q);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) hits = hits || byte_s(ow, j) == new_pos;
+    }
+    hits = hits && new_pos != cur_pos;
+    float score = __fadd_rn(0.0f, into_goal ? 5.0f : 0.0f);
+    score = __fadd_rn(score, leaves_home ? out_w : 0.0f);
+    score = __fadd_rn(score, hits ? 2.5f : 0.0f);
+    const float logit = ((m >> a) & 1u) ? __fdiv_rn(score, 0.25f) : __int_as_float(0xFF800000);
+    const float u = uniform_i(key, (uint32_t)a, 1.17549435e-38f, 1.0f);
+    const float v = __fadd_rn(-eval_log_f(-eval_log_f(u)), logit);
+    if (best_a < 0 || v > best) { best = v; best_a = a; }
+  }
+  return best_a;
+}
+
+template <bool DET>
+__global__ void __launch_bounds__(kThreads) k_madn_eval_step(const __grid_constant__ MadnGeom g, MadnPtrs p, int64_t n,
                                                                  int4 agent_type, const int32_t* __restrict__ search_action,
                                                                  Key2 rng, int64_t game_offset, int32_t* __restrict__ winners,
                                                                  unsigned long long* __restrict__ active_count) {
@@ -403,21 +448,31 @@ __global__ void __launch_bounds__(kThreads) k_madn_det_eval_step(const __grid_co
   int active = 0;
   if (i < n && p.done[i] == 0) {
     MadnRegs s;
-    load_state<true>(g, p, i, s);
+    load_state<DET>(g, p, i, s);
     const Key2 key = split_i(rng, (uint32_t)(game_offset + i + 1));  // rng_key, *step_keys = split(rng_key, num_envs + 1)
-    const uint32_t m = madn_det_valid_mask(g, s);
+    const uint32_t m = DET ? madn_det_valid_mask(g, s) : madn_cls_valid_mask(g, s);
     if (m) {
       const int cur = s.cur;
       const int type = cur == 0 ? agent_type.x : cur == 1 ? agent_type.y : cur == 2 ? agent_type.z : agent_type.w;
       int a;
       if (type == 3) a = categorical_masked(key, m);
-      else if (type == 2) a = madn_rule_based_action(g, s, m, key);
+      else if (type == 2) a = DET ? madn_rule_based_action(g, s, m, key) : madn_cls_rule_based_action(g, s, m, key);
       else a = search_action[i];
-      madn_det_step(g, s, a / 6, a % 6 + 1, m);  // map_action
+      if (DET) madn_det_step(g, s, a / 6, a % 6 + 1, m);  // map_action
+      else madn_cls_step(g, s, a, m);
     } else {
-      madn_det_no_step(g, s);
+      if (DET) madn_det_no_step(g, s);
+      else s.cur = (int)(int8_t)floormod(s.cur + 1, g.n);  // no_step of the dice game (classic_madn.py:353-365): the turn passes
     }
-    store_det_all(g, p, i, s);
+    if (DET) {
+      store_det_all(g, p, i, s);
+    } else {
+      store_board(g, p.board, i, s);
+      store_pins(g, p.pins, i, s);
+      p.cur[i] = (int8_t)s.cur;
+      p.reward[i] = (int8_t)s.reward;
+      p.done[i] = (uint8_t)s.done;
+    }
     if (s.done && winners) {  // manual_get_winner (:16-45) on the new board
       const uint64_t any = s.occ[0] | s.occ[1] | s.occ[2] | s.occ[3];
       int w[4];
@@ -1230,8 +1285,21 @@ int dogstep_madn_det_eval_step(const dogstep_madn_det_state* s, int64_t n, const
   for (int q = 0; q < g.n; ++q)
     if (agent_type[q] != 2 && agent_type[q] != 3 && !search_action) return DOGSTEP_ERR_INVALID_ARG;  // a search seat needs actions
   const int4 at = make_int4(agent_type[0], agent_type[1], agent_type[2], agent_type[3]);
-  k_madn_det_eval_step<<<blocks_for(n, kThreads), kThreads, 0, st>>>(g, p, n, at, search_action, Key2{host_rng_key[0], host_rng_key[1]},
-                                                                     game_offset, winners, active_count);
+  k_madn_eval_step<true><<<blocks_for(n, kThreads), kThreads, 0, st>>>(g, p, n, at, search_action, Key2{host_rng_key[0], host_rng_key[1]},
+                                                                       game_offset, winners, active_count);
+  return check_launch();
+}
+
+int dogstep_madn_cls_eval_step(const dogstep_madn_cls_state* s, int64_t n, const dogstep_madn_cfg* cfg, const int32_t* agent_type,
+                               const int32_t* search_action, const uint32_t* host_rng_key, int64_t game_offset, int32_t* winners,
+                               unsigned long long* active_count, void* stream) {
+  DS_PROLOGUE(cls_ptrs)
+  if (!agent_type || !host_rng_key) return DOGSTEP_ERR_INVALID_ARG;
+  for (int q = 0; q < g.n; ++q)
+    if (agent_type[q] != 2 && agent_type[q] != 3 && !search_action) return DOGSTEP_ERR_INVALID_ARG;
+  const int4 at = make_int4(agent_type[0], agent_type[1], agent_type[2], agent_type[3]);
+  k_madn_eval_step<false><<<blocks_for(n, kThreads), kThreads, 0, st>>>(g, p, n, at, search_action, Key2{host_rng_key[0], host_rng_key[1]},
+                                                                        game_offset, winners, active_count);
   return check_launch();
 }
 

@@ -1,4 +1,5 @@
-"""Evaluation loop: mirror of play_eval_loop_jitted / play_n_games_for_eval_jitted (MuZero_det_MADN/evaluate_agent.py:715-930).
+"""Evaluation loop: mirror of play_eval_loop_jitted / play_n_games_for_eval_jitted (MuZero_det_MADN/evaluate_agent.py:715-930)
+and of the dice game's twin (MuZero_Classic_MADN/evaluate_agent_stochastic.py:738-905; pass a classic_MADN env).
 
 Four seats, each played by an agent given as a params dict with a 'type' entry exactly as in the reference: 3 = random
 legal policy, 2 = the rule-based scorer (do_rule_based :780-878), anything else = MuZero tree search with that seat's
@@ -13,6 +14,7 @@ import numpy as np
 import torch
 
 from . import _lib, jaxrand
+from .MADN import classic_madn as cm
 from .MADN import deterministic_madn as dm
 
 RULES = dict(enable_teams=True, enable_initial_free_pin=True, enable_circular_board=False, enable_friendly_fire=False,
@@ -29,13 +31,17 @@ def agent_types(params_tuple):
     return out
 
 
-def eval_step(envs, types, rng_key, search_action=None, winners=None, game_offset=0, active_count=None):
-    """one lockstep iteration, in place"""
+def eval_step(envs, types, rng_key, search_action=None, winners=None, game_offset=0, active_count=None, throw=True):
+    """one lockstep iteration, in place (dice game: `throw` = roll the die of the live games first, as the reference's loop body does)"""
     cfg, st = envs.cfg(), envs.cstate()
     at = (C.c_int32 * 4)(*[int(t) for t in (list(types) + [3, 3, 3, 3])[:4]])
-    _lib.check(_lib.lib().dogstep_madn_det_eval_step(C.byref(st), C.c_int64(envs.n), C.byref(cfg), at, _lib.ptr(search_action),
-                                                    _lib.host_key(rng_key), C.c_int64(game_offset), _lib.ptr(winners),
-                                                    _lib.ptr(active_count), _lib.stream()), "madn_det_eval_step")
+    det = isinstance(envs, dm.deterministic_MADN)
+    if not det and throw:  # the dice game throws first (evaluate_agent_stochastic.py:757), live games only
+        _lib.check(_lib.lib().dogstep_madn_cls_throw_die_active(C.byref(st), C.c_int64(envs.n), C.byref(cfg), _lib.stream()),
+                   "throw_die_active")
+    fn = _lib.lib().dogstep_madn_det_eval_step if det else _lib.lib().dogstep_madn_cls_eval_step
+    _lib.check(fn(C.byref(st), C.c_int64(envs.n), C.byref(cfg), at, _lib.ptr(search_action), _lib.host_key(rng_key),
+                  C.c_int64(game_offset), _lib.ptr(winners), _lib.ptr(active_count), _lib.stream()), "madn_eval_step")
 
 
 def play_eval_loop(envs, params_tuple, rng_key, num_envs, search_fn=None, max_steps=2000, game_offset=0, poll_every=16):
@@ -54,12 +60,18 @@ def play_eval_loop(envs, params_tuple, rng_key, num_envs, search_fn=None, max_st
             break
         nxt = jaxrand.split_host(key)[0]  # rng_key, *step_keys = split(rng_key, num_envs + 1): element 0 does not depend on the count
         action = None
+        classic = not isinstance(envs, dm.deterministic_MADN)
+        if classic:  # throw_die comes before encode_board / valid_action / the search (evaluate_agent_stochastic.py:757-760)
+            cfg, st = envs.cfg(), envs.cstate()
+            _lib.check(_lib.lib().dogstep_madn_cls_throw_die_active(C.byref(st), C.c_int64(envs.n), C.byref(cfg), _lib.stream()),
+                       "throw_die_active")
         if needs_search:
+            mod = cm if classic else dm
             step_keys = jaxrand.split(key, num_envs + 1, device=dev)[1:].contiguous()
-            obs = dm.encode_board(envs)
-            valid = dm.valid_action(envs).reshape(num_envs, -1)
+            obs = mod.encode_board(envs)
+            valid = mod.valid_action(envs).reshape(num_envs, -1)
             action = search_fn(params_tuple, step_keys, obs, ~valid, envs.raw("current_player")).to(torch.int32).contiguous()
-        eval_step(envs, types, key, action, winners, game_offset)
+        eval_step(envs, types, key, action, winners, game_offset, throw=False)
         key = nxt
         step += 1
     return envs, winners

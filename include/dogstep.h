@@ -390,6 +390,11 @@ int dogstep_dog_agent_step(const dogstep_dog_state* s, int64_t n, const dogstep_
 int dogstep_madn_det_eval_step(const dogstep_madn_det_state* s, int64_t n, const dogstep_madn_cfg* cfg, const int32_t* agent_type,
                                const int32_t* search_action, const uint32_t* host_rng_key, int64_t game_offset, int32_t* winners,
                                unsigned long long* active_count, void* stream);
+/* The dice game's loop body (MuZero_Classic_MADN/evaluate_agent_stochastic.py:738-905) AFTER its throw_die (call
+ * dogstep_madn_cls_throw_die_active first): four actions = the pin to move by env.die; rule-based scorer :782-872. */
+int dogstep_madn_cls_eval_step(const dogstep_madn_cls_state* s, int64_t n, const dogstep_madn_cfg* cfg, const int32_t* agent_type,
+                               const int32_t* search_action, const uint32_t* host_rng_key, int64_t game_offset, int32_t* winners,
+                               unsigned long long* active_count, void* stream);
 
 /* ---------------------------------------------------------------- TicTacToe (BASELINE config 1)
  * Batched leaves of `TicTacToe` / `TicTacToeV2` (TicTacToe/TicTacToe.py:12-17, TicTacToeV2.py:14-20).

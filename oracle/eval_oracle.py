@@ -122,3 +122,85 @@ def play_eval_loop(state, agent_types, rng_key, search_fn=None, max_steps=2000):
                 winners[g] += manual_get_winner(cfg, geo, state.board[g]).astype(np.int32)
         step += 1
     return winners
+
+
+# --------------------------------------------------------------------------- the dice game
+def gumbel_n(key, n):
+    u = O.uniform(key, n, float(TINY), 1.0)
+    l1 = np.array([math.log(float(v)) for v in u], np.float64).astype(np.float32)
+    return -np.array([math.log(float(-v)) for v in l1], np.float64).astype(np.float32)
+
+
+def cls_rule_based_action(cfg, geometry, pins, current_player, die, valid_mask, key):
+    """do_rule_based of MuZero_Classic_MADN/evaluate_agent_stochastic.py:782-872 for one game.  pins int8 [P,4], valid bool [4]."""
+    start, target, goal = geometry
+    board_size = 4 * cfg.distance
+    cp = int(current_player)
+    current_positions = pins[cp].astype(np.int32)
+    current_goal = np.asarray(goal[cp])
+    moved_positions = current_positions + int(die)
+    fitted_positions = moved_positions % board_size
+    x = moved_positions - int(target[cp]) - int(_rule(cfg, RULE_MTS))
+    goal_pick = current_goal[np.clip(np.where(x - 1 < 0, x - 1 + 4, x - 1), 0, 3)]
+    new_positions = np.where(current_positions < 0, int(start[cp]),
+                             np.where(current_positions >= board_size, moved_positions,
+                                      np.where((4 >= x) & (x > 0) & (current_positions <= int(target[cp])), goal_pick, fitted_positions)))
+    opp = np.ones_like(pins, dtype=np.int32)
+    opp[cp] = 0
+    if _rule(cfg, RULE_TEAMS):
+        opp[(cp + 2) % 4] = 0
+    opponent_pins = np.where(opp == 1, pins, -1).flatten()
+    pins_in_home = int(np.sum(current_positions < 0))
+    base_score = np.zeros(4, np.float32)
+    goal_bonus = np.where(np.isin(new_positions, current_goal) & (current_positions < board_size), np.float32(5.0), np.float32(0.0))
+    out_bonus = np.where((current_positions < 0) & (new_positions == int(start[cp])), np.float32(3.0 if pins_in_home >= 2 else 2.0), np.float32(0.0))
+    hit_bonus = np.where((new_positions != current_positions) & np.isin(new_positions, opponent_pins), np.float32(2.5), np.float32(0.0))
+    scores = ((base_score + goal_bonus.astype(np.float32)).astype(np.float32) + out_bonus.astype(np.float32)).astype(np.float32)
+    scores = (scores + hit_bonus.astype(np.float32)).astype(np.float32)
+    scores = np.where(valid_mask, scores, np.float32(-np.inf)).astype(np.float32)
+    logits = (scores / np.float32(0.25)).astype(np.float32)
+    return int(np.argmax((gumbel_n(key, 4) + logits).astype(np.float32)))
+
+
+def play_eval_loop_classic(state, agent_types, rng_key, search_fn=None, max_steps=2000):
+    """play_eval_loop_jitted of MuZero_Classic_MADN/evaluate_agent_stochastic.py:738-905 on the C env oracle.
+    state: O.MadnState (det=False), stepped in place.  Returns winners int32 [n,4]."""
+    cfg, n = state.cfg, state.n
+    geo = cfg.geometry()
+    winners = np.zeros((n, 4), np.int32)
+    key = np.asarray(rng_key, np.uint32)
+    step = 0
+    while step < max_steps and not state.done.all():
+        keys = O.split(key, n + 1)
+        key, step_keys = keys[0], keys[1:]
+        live = state.done == 0
+        thrown = state.copy()                      # env = throw_die(env) inside do_step: live games only
+        O.madn_cls_throw_die(thrown)
+        state.die[live] = thrown.die[live]
+        state.key[live] = thrown.key[live]
+        valid = O.madn_cls_valid_action(state).reshape(n, 4)
+        action = np.zeros(n, np.int64)
+        searched = search_fn(step_keys, valid) if search_fn is not None else None
+        for g in range(n):
+            if not live[g] or not valid[g].any():
+                continue
+            t = agent_types[int(state.current_player[g])]
+            if t == 3:
+                action[g] = O.categorical_masked(step_keys[g], valid[g].astype(np.uint8))
+            elif t == 2:
+                action[g] = cls_rule_based_action(cfg, geo, state.pins[g], state.current_player[g], state.die[g], valid[g], step_keys[g])
+            else:
+                action[g] = int(searched[g])
+        stepped, skipped = state.copy(), state.copy()
+        O.madn_cls_step(stepped, action.astype(np.int8))
+        O.madn_cls_no_step(skipped)
+        for g in range(n):
+            if not live[g]:
+                continue
+            src = stepped if valid[g].any() else skipped
+            for f, v in src.fields().items():
+                getattr(state, f)[g] = v[g]
+            if state.done[g]:
+                winners[g] += manual_get_winner(cfg, geo, state.board[g]).astype(np.int32)
+        step += 1
+    return winners

@@ -97,3 +97,50 @@ def test_play_n_games_for_eval_shapes_and_seats():
     w = winners.cpu().numpy()
     assert w.shape == (256, 4) and bool(envs.raw("done").all()) and (w.sum(1) == 2).all()
     assert 0 < w[:, 0].sum() < 0.25 * 256   # the literal scorer is weak, see test_rule_based_team_against_random_team
+
+
+CLASSIC_RULES = dict(TRAIN_RULES, enable_dice_rethrow=True)
+
+
+def test_classic_rule_based_beats_random():
+    """the dice game's scorer (no off-by-one: it moves by env.die) does beat the random policy"""
+    from exploring_muzero_on_dog_b200 import jaxrand
+    n = 64
+    key = jaxrand.split_host(jaxrand.PRNGKey(8))[1]
+    seeds = O.randint(key, n, 0, 1_000_000)
+    s = O.madn_reset(O.MadnCfg(4, 0xF, 10, mask_of(CLASSIC_RULES)), seeds, 0, det=False)
+    s.current_player[:] = np.repeat(np.arange(4), n // 4)
+    winners = eval_oracle.play_eval_loop_classic(s, [2, 3, 2, 3], key)
+    assert s.done.all() and (winners.sum(1) == 2).all()
+    assert winners[:, 0].sum() > 0.6 * n
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("types", [(2, 3, 2, 3), (3, 3, 3, 3), (0, 2, 3, 0)])
+def test_cuda_classic_eval_loop_equals_oracle(types):
+    import torch
+    from exploring_muzero_on_dog_b200 import evaluate_agent as ea, jaxrand
+    from exploring_muzero_on_dog_b200.MADN import classic_madn as cm
+    n = 96
+    starting = np.repeat(np.arange(4), n // 4)
+    key = jaxrand.split_host(jaxrand.PRNGKey(50 + sum(types)))[1]
+    seeds = O.randint(key, n, 0, 1_000_000)
+    s = O.madn_reset(O.MadnCfg(4, 0xF, 10, mask_of(CLASSIC_RULES)), seeds, 0, det=False)
+    s.current_player[:] = starting
+
+    def host_search(step_keys, valid):
+        h = (step_keys[:, 0].astype(np.uint64) * 2654435761 + step_keys[:, 1]) % (2 ** 31)
+        score = ((h[:, None] + np.arange(4)[None, :] * 40503) % 1009).astype(np.float32)
+        score[~valid] = -1
+        return score.argmax(1).astype(np.int32)
+
+    def dev_search(params, step_keys, obs, invalid, current_player):
+        return torch.as_tensor(host_search(step_keys.cpu().numpy(), ~invalid.cpu().numpy()), device="cuda")
+
+    exp = eval_oracle.play_eval_loop_classic(s, list(types), key, search_fn=host_search)
+    envs = cm.env_reset(0, seed=seeds, **CLASSIC_RULES)
+    envs.raw("current_player").copy_(torch.as_tensor(starting, dtype=torch.int8, device="cuda"))
+    _, winners = ea.play_eval_loop(envs, tuple({"type": t} for t in types), key, n, search_fn=dev_search)
+    assert_state_equal(s, envs.numpy())
+    assert np.array_equal(winners.cpu().numpy(), exp)
+    assert s.done.all() and (exp.sum(1) == 2).all()
