@@ -207,6 +207,22 @@ def measure_extras(dev, key):
                                  "roofline": {"bound": "hbm", "kernel": "k_madn_det_random_step", "algorithmic_bytes_per_env_step": BYTES_PER_STEP,
                                               "achieved": steps2 * BYTES_PER_STEP / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
                                               "frac": steps2 * BYTES_PER_STEP / (ms / 1e3) / 1e9 / peak}}
+    # evaluation loop: rule-based team against random team, one fused launch per lockstep iteration
+    from exploring_muzero_on_dog_b200 import evaluate_agent as ea
+    n3 = 16384
+    seeds3 = jaxrand.randint(key, n3, 0, 1_000_000, device=dev)
+    for rep in range(2):
+        env3 = dm.env_reset(0, seed=seeds3, device=dev, **RULES)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        env3, win3 = ea.play_eval_loop(env3, ({"type": 2}, {"type": 3}, {"type": 2}, {"type": 3}), key, n3, poll_every=64)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    out["eval_loop_rule_vs_random"] = {"workload": "play_eval_loop: 16,384 det-MADN games, seats 0/2 rule-based scorer, seats 1/3 random, to termination "
+                                                   "(k_madn_eval_step per lockstep iteration)",
+                                       "ms": ms, "games_per_s": n3 / (ms / 1e3), "team_0_2_wins": int(win3[:, 0].sum().item()),
+                                       "team_1_3_wins": int(win3[:, 1].sum().item())}
     # config 1: TicTacToeV2, 512 lockstep games x 50 simulations per ply, true-env callbacks with rollout, PUCT (TicTacToe/mcts.py:9-23)
     from exploring_muzero_on_dog_b200.TicTacToe import mcts as tm
     cache = mcts.GraphCache()
