@@ -596,7 +596,7 @@ __global__ void __launch_bounds__(kThreads) k_madn_det_play_random(const __grid_
 #ifdef DOGSTEP_TRACE
 __device__ unsigned long long g_play_trace[128];
 #endif
-constexpr int kPlayRound = 32;
+constexpr int kPlayRound = 64;  // 24 / 32 / 48 / 64: 2.21 / 2.19 / 2.18 / 2.175 ms on config 2 (with key ring and tail mode)
 constexpr int kPlayMaxThreads = 512;  // game threads per CTA (+ 32: the producer warp)
 constexpr int kXWords = 23;  // occ 8, pins 4, action set 8, cur|reward, len, game index
 
