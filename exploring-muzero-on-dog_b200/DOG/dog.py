@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from .. import _lib, rules as _rules
-from ..MADN._state import BatchedEnv, seeds_to_dev, to_dev
+from ..MADN._state import BatchedEnv, reuse_or_alloc, seeds_to_dev, to_dev
 from ..MADN.deterministic_madn import _geometry, _layout_mask, _out
 
 
@@ -63,9 +63,9 @@ class DOG(BatchedEnv):
 
     def _make_cstate(self):
         t = self._t
-        return _lib.DogState(*[C.c_void_p(t[k].data_ptr()) for k in
-                               ("board", "current_player", "pins", "reward", "done", "deck", "hands", "swap_choices",
-                                "round_starter", "phase", "key", "hand_size")])
+        return _lib.tag(_lib.DogState(*[C.c_void_p(t[k].data_ptr()) for k in
+                                        ("board", "current_player", "pins", "reward", "done", "deck", "hands", "swap_choices",
+                                         "round_starter", "phase", "key", "hand_size")]), t["board"].device)
 
 
 RAW_OBS_SIZE = 56 + 14 + 4
@@ -91,7 +91,7 @@ def get_play_action_size(env):
 def env_reset(_, num_players=4, layout=None, distance=10, starting_player=0, seed=42, enable_teams=False,
               enable_initial_free_pin=False, enable_circular_board=True, enable_start_blocking=False,
               enable_jump_in_goal_area=True, enable_friendly_fire=False, must_traverse_start=True, disable_swapping=False,
-              disable_hot_seven=False, disable_joker=False, device="cuda"):
+              disable_hot_seven=False, disable_joker=False, device="cuda", out=None):
     """env_reset (:83-181), seed scalar or int array [n]."""
     num_players, distance = int(num_players), int(distance)
     batched, seeds = seeds_to_dev(seed, device)
@@ -104,8 +104,7 @@ def env_reset(_, num_players=4, layout=None, distance=10, starting_player=0, see
                  disable_hot_seven=bool(disable_hot_seven), disable_joker=bool(disable_joker))
     static = dict(num_players=num_players, num_cards=14, board_size=4 * distance, total_board_size=4 * distance + 16,
                   rules=rules, layout_mask=lm, _start=start, _target=target, _goal=goal)
-    env = DOG(int(seeds.numel()), static, torch.device(device), batched)
-    env.alloc()
+    env = reuse_or_alloc(DOG, out, int(seeds.numel()), static, device, batched)  # out=: overwrite that env's leaves
     cfg, st = env.cfg(), env.cstate()
     _lib.check(_lib.lib().dogstep_dog_reset(C.byref(st), C.c_int64(env.n), C.byref(cfg), _lib.ptr(seeds),
                                            C.c_int32(int(starting_player)), _lib.stream()), "dog_reset")

@@ -28,6 +28,19 @@ def seeds_to_dev(seed, device):
     return a.ndim > 0, to_dev(np.atleast_1d(a), torch.int32, device)
 
 
+def reuse_or_alloc(cls, out, n, static, device, batched):
+    """env_reset(out=...): overwrite the leaves of an existing env of the same size and configuration instead of
+    allocating new ones (the steady state of a self-play iteration re-seeds the same buffers)"""
+    if out is None:
+        env = cls(n, static, torch.device(device), batched)
+        env.alloc()
+        return env
+    pub = lambda d: {k: v for k, v in d.items() if not k.startswith("_")}
+    if not isinstance(out, cls) or out.n != n or pub(out.static) != pub(static):
+        raise ValueError("env_reset(out=...): size or configuration differs from the env to be overwritten")
+    return out
+
+
 class BatchedEnv:
     """Leaves: name -> (torch dtype, trailing shape).  Static fields live in `static`."""
 

@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from .. import _lib, rules as _rules
-from ._state import BatchedEnv, seeds_to_dev, to_dev
+from ._state import BatchedEnv, reuse_or_alloc, seeds_to_dev, to_dev
 from .deterministic_madn import _geometry, _layout_mask, _out, set_pins_on_board  # noqa: F401  (same function in both files)
 
 
@@ -48,14 +48,14 @@ class classic_MADN(BatchedEnv):
 
     def _make_cstate(self):
         t = self._t
-        return _lib.MadnClsState(*[C.c_void_p(t[k].data_ptr()) for k in
-                                   ("board", "current_player", "pins", "reward", "done", "die", "key")])
+        return _lib.tag(_lib.MadnClsState(*[C.c_void_p(t[k].data_ptr()) for k in
+                                            ("board", "current_player", "pins", "reward", "done", "die", "key")]), t["board"].device)
 
 
 def env_reset(_, num_players=4, layout=None, distance=10, starting_player=0, seed=42, enable_teams=False,
               enable_initial_free_pin=False, enable_circular_board=True, enable_start_blocking=False,
               enable_jump_in_goal_area=True, enable_friendly_fire=False, enable_start_on_1=True,
-              enable_bonus_turn_on_6=True, enable_dice_rethrow=False, must_traverse_start=False, device="cuda"):
+              enable_bonus_turn_on_6=True, enable_dice_rethrow=False, must_traverse_start=False, device="cuda", out=None):
     """env_reset (:51-131); `seed` scalar (single env) or int array [n] (vmapped)."""
     num_players, distance = int(num_players), int(distance)
     batched, seeds = seeds_to_dev(seed, device)
@@ -69,8 +69,7 @@ def env_reset(_, num_players=4, layout=None, distance=10, starting_player=0, see
                  enable_dice_rethrow=bool(enable_dice_rethrow), must_traverse_start=bool(must_traverse_start))
     static = dict(num_players=num_players, board_size=4 * distance, total_board_size=4 * distance + 16, rules=rules,
                   layout_mask=lm, _start=start, _target=target, _goal=goal)
-    env = classic_MADN(int(seeds.numel()), static, torch.device(device), batched)
-    env.alloc()
+    env = reuse_or_alloc(classic_MADN, out, int(seeds.numel()), static, device, batched)  # out=: overwrite that env's leaves
     cfg, st = env.cfg(), env.cstate()
     _lib.check(_lib.lib().dogstep_madn_cls_reset(C.byref(st), C.c_int64(env.n), C.byref(cfg), _lib.ptr(seeds),
                                                 C.c_int32(int(starting_player)), _lib.stream()), "madn_cls_reset")

@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from .. import _lib, rules as _rules
-from ._state import BatchedEnv, seeds_to_dev, to_dev
+from ._state import BatchedEnv, reuse_or_alloc, seeds_to_dev, to_dev
 
 RULE_KEYS = ("enable_teams", "enable_initial_free_pin", "enable_circular_board", "enable_start_blocking",
              "enable_jump_in_goal_area", "enable_friendly_fire", "enable_start_on_1", "enable_bonus_turn_on_6",
@@ -84,16 +84,17 @@ class deterministic_MADN(BatchedEnv):
 
     def _make_cstate(self):
         t = self._t
-        return _lib.MadnDetState(*[C.c_void_p(t[k].data_ptr()) for k in
-                                   ("board", "current_player", "pins", "reward", "done", "action_set", "key")])
+        return _lib.tag(_lib.MadnDetState(*[C.c_void_p(t[k].data_ptr()) for k in
+                                            ("board", "current_player", "pins", "reward", "done", "action_set", "key")]), t["board"].device)
 
 
 def env_reset(_, num_players=4, layout=None, distance=10, starting_player=0, seed=42, enable_teams=False,
               enable_initial_free_pin=False, enable_circular_board=True, enable_start_blocking=False,
               enable_jump_in_goal_area=True, enable_friendly_fire=False, enable_start_on_1=True,
-              enable_bonus_turn_on_6=True, must_traverse_start=False, device="cuda"):
+              enable_bonus_turn_on_6=True, must_traverse_start=False, device="cuda", out=None):
     """env_reset (:42-120).  `seed` may be a scalar (single env) or an int array [n] (what
-    jax.vmap(env_reset_batched) receives, game_agent.py:24-44)."""
+    jax.vmap(env_reset_batched) receives, game_agent.py:24-44).  `out`: an env of the same size and configuration whose
+    leaves are overwritten (no allocation: the steady state of a self-play iteration re-seeds the same buffers)."""
     num_players, distance = int(num_players), int(distance)
     batched, seeds = seeds_to_dev(seed, device)
     lm = _layout_mask(layout)
@@ -106,8 +107,7 @@ def env_reset(_, num_players=4, layout=None, distance=10, starting_player=0, see
                  must_traverse_start=bool(must_traverse_start))
     static = dict(num_players=num_players, board_size=4 * distance, total_board_size=4 * distance + 16, rules=rules,
                   layout_mask=lm, _start=start, _target=target, _goal=goal)
-    env = deterministic_MADN(int(seeds.numel()), static, torch.device(device), batched)
-    env.alloc()
+    env = reuse_or_alloc(deterministic_MADN, out, int(seeds.numel()), static, device, batched)
     cfg, st = env.cfg(), env.cstate()
     _lib.check(_lib.lib().dogstep_madn_det_reset(C.byref(st), C.c_int64(env.n), C.byref(cfg), _lib.ptr(seeds),
                                                 C.c_int32(int(starting_player)), _lib.stream()), "madn_det_reset")

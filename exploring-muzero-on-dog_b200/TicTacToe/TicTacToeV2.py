@@ -24,7 +24,8 @@ class TicTacToeV2(BatchedEnv):
 
     def cstate(self):
         t = self._t
-        return _lib.TttState(*[C.c_void_p(t[k].data_ptr()) for k in ("board", "current_player", "reward", "done", "memory")])
+        return _lib.tag(_lib.TttState(*[C.c_void_p(t[k].data_ptr()) for k in ("board", "current_player", "reward", "done", "memory")]),
+                        t["board"].device)
 
 
 def env_reset(_, n=None, device="cuda", variant=None):

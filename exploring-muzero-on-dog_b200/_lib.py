@@ -31,6 +31,62 @@ class MadnClsState(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("board", "current_player", "pins", "reward", "done", "die", "key")]
 
 
+class _DevPtr(C.c_void_p):
+    """a device pointer that remembers which GPU it lives on (attribute `dev`)"""
+
+
+class _Stream:
+    """placeholder argument: replaced at call time by the current torch stream of the device the pointers live on"""
+
+
+_STREAM = _Stream()
+
+
+class _Entry:
+    """One extern "C" entry point.  The kernels launch on the CUDA device that is current at call time, so the call is made
+    with the device of its pointer arguments current and on torch's current stream OF THAT DEVICE: an env, tree or replay
+    shard created with device='cuda:1' works whatever torch.cuda.current_device() is, and stays ordered with the torch ops
+    on its tensors.  Pointers of two different GPUs in one call raise."""
+    __slots__ = ("fn", "name")
+
+    def __init__(self, fn, name):
+        self.fn, self.name = fn, name
+
+    def __call__(self, *args):
+        dev = None
+        for a in args:
+            d = getattr(a, "dev", None)
+            if d is None:
+                o = getattr(a, "_obj", None)  # byref(struct): the struct carries the device of its leaves (tag())
+                if o is not None:
+                    d = getattr(o, "dev", None)
+            if d is not None:
+                if dev is None:
+                    dev = d
+                elif d != dev:
+                    raise DogstepError(f"{self.name}: arguments live on different GPUs (cuda:{dev} and cuda:{d})")
+        if dev is None and not any(a is _STREAM for a in args):
+            return self.fn(*args)  # no device pointer and no stream placeholder: argument validation only (works without a GPU)
+        if dev is None or dev == torch.cuda.current_device():
+            s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            return self.fn(*[s if a is _STREAM else a for a in args])
+        with torch.cuda.device(dev):
+            s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            return self.fn(*[s if a is _STREAM else a for a in args])
+
+
+class _Lib:
+    def __init__(self, cdll):
+        self._cdll = cdll
+        cdll.dogstep_last_error.restype = C.c_char_p
+        self.dogstep_last_error = cdll.dogstep_last_error
+
+    def __getattr__(self, name):
+        e = _Entry(getattr(self._cdll, name), name)  # AttributeError for a symbol the library does not export
+        setattr(self, name, e)
+        return e
+
+
 def lib():
     """Load libdogstep.so; raise loudly when it has not been built (python __graft_entry__.py build)."""
     global _lib
@@ -39,9 +95,14 @@ def lib():
             raise DogstepError(
                 f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(nvcc, sm_100a). There is no CPU fallback.")
-        _lib = C.CDLL(LIB_PATH)
-        _lib.dogstep_last_error.restype = C.c_char_p
+        _lib = _Lib(C.CDLL(LIB_PATH))
     return _lib
+
+
+def tag(struct, device):
+    """mark a ctypes struct of device pointers with the GPU its leaves live on (see _Entry)"""
+    struct.dev = device.index if device.index is not None else torch.cuda.current_device()
+    return struct
 
 
 def check(rc, what):
@@ -58,11 +119,14 @@ def ptr(t):
         raise DogstepError("dogstep kernels need CUDA tensors; there is no CPU path")
     if not t.is_contiguous():
         raise DogstepError("dogstep kernels need contiguous tensors")
-    return C.c_void_p(t.data_ptr())
+    p = _DevPtr(t.data_ptr())
+    p.dev = t.device.index
+    return p
 
 
 def stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """the `stream` argument of an entry point: torch's current stream on the device of the call's pointers"""
+    return _STREAM
 
 
 def host_key(key):

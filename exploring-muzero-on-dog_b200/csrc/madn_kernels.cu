@@ -1007,6 +1007,20 @@ __global__ void k_random_split_each(const uint32_t* __restrict__ keys, int64_t n
   out[2 * i + 1] = k.b;
 }
 
+// `rng_key, *step_keys = jax.random.split(rng_key, n + 1)` with the loop key RESIDENT ON THE DEVICE (game_agent.py:60): the
+// self-play loop then needs no host round trip per lockstep iteration and one iteration can be replayed as a CUDA graph.
+__global__ void k_random_split_chain_keys(const uint32_t* __restrict__ key, int64_t n, uint32_t* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Key2 k = split_i(Key2{key[0], key[1]}, (uint32_t)(i + 1));
+  reinterpret_cast<uint2*>(out)[i] = make_uint2(k.a, k.b);
+}
+__global__ void k_random_split_chain_carry(uint32_t* __restrict__ key) {
+  Key2 k = split_i(Key2{key[0], key[1]}, 0u);
+  key[0] = k.a;
+  key[1] = k.b;
+}
+
 // ---- jax.random helpers -------------------------------------------------------------------------
 __global__ void k_random_split(Key2 key, int64_t n, uint32_t* __restrict__ out) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1300,6 +1314,13 @@ int dogstep_madn_cls_eval_step(const dogstep_madn_cls_state* s, int64_t n, const
   const int4 at = make_int4(agent_type[0], agent_type[1], agent_type[2], agent_type[3]);
   k_madn_eval_step<false><<<blocks_for(n, kThreads), kThreads, 0, st>>>(g, p, n, at, search_action, Key2{host_rng_key[0], host_rng_key[1]},
                                                                         game_offset, winners, active_count);
+  return check_launch();
+}
+
+int dogstep_random_split_chain(uint32_t* key, int64_t n, uint32_t* step_keys, void* stream) {
+  if (!key || !step_keys || n < 0 || n >= 0xFFFFFFFFll) return DOGSTEP_ERR_INVALID_ARG;
+  if (n) k_random_split_chain_keys<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(key, n, step_keys);
+  k_random_split_chain_carry<<<1, 1, 0, (cudaStream_t)stream>>>(key);  // after every reader of the old key (stream order)
   return check_launch();
 }
 

@@ -14,13 +14,15 @@ namespace dogstep {
 
 __global__ void __launch_bounds__(256) k_replay_save(dogstep_replay_arrays buf, dogstep_replay_arrays traj, int64_t n_games,
                                                      const int32_t* __restrict__ slot) {
-  const int64_t game = blockIdx.y;
+  const int64_t game = blockIdx.x;  // games on grid.x (2^31 - 1 of them), ply chunks on grid.y
   if (game >= n_games) return;
   const int pos = slot[game];
   if (pos < 0) return;
-  const int length = min(traj.episode_lengths[game], buf.max_episode_length);
   const int Tb = buf.max_episode_length, Tt = traj.max_episode_length;
-  const int t0 = blockIdx.x * 8, t1 = min(t0 + 8, length);  // 8 plies per CTA
+  // an episode can be no longer than the rows that exist on either side: idx > T' (a trajectory cut short) must not make the
+  // stored length exceed the plies actually copied
+  const int length = min(traj.episode_lengths[game], min(Tb, Tt));
+  const int t0 = blockIdx.y * 8, t1 = min(t0 + 8, length);  // 8 plies per CTA
   const int tid = threadIdx.x;
   if (t1 > t0) {
     // the plies t0..t1-1 of one episode are contiguous in the trajectory and in the ring slot: one vectorised chunk per leaf
@@ -51,7 +53,7 @@ __global__ void __launch_bounds__(256) k_replay_save(dogstep_replay_arrays buf, 
       if (buf.stochastic) buf.dice_outcomes[b] = traj.dice_outcomes[a];
     }
   }
-  if (blockIdx.x == 0 && tid == 0) buf.episode_lengths[pos] = length;
+  if (blockIdx.y == 0 && tid == 0) buf.episode_lengths[pos] = length;
 }
 
 __global__ void k_replay_plan(const int32_t* __restrict__ episode_lengths, int size, int B, int unroll_steps, int n_normal,
@@ -79,8 +81,10 @@ __global__ void __launch_bounds__(128) k_replay_gather(dogstep_replay_arrays buf
   const int b = blockIdx.x;
   if (b >= B) return;
   const int K = unroll_steps + 1, A = buf.action_dim, T = buf.max_episode_length, tid = threadIdx.x;
-  const int ep = ep_indices[b], t0 = t_starts[b];
-  const int len = buf.episode_lengths[ep];
+  // a caller-supplied plan is clamped into the stored arrays (an empty slot reads as one all-zero ply)
+  const int ep = min(max(ep_indices[b], 0), buf.capacity - 1);
+  const int len = min(max(buf.episode_lengths[ep], 1), T);
+  const int t0 = min(max(t_starts[b], 0), len - 1);
   const int64_t base = (int64_t)ep * T;
   // root observation (:104)
   {
@@ -140,10 +144,12 @@ __global__ void __launch_bounds__(128) k_replay_gather(dogstep_replay_arrays buf
 // independent of the order it is taken in: the parallel scans below and the NumPy oracle agree bit for bit.
 constexpr int kPrioShift = 20;
 
+// a stored priority is never 0 (floor: one fixed-point unit): a ply whose error reached 0 stays drawable, and the total can
+// only be 0 for an empty buffer
 __device__ __forceinline__ uint32_t prio_to_fixed(float p) {
-  if (!(p > 0.0f)) return 0u;
+  if (!(p > 0.0f)) return 1u;
   const double v = (double)p * (double)(1u << kPrioShift);
-  return v >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)(v + 0.5);
+  return v >= 4294967295.0 ? 0xFFFFFFFFu : max((uint32_t)(v + 0.5), 1u);
 }
 
 // rows[i] < 0 is skipped; row = value for t < episode_lengths[row], 0 beyond; row sum recomputed (warp per row)
@@ -161,14 +167,18 @@ __global__ void __launch_bounds__(128) k_replay_prio_fill(uint32_t* __restrict__
   if (lane == 0) row_sum[row] = (unsigned long long)v * (unsigned long long)max(len, 0);
 }
 
-// prio[ep[b], t[b]] = value[b]; the row sum follows through atomics, so duplicates in the batch stay consistent
-__global__ void k_replay_prio_update(uint32_t* __restrict__ prio, unsigned long long* __restrict__ row_sum, int T, int B,
+// prio[ep[b], t[b]] = value[b]; the row sum follows through atomics, so duplicates in the batch stay consistent.  Pairs outside
+// the stored episodes (ep outside [0, capacity), t outside [0, episode length)) are ignored.
+__global__ void k_replay_prio_update(uint32_t* __restrict__ prio, unsigned long long* __restrict__ row_sum,
+                                     const int32_t* __restrict__ episode_lengths, int capacity, int T, int B,
                                      const int32_t* __restrict__ ep, const int32_t* __restrict__ ts, const float* __restrict__ value) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
+  const int e = ep[b], t = ts[b];
+  if (e < 0 || e >= capacity || t < 0 || t >= min(episode_lengths[e], T)) return;
   const uint32_t nv = prio_to_fixed(value[b]);
-  const uint32_t old = atomicExch(&prio[(int64_t)ep[b] * T + ts[b]], nv);
-  atomicAdd(&row_sum[ep[b]], (unsigned long long)nv - (unsigned long long)old);  // wraps modulo 2^64: exact
+  const uint32_t old = atomicExch(&prio[(int64_t)e * T + t], nv);
+  atomicAdd(&row_sum[e], (unsigned long long)nv - (unsigned long long)old);  // wraps modulo 2^64: exact
 }
 
 // inclusive scan of row_sum[0..size) -> cdf (one CTA of 1024 threads, chunks of 1024 with a running carry)
@@ -256,11 +266,11 @@ int dogstep_replay_save(const dogstep_replay_arrays* buf, const dogstep_replay_a
                         void* stream) {
   if (int rc = replay_check(buf)) return rc;
   if (int rc = replay_check(traj)) return rc;
-  if (!slot || n_games < 0 || n_games > 65535) return DOGSTEP_ERR_INVALID_ARG;
+  if (!slot || n_games < 0 || n_games > 0x7FFFFFFF || (traj->max_episode_length + 7) / 8 > 65535) return DOGSTEP_ERR_INVALID_ARG;
   if (buf->obs_size != traj->obs_size || buf->action_dim != traj->action_dim || buf->stochastic != traj->stochastic)
     return DOGSTEP_ERR_INVALID_ARG;
   if (n_games == 0) return DOGSTEP_OK;
-  dim3 grid((unsigned)((traj->max_episode_length + 7) / 8), (unsigned)n_games);
+  dim3 grid((unsigned)n_games, (unsigned)((traj->max_episode_length + 7) / 8));
   k_replay_save<<<grid, 256, 0, (cudaStream_t)stream>>>(*buf, *traj, n_games, slot);
   return check_launch();
 }
@@ -300,11 +310,15 @@ int dogstep_replay_prio_fill(uint32_t* prio, unsigned long long* row_sum, const 
   return check_launch();
 }
 
-int dogstep_replay_prio_update(uint32_t* prio, unsigned long long* row_sum, int32_t max_episode_length, int32_t batch_size,
-                               const int32_t* ep_indices, const int32_t* t_starts, const float* value, void* stream) {
-  if (!prio || !row_sum || !ep_indices || !t_starts || !value || max_episode_length < 1 || batch_size < 0) return DOGSTEP_ERR_INVALID_ARG;
+int dogstep_replay_prio_update(uint32_t* prio, unsigned long long* row_sum, const int32_t* episode_lengths, int32_t capacity,
+                               int32_t max_episode_length, int32_t batch_size, const int32_t* ep_indices, const int32_t* t_starts,
+                               const float* value, void* stream) {
+  if (!prio || !row_sum || !episode_lengths || !ep_indices || !t_starts || !value || capacity < 1 || max_episode_length < 1 ||
+      batch_size < 0)
+    return DOGSTEP_ERR_INVALID_ARG;
   if (batch_size == 0) return DOGSTEP_OK;
-  k_replay_prio_update<<<(batch_size + 127) / 128, 128, 0, (cudaStream_t)stream>>>(prio, row_sum, max_episode_length, batch_size, ep_indices,
+  k_replay_prio_update<<<(batch_size + 127) / 128, 128, 0, (cudaStream_t)stream>>>(prio, row_sum, episode_lengths, capacity,
+                                                                                   max_episode_length, batch_size, ep_indices,
                                                                                    t_starts, value);
   return check_launch();
 }

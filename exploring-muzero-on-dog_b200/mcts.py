@@ -74,8 +74,8 @@ class Tree:
         self.num_actions, self.num_chance, self.n = num_actions, num_chance, n
 
     def cstruct(self):
-        return _lib.MctsTree(*[None if getattr(self, k) is None else C.c_void_p(getattr(self, k).data_ptr())
-                               for k in _lib.MCTS_TREE_FIELDS])
+        return _lib.tag(_lib.MctsTree(*[None if getattr(self, k) is None else C.c_void_p(getattr(self, k).data_ptr())
+                                        for k in _lib.MCTS_TREE_FIELDS]), self.node_visits.device)
 
     def qvalues(self, indices=0):
         return self.children_rewards[:, indices] + self.children_discounts[:, indices] * self.children_values[:, indices]
@@ -178,23 +178,50 @@ def _run(search, params, root, recurrent_fn, invalid_actions, keys, dirichlet_no
     return search.policy_output()[0]
 
 
+def _tree_copy_(dst, src):
+    """copy the tensors of a nested dict / list / tuple `src` into the same-shaped structure `dst` in place; False if the
+    structures do not match (different keys, shapes or dtypes)"""
+    if isinstance(dst, torch.Tensor):
+        if not isinstance(src, torch.Tensor) or dst.shape != src.shape or dst.dtype != src.dtype:
+            return False
+        dst.copy_(src)
+        return True
+    if isinstance(dst, dict):
+        return isinstance(src, dict) and dst.keys() == src.keys() and all(_tree_copy_(dst[k], src[k]) for k in dst)
+    if isinstance(dst, (list, tuple)):
+        return isinstance(src, (list, tuple)) and len(dst) == len(src) and all(_tree_copy_(a, b) for a, b in zip(dst, src))
+    return dst is src or dst == src
+
+
 class GraphCache:
-    """Caller-owned cache of searches captured as CUDA graphs.
+    """Caller-owned, bounded cache of searches captured as CUDA graphs.
 
     A search is 2-3 small launches per simulation (select, the caller's recurrent function, expand); at the batch sizes of
     the reference's configurations that loop is launch-bound.  Passing the same `GraphCache()` to a policy function on
     every move makes the first call capture `init -> num_simulations x (select, recurrent_fn, expand) -> policy_output`
     into one CUDA graph and every later call with the same shapes replay it: inputs are copied into the captured buffers,
     the returned PolicyOutput tensors are the captured ones (consume them before the next call).  The recurrent function
-    must be capturable (CUDA work on the current stream only, no host synchronisation) and `params` must be updated in
-    place between calls — both hold for torch modules and for the true-env callbacks shipped here."""
+    must be capturable (CUDA work on the current stream only, no host synchronisation).
 
-    def __init__(self):
-        self.entries = {}
+    `params`: the captured kernels read the parameter tensors that were passed at capture time.  A later call with the SAME
+    object (torch modules / tensors updated in place by the optimiser) replays as is.  A later call with a NEW object of the
+    same structure (immutable pytrees replaced at every optimiser step, as Flax does) has its tensors copied into the captured
+    ones before the replay — no re-capture, nothing leaks.  A structure mismatch re-captures.  At most `max_entries` graphs
+    (with their trees) are kept, least recently used first out; clear() drops all."""
 
-    def run(self, key, inputs, fn):
+    def __init__(self, max_entries=4):
+        from collections import OrderedDict
+        self.entries, self.max_entries = OrderedDict(), max(1, int(max_entries))
+
+    def clear(self):
+        self.entries.clear()
+
+    def run(self, key, inputs, fn, params=None):
         """inputs: dict name -> tensor or None; fn(static_inputs) -> PolicyOutput"""
         ent = self.entries.get(key)
+        if ent is not None and ent[4] is not params and not _tree_copy_(ent[4], params):
+            del self.entries[key]
+            ent = None
         if ent is None:
             static = {k: (None if v is None else v.detach().clone().contiguous()) for k, v in inputs.items()}
             side = torch.cuda.Stream()
@@ -206,9 +233,12 @@ class GraphCache:
             with torch.cuda.graph(graph):
                 out = fn(static)
             # `fn` is kept: its closure owns the Search whose work buffers (parent, action, embedding, keys) the captured
-            # kernels write on every replay
-            ent = self.entries[key] = (static, graph, out, fn)
-        static, graph, out, _ = ent
+            # kernels write on every replay; `params` is kept because the captured kernels read its tensors
+            ent = self.entries[key] = (static, graph, out, fn, params)
+            while len(self.entries) > self.max_entries:
+                self.entries.popitem(last=False)
+        self.entries.move_to_end(key)
+        static, graph, out = ent[0], ent[1], ent[2]
         for k, v in inputs.items():
             if v is not None:
                 static[k].copy_(v)
@@ -225,13 +255,13 @@ def _run_cached(graph_cache, cfg, n, dev, params, root, recurrent_fn, invalid_ac
         return _run(Search(cfg, n, dev), params, root, recurrent_fn, invalid_actions, keys, dirichlet_noise)
     inputs = dict(keys=keys, prior=root.prior_logits.float(), value=root.value.float(), emb=root.embedding.float().reshape(n, -1),
                   invalid=None if invalid_actions is None else invalid_actions.reshape(n, -1).to(torch.uint8), noise=dirichlet_noise)
-    key = (_cfg_key(cfg), n, str(dev), id(recurrent_fn), id(params), invalid_actions is None, dirichlet_noise is None)
+    key = (_cfg_key(cfg), n, str(dev), id(recurrent_fn), invalid_actions is None, dirichlet_noise is None)
     search = Search(cfg, n, dev) if key not in graph_cache.entries else None
 
     def fn(st):
         return _run(search, params, RootFnOutput(st["prior"], st["value"], st["emb"]), recurrent_fn, st["invalid"], st["keys"], st["noise"])
 
-    return graph_cache.run(key, inputs, fn)
+    return graph_cache.run(key, inputs, fn, params)
 
 
 def muzero_policy(params, rng_key, root, recurrent_fn, num_simulations, invalid_actions=None, max_depth=None, *,
@@ -295,7 +325,6 @@ def stochastic_muzero_policy(params, rng_key, root, decision_recurrent_fn, chanc
                   invalid=None if invalid_actions is None else invalid_actions.reshape(n, -1).to(torch.uint8), noise=noise)
     if graph_cache is None:
         return search_loop(Search(cfg, n, dev), inputs)
-    key = (_cfg_key(cfg), n, str(dev), id(decision_recurrent_fn), id(chance_recurrent_fn), id(params), invalid_actions is None,
-           noise is None)
+    key = (_cfg_key(cfg), n, str(dev), id(decision_recurrent_fn), id(chance_recurrent_fn), invalid_actions is None, noise is None)
     s = Search(cfg, n, dev) if key not in graph_cache.entries else None
-    return graph_cache.run(key, inputs, lambda st: search_loop(s, st))
+    return graph_cache.run(key, inputs, lambda st: search_loop(s, st), params)

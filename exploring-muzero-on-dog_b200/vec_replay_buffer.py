@@ -28,7 +28,8 @@ class VectorizedReplayBuffer:
     STOCHASTIC = False
 
     def __init__(self, capacity, batch_size, unroll_steps, td_steps, obs_shape=(14, 56), action_dim=24, max_episode_length=500,
-                 bootstrap_value_target=True, device="cuda", obs_dtype=torch.float32, seed=0, prioritized=False):
+                 bootstrap_value_target=True, device="cuda", obs_dtype=torch.float32, seed=0, prioritized=False,
+                 priority_alpha=1.0, priority_eps=0.0):
         self.capacity, self.batch_size, self.unroll_steps, self.td_steps = capacity, batch_size, unroll_steps, td_steps
         self.obs_shape, self.action_dim, self.max_episode_length = tuple(obs_shape), action_dim, max_episode_length
         self.bootstrap_value_target = bootstrap_value_target
@@ -45,6 +46,7 @@ class VectorizedReplayBuffer:
         self.dice_distributions = z((capacity, T, 6), torch.float32) if self.STOCHASTIC else None
         self.position, self.size = 0, 0
         self.prioritized, self.max_priority = bool(prioritized), 1.0
+        self.priority_alpha, self.priority_eps = float(priority_alpha), float(priority_eps)  # stored = (|p| + eps) ** alpha
         if self.prioritized:  # fixed-point priorities (2^-20 units) + exact uint64 row sums, see include/dogstep.h
             self.priorities = z((capacity, T), torch.uint32)
             self.priority_row_sums = z((capacity,), torch.uint64)
@@ -57,11 +59,11 @@ class VectorizedReplayBuffer:
     def _arrays(self, src, capacity, T):
         ptr = lambda t: None if t is None else C.c_void_p(t.data_ptr())
         obs = src["observations"]
-        return _lib.ReplayArrays(capacity, T, int(np.prod(self.obs_shape)), self.action_dim, int(obs.dtype == torch.int8),
-                                 int(self.STOCHASTIC), *[ptr(src.get(k)) for k in
-                                                         ("observations", "actions", "rewards", "root_values", "child_visits", "masks",
-                                                          "players", "teams", "discounts", "episode_lengths", "dice_outcomes",
-                                                          "dice_distributions")])
+        return _lib.tag(_lib.ReplayArrays(capacity, T, int(np.prod(self.obs_shape)), self.action_dim, int(obs.dtype == torch.int8),
+                                          int(self.STOCHASTIC), *[ptr(src.get(k)) for k in
+                                                                  ("observations", "actions", "rewards", "root_values", "child_visits",
+                                                                   "masks", "players", "teams", "discounts", "episode_lengths",
+                                                                   "dice_outcomes", "dice_distributions")]), obs.device)
 
     def _own(self):
         names = ("observations", "actions", "rewards", "root_values", "child_visits", "masks", "players", "teams", "discounts",
@@ -137,8 +139,9 @@ class VectorizedReplayBuffer:
             out["dice_outcomes"] = e((B, K - 1), torch.int32)
             out["dice_probs"] = e((B, K - 1, 6), torch.float32)
         ptr = lambda k: C.c_void_p(out[k].data_ptr()) if k in out else None
-        cb = _lib.ReplayBatch(*[ptr(k) for k in ("observations", "actions", "rewards", "policies", "values", "masks", "target_values",
-                                                 "discount_targets", "dice_outcomes", "dice_probs")])
+        cb = _lib.tag(_lib.ReplayBatch(*[ptr(k) for k in ("observations", "actions", "rewards", "policies", "values", "masks",
+                                                          "target_values", "discount_targets", "dice_outcomes", "dice_probs")]),
+                      out["observations"].device)
         buf = self._own()
         _lib.check(_lib.lib().dogstep_replay_gather(C.byref(buf), C.c_int32(B), C.c_int32(self.unroll_steps), C.c_int32(self.td_steps),
                                                    C.c_int32(int(bool(self.bootstrap_value_target))), _lib.ptr(self._gamma_pow),
@@ -175,11 +178,15 @@ class VectorizedReplayBuffer:
         return out
 
     def update_priorities(self, ep_indices, t_starts, priorities):
-        """set the priority of the sampled (episode, ply) pairs (e.g. |search value - target|); float32 >= 0"""
-        pr = self._as(priorities, torch.float32)
+        """set the priority of the sampled (episode, ply) pairs to (|priorities| + priority_eps) ** priority_alpha (e.g. from
+        |search value - target|); stored with a floor of one fixed-point unit; pairs outside the stored episodes are ignored"""
+        pr = self._as(priorities, torch.float32).abs()
+        if self.priority_eps or self.priority_alpha != 1.0:
+            pr = ((pr + self.priority_eps) ** self.priority_alpha).contiguous()
         ep, ts = self._as(ep_indices, torch.int32), self._as(t_starts, torch.int32)
         self.max_priority = max(self.max_priority, float(pr.max().item()))
         _lib.check(_lib.lib().dogstep_replay_prio_update(_lib.ptr(self.priorities), _lib.ptr(self.priority_row_sums),
+                                                        _lib.ptr(self.episode_lengths), C.c_int32(self.capacity),
                                                         C.c_int32(self.max_episode_length), C.c_int32(int(ep.numel())), _lib.ptr(ep),
                                                         _lib.ptr(ts), _lib.ptr(pr), _lib.stream()), "replay_prio_update")
 

@@ -343,14 +343,17 @@ int dogstep_replay_gather(const dogstep_replay_arrays* buf, int32_t batch_size, 
  * P(e, t) = p[e, t] / sum(p) over fixed-point priorities: prio uint32 [capacity, T] in 2^-20 units, row_sum uint64 [capacity];
  * every sum is an exact integer, so the result does not depend on summation order.
  *   prio_fill    rows[i] (int32, -1 = skip) get `value` for t < episode_lengths[row], 0 beyond; row sums recomputed
- *   prio_update  prio[ep[b], t[b]] = value[b] (float32 [B]); row sums follow atomically
+ *   prio_update  prio[ep[b], t[b]] = value[b] (float32 [B]); row sums follow atomically; pairs outside the stored episodes
+ *                (ep outside [0, capacity), t outside [0, episode_lengths[ep])) are ignored
+ * A stored priority is at least one fixed-point unit, so no stored ply ever becomes undrawable.
  *   plan_prioritized  batch_size draws: target = floor(bits64 * total / 2^64) (threefry bits 2b, 2b+1 of host_key), episode
  *                     by binary search in the scanned row sums (cdf_work: uint64 [capacity] scratch), ply by a row scan;
  *                     prob[b] = P(e, t) as float64 (for importance weights) */
 int dogstep_replay_prio_fill(uint32_t* prio, unsigned long long* row_sum, const int32_t* episode_lengths, int32_t max_episode_length,
                              const int32_t* rows, int32_t n_rows, float value, void* stream);
-int dogstep_replay_prio_update(uint32_t* prio, unsigned long long* row_sum, int32_t max_episode_length, int32_t batch_size,
-                               const int32_t* ep_indices, const int32_t* t_starts, const float* value, void* stream);
+int dogstep_replay_prio_update(uint32_t* prio, unsigned long long* row_sum, const int32_t* episode_lengths, int32_t capacity,
+                               int32_t max_episode_length, int32_t batch_size, const int32_t* ep_indices, const int32_t* t_starts,
+                               const float* value, void* stream);
 int dogstep_replay_plan_prioritized(const uint32_t* prio, const unsigned long long* row_sum, unsigned long long* cdf_work, int32_t size,
                                     int32_t max_episode_length, int32_t batch_size, const uint32_t* host_key, int32_t* ep_indices,
                                     int32_t* t_starts, double* prob, void* stream);
@@ -432,6 +435,10 @@ int dogstep_random_split(const uint32_t* host_key, int64_t n, uint32_t* out, voi
 int dogstep_random_randint(const uint32_t* host_key, int64_t n, int32_t lo, int32_t hi, int32_t* out, void* stream);
 /* jax.random.uniform(key, (n,), float32, lo, hi) */
 int dogstep_random_uniform(const uint32_t* host_key, int64_t n, float lo, float hi, float* out, void* stream);
+/* rng_key, *step_keys = jax.random.split(rng_key, n + 1) (MuZero_det_MADN/game_agent.py:60) with the loop key uint32 [2] ON
+ * THE DEVICE: step_keys uint32 [n,2] = split(key, n + 1)[1:], then key <- split(key, n + 1)[0] in place.  No host value is
+ * baked into the launch, so a lockstep iteration that starts with this call can be captured once and replayed as a CUDA graph. */
+int dogstep_random_split_chain(uint32_t* key, int64_t n, uint32_t* step_keys, void* stream);
 /* out[i] = jax.random.split(keys[i], m)[index] for every i: keys, out uint32 [n,2] on the device */
 int dogstep_random_split_each(const uint32_t* keys, int64_t n, uint32_t index, uint32_t* out, void* stream);
 /* jax.random.bits(key, (n,), uint32) */

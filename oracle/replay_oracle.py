@@ -116,9 +116,10 @@ PRIO_SHIFT = 20
 
 
 def prio_to_fixed(p):
+    """float32 priority -> stored fixed-point value; floor of one unit (a stored ply never becomes undrawable)"""
     p = np.asarray(p, np.float32)
     v = np.floor(p.astype(np.float64) * float(1 << PRIO_SHIFT) + 0.5)
-    return np.where(p > 0, np.minimum(v, 4294967295.0), 0.0).astype(np.uint64).astype(np.uint32)
+    return np.where(p > 0, np.clip(v, 1.0, 4294967295.0), 1.0).astype(np.uint64).astype(np.uint32)
 
 
 def plan_prioritized(prio_fixed, size, bits):

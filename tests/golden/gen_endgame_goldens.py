@@ -1,0 +1,451 @@
+"""End-game goldens produced by the REFERENCE ITSELF (unmodified /root/reference sources on the NumPy-backed jaxshim;
+build container only), fanned out over the host cores.
+
+    python tests/golden/gen_endgame_goldens.py [dog] [det] [cls]
+        -> tests/golden/{dog,madn_det,madn_cls}_reference_endgames.npz  (+ a per-category table on stdout,
+           copied into DESIGN.md section 6)
+
+What the first generators (gen_dog_goldens.py / gen_madn_goldens.py) left unpinned: games that REACH `done`
+(get_winner, the +1 reward, the frozen current_player), plies played as TEAM PROXY (a finished player moving the
+partner's pins, DOG/dog.py:370,410,493,578,627,766,805,876,924,997; deterministic_madn.py:184,310), and rare action
+categories.  Three kinds of game, every rule set:
+
+  full    env_reset(seed) and play to termination (cap 2000 plies)
+  late    a position late in a random game: the C oracle plays a game to its end with a NumPy action stream, replays
+          it up to `tail` plies before the end, and that state is handed to the reference with env.replace(...) — the
+          reference's own fixture style (DOG/test.py:376-388).  The start state is a fixture (state[0] in the file);
+          everything after it is computed by the reference.
+  built   env_reset(seed) + env.replace(pins=…, board=set_pins_on_board(…)) with most pins already in the goal area
+          and one player finished, so the team-proxy stage starts at once.
+
+Actions: mostly a random legal action — drawn category-first, so rare categories (joker -4, joker swap) are taken
+whenever they are legal — sometimes an arbitrary index, drawn category-first as well (illegal card, illegal move,
+play index during the swap phase).  Every leaf of every state, the legal mask (bit-packed for DOG), reward, done.
+"""
+import json
+import multiprocessing as mp
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "oracle", "jaxshim"))
+sys.path.insert(0, "/root/reference")
+
+DOG_BENCH = dict(enable_teams=True, enable_initial_free_pin=False, enable_circular_board=True, enable_friendly_fire=True,
+                 enable_start_blocking=True, enable_jump_in_goal_area=False, must_traverse_start=True)  # MuZero_DOG/game_agent.py:12-23
+MADN_TRAIN = dict(enable_teams=True, enable_initial_free_pin=True, enable_circular_board=False, enable_friendly_fire=False,
+                  enable_start_blocking=False, enable_jump_in_goal_area=True, enable_start_on_1=True,
+                  enable_bonus_turn_on_6=True, must_traverse_start=False)  # MuZero_det_MADN/game_agent.py:12-22
+DOG_LEAVES = ("board", "current_player", "pins", "reward", "done", "deck", "hands", "swap_choices", "round_starter", "phase",
+              "key", "hand_size")
+CAP = 2000
+
+# DOG action categories (DOG/dog.py:1134-1196, 693-711): index < 396 joker copy, [396, 792) real card, [792, 806) swap-phase card
+DOG_CATS = ("joker-swap", "joker-hot7", "joker-normal", "joker-neg4", "swap", "hot7", "normal", "neg4", "swap-phase")
+_DOG_BOUNDS = [(0, 224), (224, 344), (344, 392), (392, 396)]
+
+
+def dog_cat(a):
+    if a >= 792:
+        return 8
+    r = a % 396
+    return (0 if a < 396 else 4) + next(i for i, (lo, hi) in enumerate(_DOG_BOUNDS) if lo <= r < hi)
+
+
+def dog_cat_range(c):
+    if c == 8:
+        return 792, 806
+    lo, hi = _DOG_BOUNDS[c % 4]
+    off = 0 if c < 4 else 396
+    return lo + off, hi + off
+
+
+_DOG_CAT_OF = np.array([dog_cat(a) for a in range(806)])
+
+
+def mask_bits(rules):
+    from helpers import mask_of
+    return mask_of(rules)
+
+
+# ---------------------------------------------------------------------------------------------------------------- DOG
+def _dog_pick(m, rng, p_arbitrary):
+    """(action or -1 for no_step, kind)"""
+    arbitrary = rng.random() < p_arbitrary
+    if not m.any() and not arbitrary:
+        return -1, 0
+    if arbitrary or not m.any():
+        lo, hi = dog_cat_range(int(rng.integers(9)))
+        return int(rng.integers(lo, hi)), 1
+    legal = np.flatnonzero(m)
+    cats = np.unique(_DOG_CAT_OF[legal])
+    if rng.random() < 0.5:  # category-first: rare categories are taken whenever they are legal
+        legal = legal[_DOG_CAT_OF[legal] == rng.choice(cats)]
+    return int(rng.choice(legal)), 1
+
+
+def _dog_oracle_forward(cfg, seed, sp, rng_seed, stop_before):
+    """play one game on the C oracle with a NumPy action stream; returns (length, state at ply max(0, length - stop_before))"""
+    import oracle as O
+
+    def run(limit):
+        rng = np.random.default_rng(rng_seed)
+        s = O.dog_reset(cfg, [seed], sp)
+        t = 0
+        while t < limit and not s.done[0]:
+            m = O.dog_valid_actions(s)[0].astype(bool)
+            if m.any():
+                O.dog_step(s, [int(rng.choice(np.flatnonzero(m)))])
+            else:
+                O.dog_no_step(s)
+            t += 1
+        return t, s
+    length, _ = run(CAP)
+    return length, run(max(0, length - stop_before))[1]
+
+
+def _dog_built_pins(num_players, teams, rng):
+    """most pins in the goal area; with teams, one player per game already finished (team proxy from ply 0)"""
+    pins = np.full((num_players, 4), -1, np.int64)
+    finished = int(rng.integers(num_players))
+    used = set()
+    for p in range(num_players):
+        g = 4 if p == finished else int(rng.integers(2, 4))
+        lane = 40 + 4 * p
+        cells = sorted(rng.choice(4, size=g, replace=False).tolist(), reverse=True) if g < 4 else [3, 2, 1, 0]
+        if g < 4 and rng.random() < 0.7:
+            cells = [3, 2, 1, 0][:g]  # packed at the end of the lane: those pins never have to move again
+        for i, c in enumerate(cells):
+            pins[p, i] = lane + c
+        for i in range(g, 4):
+            if rng.random() < 0.25:
+                continue  # at home
+            while True:
+                c = int(rng.integers(40))
+                if c not in used:
+                    used.add(c)
+                    pins[p, i] = c
+                    break
+    return pins
+
+
+def dog_game(task):
+    import jax.numpy as jnp
+    from DOG import dog
+    import oracle as O
+    kind, rules, num_players, seed, sp, rng_seed, tail, cap = task
+    rng = np.random.default_rng(rng_seed)
+    env = dog.env_reset(0, num_players=num_players, distance=10, starting_player=sp, seed=seed, **rules)
+    if kind == "late":
+        cfg = O.DogCfg(num_players, 0xF, 10, mask_bits(rules))
+        _, s = _dog_oracle_forward(cfg, seed, sp, rng_seed + 1, tail)
+        upd = {}
+        for k in DOG_LEAVES:
+            ref = np.asarray(getattr(env, k))
+            upd[k] = jnp.array(np.asarray(getattr(s, k)[0]).astype(ref.dtype).reshape(ref.shape), dtype=ref.dtype)
+        env = env.replace(**upd)
+    elif kind == "built":
+        pins = jnp.array(_dog_built_pins(num_players, rules["enable_teams"], rng), dtype=env.pins.dtype)
+        env = env.replace(pins=pins, board=dog.set_pins_on_board(env.board, pins))
+    leaves = lambda e: {k: np.asarray(getattr(e, k)) for k in DOG_LEAVES}
+    rec = {k: [v] for k, v in leaves(env).items()}
+    masks, actions, rewards, dones, kinds = [], [], [], [], []
+    t = 0
+    extra = 3  # a few plies past `done`: the frozen current_player / reward 0 of a finished game
+    while t < cap and extra > 0:
+        if bool(np.asarray(env.done)):
+            extra -= 1
+        m = np.asarray(dog.valid_actions(env)).astype(bool)
+        a, kd = _dog_pick(m, rng, 0.08)
+        if kd:
+            env, r, d = dog.env_step(env, jnp.array(a, dtype=jnp.int32))
+        else:
+            env, r, d = dog.no_step(env)
+        masks.append(np.packbits(m))
+        actions.append(a)
+        kinds.append(kd)
+        rewards.append(int(np.asarray(r)))
+        dones.append(bool(np.asarray(d)))
+        for k, v in leaves(env).items():
+            rec[k].append(v)
+        t += 1
+    out = {f"state_{k}": np.stack(v) for k, v in rec.items()}
+    out.update(mask=np.stack(masks), action=np.array(actions, np.int32), reward=np.array(rewards, np.int8),
+               done=np.array(dones, bool), kind=np.array(kinds, np.int8))
+    meta = dict(rules=rules, num_players=num_players, seed=seed, starting_player=sp, plies=t, kind=kind, from_state=kind != "full")
+    return out, meta
+
+
+def dog_proxy_plies(g, meta):
+    """plies stepped by a player whose own four goal cells were all occupied (the team-proxy stage)"""
+    if not meta["rules"]["enable_teams"] or meta["num_players"] != 4:
+        return 0
+    n = 0
+    for t in range(meta["plies"]):
+        if g["kind"][t] != 1 or g["state_done"][t] or g["state_phase"][t] != 0:
+            continue
+        cp = int(g["state_current_player"][t])
+        if (g["state_board"][t][40 + 4 * cp: 44 + 4 * cp] >= 0).all():
+            n += 1
+    return n
+
+
+def dog_tasks():
+    rng = np.random.default_rng(20261018)
+    keys = list(DOG_BENCH)
+    sets = [dict(DOG_BENCH)] + [{k: bool(rng.integers(2)) for k in keys} for _ in range(4)]
+    sets[2]["enable_teams"] = True   # two team and two non-team random rule sets
+    sets[3]["enable_teams"] = False
+    tasks = []
+    for ri, rules in enumerate(sets):
+        plan = [("full", 4, 6), ("late", 4, 6), ("built", 4, 4)] if ri == 0 else [("late", 4, 8), ("built", 4, 4)]
+        plan += [("late", 2, 1), ("late", 3, 1)]
+        for kind, num_players, reps in plan:
+            for _ in range(reps):
+                seed = int(rng.integers(0, 1_000_000))
+                sp = int(rng.integers(-1, num_players)) if kind != "full" else 0
+                tasks.append((kind, rules, num_players, seed, sp, int(rng.integers(1 << 31)), int(rng.integers(100, 220)), CAP))
+    # Two of the four random rule sets above (start blocking + must_traverse_start + jump_in_goal_area, with / without teams)
+    # deadlock under random play: 0 / 14 and 7 / 14 games finished within 2000 plies, half of the plies are no_step discards.
+    # They stay in the file as deadlock coverage (truncated, see dog_postprocess); two hand-picked rule sets that do finish
+    # bring the count of rule sets with >= 10 finished games to five.
+    extra = [dict(enable_teams=True, enable_initial_free_pin=False, enable_circular_board=True, enable_friendly_fire=True,
+                  enable_start_blocking=False, enable_jump_in_goal_area=True, must_traverse_start=False),
+             dict(enable_teams=False, enable_initial_free_pin=True, enable_circular_board=False, enable_friendly_fire=False,
+                  enable_start_blocking=False, enable_jump_in_goal_area=True, must_traverse_start=True)]
+    rng = np.random.default_rng(20261020)
+    for rules in extra:
+        for kind, num_players, reps in [("late", 4, 9), ("built", 4, 4), ("late", 2, 1), ("late", 3, 1)]:
+            for _ in range(reps):
+                seed = int(rng.integers(0, 1_000_000))
+                sp = int(rng.integers(-1, num_players))
+                tasks.append((kind, rules, num_players, seed, sp, int(rng.integers(1 << 31)), int(rng.integers(100, 220)), CAP))
+    return tasks
+
+
+def dog_postprocess(results):
+    """rule sets in which fewer than 10 games finish (random play deadlocks): keep the finished games and the first 300 plies of
+    two unfinished ones"""
+    by_rules = {}
+    for g, m in results:
+        by_rules.setdefault(json.dumps(m["rules"], sort_keys=True), []).append((g, m))
+    out = []
+    for key, games in by_rules.items():
+        if sum(bool(g["done"].any()) for g, _ in games) >= 10:
+            out += games
+            continue
+        kept_unfinished = 0
+        for g, m in games:
+            if g["done"].any():
+                out.append((g, m))
+            elif kept_unfinished < 2:
+                kept_unfinished += 1
+                T = min(300, m["plies"])
+                g2 = {k: (v[:T + 1] if k.startswith("state_") else v[:T]) for k, v in g.items()}
+                out.append((g2, dict(m, plies=T, truncated=True)))
+    return out
+
+
+def dog_cached(tasks):
+    """games already present in the output file (same task tuple -> same game: every task owns its RNG) are not recomputed"""
+    path = os.path.join(HERE, "dog_reference_endgames.npz")
+    have = {}
+    if os.path.exists(path):
+        z = np.load(path)
+        meta = json.loads(bytes(z["meta"]).decode())
+        for gi, m in enumerate(meta):
+            if m.get("truncated"):
+                continue
+            key = (m["kind"], json.dumps(m["rules"], sort_keys=True), m["num_players"], m["seed"], m["starting_player"])
+            have[key] = ({k[len(f"g{gi}_"):]: z[k] for k in z.files if k.startswith(f"g{gi}_")}, m)
+    hits, todo = {}, []
+    for i, t in enumerate(tasks):
+        key = (t[0], json.dumps(t[1], sort_keys=True), t[2], t[3], t[4])
+        if key in have:
+            hits[i] = have[key]
+        else:
+            todo.append((i, t))
+    return hits, todo
+
+
+# --------------------------------------------------------------------------------------------------------------- MADN
+def _madn_leaves(env, det):
+    d = dict(board=np.asarray(env.board), current_player=np.asarray(env.current_player), pins=np.asarray(env.pins),
+             reward=np.asarray(env.reward), done=np.asarray(env.done), key=np.asarray(env.key))
+    d["action_set" if det else "die"] = np.asarray(env.action_set if det else env.die)
+    return d
+
+
+OBS_STRIDE = 8
+
+
+def madn_game(task):
+    import jax.numpy as jnp
+    from MADN import classic_madn as cm
+    from MADN import deterministic_madn as dm
+    det, kind, rules, num_players, seed, sp, rng_seed, cap = task
+    mod = dm if det else cm
+    rng = np.random.default_rng(rng_seed)
+    env = mod.env_reset(0, num_players=num_players, distance=10, starting_player=sp, seed=seed, **rules)
+    if kind == "built":
+        pins = jnp.array(_dog_built_pins(num_players, rules["enable_teams"], rng), dtype=env.pins.dtype)
+        env = env.replace(pins=pins, board=mod.set_pins_on_board(env.board, pins))
+    rec = {k: [v] for k, v in _madn_leaves(env, det).items()}
+    masks, actions, rewards, dones, kinds, obs, probs = [], [], [], [], [], [], []
+    t, extra = 0, 3
+    while t < cap and extra > 0:
+        if bool(np.asarray(env.done)):
+            extra -= 1
+        if not det:
+            probs.append(np.asarray(cm.dice_probabilities(env)))
+            env = cm.throw_die(env)
+        m = np.asarray(mod.valid_action(env)).astype(bool)
+        if t % OBS_STRIDE == 0:
+            obs.append(np.asarray(mod.encode_board(env)).astype(np.int8))
+        flat = m.reshape(-1)
+        arbitrary = rng.random() < 0.06
+        if flat.any() or arbitrary:
+            a = int(rng.integers(flat.size)) if (arbitrary or not flat.any()) else int(rng.choice(np.flatnonzero(flat)))
+            if det:
+                act = np.array([a // 6, a % 6 + 1], np.int8)
+                env, r, d = dm.env_step(env, jnp.array(act))
+            else:
+                act = np.array([a, 0], np.int8)
+                env, r, d = cm.env_step(env, jnp.array(a, dtype=jnp.int8))
+            kinds.append(1)
+        else:
+            act = np.array([-1, -1], np.int8)
+            env, r, d = mod.no_step(env)
+            kinds.append(0)
+        masks.append(m)
+        actions.append(act)
+        rewards.append(np.asarray(r))
+        dones.append(np.asarray(d))
+        for k, v in _madn_leaves(env, det).items():
+            rec[k].append(v)
+        t += 1
+    out = {f"state_{k}": np.stack(v) for k, v in rec.items()}
+    out.update(mask=np.stack(masks), action=np.stack(actions), reward=np.stack(rewards).astype(np.int8),
+               done=np.stack(dones).astype(bool), kind=np.array(kinds, np.int8), obs=np.stack(obs))
+    if not det:
+        out["dice_probs"] = np.stack(probs).astype(np.float32)
+    meta = dict(rules=rules, num_players=num_players, seed=seed, starting_player=sp, plies=t, kind=kind, from_state=kind != "full",
+                obs_stride=OBS_STRIDE)
+    return out, meta
+
+
+def madn_proxy_plies(g, meta):
+    if not meta["rules"]["enable_teams"] or meta["num_players"] != 4:
+        return 0
+    n = 0
+    for t in range(meta["plies"]):
+        if g["kind"][t] != 1 or g["state_done"][t]:
+            continue
+        cp = int(g["state_current_player"][t])
+        if (g["state_board"][t][40 + 4 * cp: 44 + 4 * cp] >= 0).all():
+            n += 1
+    return n
+
+
+def madn_tasks(det):
+    rng = np.random.default_rng(20261019 + int(det))
+    keys = list(MADN_TRAIN)
+    sets = [dict(MADN_TRAIN)] + [{k: bool(rng.integers(2)) for k in keys} for _ in range(5)]
+    sets[1]["enable_teams"], sets[2]["enable_teams"] = True, False
+    if not det:
+        for i, r in enumerate(sets):
+            r["enable_dice_rethrow"] = bool(i % 2 == 0)
+    tasks = []
+    for ri, rules in enumerate(sets):
+        for kind, num_players, reps in (("full", 4, 9), ("built", 4, 3), ("full", 2, 1), ("full", 3, 1)):
+            for _ in range(reps):
+                seed = int(rng.integers(0, 1_000_000))
+                sp = int(rng.integers(-1, num_players))
+                tasks.append((det, kind, rules, num_players, seed, sp, int(rng.integers(1 << 31)), CAP))
+    return tasks
+
+
+# --------------------------------------------------------------------------------------------------------------- main
+def save(name, results):
+    flat, metas = {}, []
+    for i, (g, m) in enumerate(results):
+        metas.append(m)
+        for k, v in g.items():
+            flat[f"g{i}_{k}"] = v
+    flat["meta"] = np.frombuffer(json.dumps(metas).encode(), dtype=np.uint8)
+    path = os.path.join(HERE, name)
+    np.savez_compressed(path, **flat)
+    return os.path.getsize(path)
+
+
+def report_dog(results):
+    rs = {}
+    cat = np.zeros((9, 2), np.int64)
+    for g, m in results:
+        key = json.dumps(m["rules"], sort_keys=True)
+        r = rs.setdefault(key, dict(games=0, done=0, plies=0, proxy=0, no_step=0))
+        r["games"] += 1
+        r["done"] += int(g["done"].any())
+        r["plies"] += m["plies"]
+        r["proxy"] += dog_proxy_plies(g, m)
+        r["no_step"] += int((g["kind"] == 0).sum())
+        for t in range(m["plies"]):
+            if g["kind"][t] == 1 and not g["state_done"][t]:
+                cat[_DOG_CAT_OF[g["action"][t]], int(g["reward"][t] == -1)] += 1
+    print("| DOG rule set | games | reach done | plies | team-proxy plies | no_step plies |\n|---|---|---|---|---|---|")
+    for k, r in rs.items():
+        on = ",".join(x.replace("enable_", "") for x, v in json.loads(k).items() if v)
+        print(f"| {on} | {r['games']} | {r['done']} | {r['plies']} | {r['proxy']} | {r['no_step']} |")
+    print("\n| DOG action category | valid steps | invalid steps (reward -1) |\n|---|---|---|")
+    for c, name in enumerate(DOG_CATS):
+        print(f"| {name} | {cat[c, 0]} | {cat[c, 1]} |")
+
+
+def report_madn(name, results):
+    rs = {}
+    for g, m in results:
+        key = json.dumps(m["rules"], sort_keys=True)
+        r = rs.setdefault(key, dict(games=0, done=0, plies=0, proxy=0, invalid=0))
+        r["games"] += 1
+        r["done"] += int(g["done"].any())
+        r["plies"] += m["plies"]
+        r["proxy"] += madn_proxy_plies(g, m)
+        r["invalid"] += int((g["reward"] == -1).sum())
+    print(f"| {name} MADN rule set | games | reach done | plies | team-proxy plies | invalid steps |\n|---|---|---|---|---|---|")
+    for k, r in rs.items():
+        on = ",".join(x.replace("enable_", "") for x, v in json.loads(k).items() if v)
+        print(f"| {on} | {r['games']} | {r['done']} | {r['plies']} | {r['proxy']} | {r['invalid']} |")
+
+
+def main():
+    which = [a for a in sys.argv[1:] if not a.startswith("--")] or ["det", "cls", "dog"]
+    import oracle as O
+    O.build()
+    with mp.Pool(os.cpu_count()) as pool:
+        for w in which:
+            t0 = time.time()
+            if w == "dog":
+                tasks = dog_tasks()
+                hits, todo = dog_cached(tasks) if "--no-cache" not in sys.argv else ({}, list(enumerate(tasks)))
+                fresh = pool.map(dog_game, [t for _, t in todo], chunksize=1)
+                for (i, _), r in zip(todo, fresh):
+                    hits[i] = r
+                res = dog_postprocess([hits[i] for i in range(len(tasks))])
+                size = save("dog_reference_endgames.npz", res)
+                report_dog(res)
+            else:
+                det = w == "det"
+                res = pool.map(madn_game, madn_tasks(det), chunksize=1)
+                size = save(f"madn_{w}_reference_endgames.npz", res)
+                report_madn(w, res)
+            print(f"[{w}] {len(res)} games, {sum(m['plies'] for _, m in res)} plies, {size / 1e6:.2f} MB, {time.time() - t0:.0f} s\n", flush=True)
+
+
+if __name__ == "__main__":
+    main()

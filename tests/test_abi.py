@@ -59,3 +59,20 @@ def test_cpu_tensors_fail_loudly():
     from exploring_muzero_on_dog_b200 import _lib
     with pytest.raises(_lib.DogstepError):
         _lib.ptr(torch.zeros(4))
+
+
+def test_entry_points_follow_the_device_of_their_pointers():
+    """_lib._Entry: pointers of two GPUs in one call raise; the device is read off tagged structs and device pointers"""
+    import pytest
+    from exploring_muzero_on_dog_b200 import _lib
+    a, b = _lib._DevPtr(16), _lib._DevPtr(32)
+    a.dev, b.dev = 0, 1
+    calls = []
+    e = _lib._Entry(lambda *args: calls.append(args) or 0, "fake")
+    with pytest.raises(_lib.DogstepError, match="different GPUs"):
+        e(a, b)
+    st = _lib.MadnDetState()
+    st.dev = 1
+    with pytest.raises(_lib.DogstepError, match="different GPUs"):
+        e(ctypes.byref(st), a)
+    assert e(ctypes.c_int64(3), None) == 0 and len(calls) == 1   # nothing device-side: passed straight through

@@ -1,0 +1,240 @@
+"""End-game goldens (tests/golden/gen_endgame_goldens.py: the REFERENCE's own MADN/*.py and DOG/dog.py run on the jaxshim,
+games that reach `done`, team-proxy plies, late / constructed positions, every action category) replayed through the C
+oracle (CPU) and through the CUDA path (GPU), bit-exact on every leaf, legal mask, reward and done of every ply.
+
+Games of one (rule set, player count) are replayed in lockstep as one batch: state[0] of each game is loaded (for `full`
+games it is first checked against env_reset), then per ply both env_step and no_step are evaluated and each game takes
+the branch its recording took; games whose recording has ended are ignored from then on.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle as O
+from helpers import mask_of
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+LEAVES = {
+    "det": ("board", "current_player", "pins", "reward", "done", "key", "action_set"),
+    "cls": ("board", "current_player", "pins", "reward", "done", "key", "die"),
+    "dog": ("board", "current_player", "pins", "reward", "done", "deck", "hands", "swap_choices", "round_starter", "phase", "key",
+            "hand_size"),
+}
+FILES = {"det": "madn_det_reference_endgames.npz", "cls": "madn_cls_reference_endgames.npz", "dog": "dog_reference_endgames.npz"}
+
+
+def _groups(env):
+    z = np.load(os.path.join(G, FILES[env]))
+    meta = json.loads(bytes(z["meta"]).decode())
+    groups = {}
+    for gi, m in enumerate(meta):
+        groups.setdefault((json.dumps(m["rules"], sort_keys=True), m["num_players"]), []).append(gi)
+    return z, meta, groups
+
+
+# ------------------------------------------------------------------------------------------------------------ backends
+class OracleBackend:
+    def __init__(self, env, rules, num_players):
+        self.env = env
+        self.cfg = (O.DogCfg if env == "dog" else O.MadnCfg)(num_players, 0xF, 10, mask_of(rules))
+
+    def reset(self, seed, sp):
+        if self.env == "dog":
+            return O.dog_reset(self.cfg, [seed], sp).fields()
+        return O.madn_reset(self.cfg, [seed], sp, det=self.env == "det").fields()
+
+    def load(self, leaves):
+        n = leaves["board"].shape[0]
+        s = O.DogState(self.cfg, n) if self.env == "dog" else O.MadnState(self.cfg, n, det=self.env == "det")
+        for k, v in leaves.items():
+            cur = getattr(s, k)
+            setattr(s, k, np.ascontiguousarray(np.asarray(v).astype(cur.dtype).reshape(cur.shape)))
+        self.s = s
+
+    def leaves(self):
+        return self.s.fields()
+
+    def throw_die(self):
+        p = O.madn_cls_dice_probabilities(self.s)
+        O.madn_cls_throw_die(self.s)
+        return p
+
+    def mask(self):
+        s = self.s
+        m = O.dog_valid_actions(s) if self.env == "dog" else (O.madn_det_valid_action(s) if self.env == "det" else O.madn_cls_valid_action(s))
+        return m.reshape(s.n, -1)
+
+    def obs(self):
+        return O.madn_det_encode_board(self.s) if self.env == "det" else O.madn_cls_encode_board(self.s)
+
+    def advance(self, kind, action):
+        """per game: env_step(action) where kind == 1, no_step where kind == 0 -> (reward, done)"""
+        a, b = self.s, self.s.copy()
+        if self.env == "dog":
+            ra, da = O.dog_step(a, action)
+            rb, db = O.dog_no_step(b)
+        elif self.env == "det":
+            ra, da = O.madn_det_step(a, action)
+            rb, db = O.madn_det_no_step(b)
+        else:
+            ra, da = O.madn_cls_step(a, action[:, 0])
+            rb, db = O.madn_cls_no_step(b)
+        st = kind == 1
+        for k in a.fields():
+            va, vb = getattr(a, k), getattr(b, k)
+            va[~st] = vb[~st]
+        return np.where(st, ra, rb), np.where(st, da, db)
+
+
+class CudaBackend:
+    def __init__(self, env, rules, num_players):
+        import torch
+        self.torch = torch
+        self.env, self.rules, self.num_players = env, rules, num_players
+        if env == "dog":
+            from exploring_muzero_on_dog_b200.DOG import dog as mod
+        elif env == "det":
+            from exploring_muzero_on_dog_b200.MADN import deterministic_madn as mod
+        else:
+            from exploring_muzero_on_dog_b200.MADN import classic_madn as mod
+        self.mod = mod
+
+    def _reset(self, seeds, sp):
+        return self.mod.env_reset(0, num_players=self.num_players, distance=10, starting_player=sp, seed=np.asarray(seeds, np.int32),
+                                  **self.rules)
+
+    def reset(self, seed, sp):
+        return {k: v for k, v in self._reset([seed], sp).numpy().items()}
+
+    def load(self, leaves):
+        n = leaves["board"].shape[0]
+        e = self._reset(np.zeros(n, np.int32), 0)
+        self.e = e.replace(**{k: (v.astype(np.int64) if v.dtype != np.uint32 else v) for k, v in leaves.items()})
+
+    def leaves(self):
+        return self.e.numpy()
+
+    def throw_die(self):
+        p = self.mod.dice_probabilities(self.e).cpu().numpy()
+        self.mod.throw_die(self.e, inplace=True)
+        return p
+
+    def mask(self):
+        m = self.mod.valid_actions(self.e) if self.env == "dog" else self.mod.valid_action(self.e)
+        return m.reshape(self.e.n, -1).cpu().numpy()
+
+    def obs(self):
+        return self.mod.encode_board(self.e).cpu().numpy()
+
+    def advance(self, kind, action):
+        torch, mod, e = self.torch, self.mod, self.e
+        act = action if self.env != "cls" else action[:, 0]
+        a, ra, da = mod.env_step(e, act)          # the pure API: e itself is untouched
+        b, rb, db = mod.no_step(e)
+        st = torch.as_tensor(kind == 1, device=e.device)
+        upd = {}
+        for k in a._t:
+            va, vb = a.raw(k), b.raw(k)
+            upd[k] = torch.where(st.reshape((-1,) + (1,) * (va.dim() - 1)), va, vb)
+        self.e = e.replace(**upd)
+        return torch.where(st, ra, rb).cpu().numpy(), torch.where(st, da, db).cpu().numpy()
+
+
+# ------------------------------------------------------------------------------------------------------------ replayer
+def replay(env, backend_cls, obs_every=1):
+    z, meta, groups = _groups(env)
+    names = LEAVES[env]
+    stats = dict(plies=0, done_games=0, games=len(meta))
+    for (rules_json, num_players), gis in groups.items():
+        rules = json.loads(rules_json)
+        be = backend_cls(env, rules, num_players)
+        for gi in gis:  # games recorded from env_reset: the reset itself is part of the pin
+            m = meta[gi]
+            if not m["from_state"]:
+                got = be.reset(m["seed"], m["starting_player"])
+                for k in names:
+                    assert np.array_equal(np.asarray(got[k][0]).astype(np.int64), z[f"g{gi}_state_{k}"][0].astype(np.int64)), \
+                        f"{env} reset: game {gi} leaf {k}"
+        plies = np.array([meta[gi]["plies"] for gi in gis])
+        st = {k: [z[f"g{gi}_state_{k}"] for gi in gis] for k in names}
+        rec = {k: [z[f"g{gi}_{k}"] for gi in gis] for k in ("mask", "action", "reward", "done", "kind")}
+        be.load({k: np.stack([st[k][j][0] for j in range(len(gis))]) for k in names})
+        nact = 806 if env == "dog" else (24 if env == "det" else 4)
+        for t in range(int(plies.max())):
+            live = np.flatnonzero(plies > t)
+            if env == "cls":
+                p = be.throw_die()
+                for j in live:
+                    assert np.array_equal(p[j], z[f"g{gis[j]}_dice_probs"][t]), f"cls dice_probabilities: game {gis[j]} ply {t}"
+            mask = be.mask()
+            for j in live:
+                exp = rec["mask"][j][t]
+                exp = np.unpackbits(exp)[:nact].astype(bool) if env == "dog" else exp.reshape(-1)
+                if not np.array_equal(mask[j], exp):
+                    diff = np.flatnonzero(mask[j] != exp)
+                    raise AssertionError(f"{env} mask: game {gis[j]} ply {t} differs at actions {diff[:10].tolist()}")
+            if env != "dog" and t % (meta[gis[0]]["obs_stride"] * obs_every) == 0:
+                obs = be.obs()
+                for j in live:
+                    assert np.array_equal(obs[j], z[f"g{gis[j]}_obs"][t // meta[gis[j]]["obs_stride"]]), f"{env} obs: game {gis[j]} ply {t}"
+            kind = np.array([rec["kind"][j][t] if plies[j] > t else 0 for j in range(len(gis))])
+            if env == "dog":
+                action = np.array([max(int(rec["action"][j][t]), 0) if plies[j] > t else 0 for j in range(len(gis))], np.int32)
+            else:
+                action = np.stack([np.maximum(rec["action"][j][t], 0) if plies[j] > t else np.zeros(2, np.int8) for j in range(len(gis))]).astype(np.int8)
+            r, d = be.advance(kind, action)
+            got = be.leaves()
+            for j in live:
+                assert int(r[j]) == int(rec["reward"][j][t]) and bool(d[j]) == bool(rec["done"][j][t]), \
+                    f"{env} reward/done: game {gis[j]} ply {t}: got {int(r[j])}/{bool(d[j])} want {int(rec['reward'][j][t])}/{bool(rec['done'][j][t])}"
+                for k in names:
+                    a, b = np.asarray(got[k][j]).astype(np.int64), st[k][j][t + 1].astype(np.int64)
+                    assert np.array_equal(a, b), f"{env} step: game {gis[j]} ply {t} leaf {k}: got {a.tolist()} want {b.tolist()}"
+            stats["plies"] += len(live)
+        stats["done_games"] += sum(bool(rec["done"][j].any()) for j in range(len(gis)))
+    return stats
+
+
+def _proxy_plies(env):
+    """plies stepped by a player whose own goal lane was full (the mover acts for the partner)"""
+    z, meta, _ = _groups(env)
+    n = 0
+    for gi, m in enumerate(meta):
+        if not m["rules"]["enable_teams"] or m["num_players"] != 4:
+            continue
+        board, cp, kind, done = z[f"g{gi}_state_board"], z[f"g{gi}_state_current_player"], z[f"g{gi}_kind"], z[f"g{gi}_state_done"]
+        for t in range(m["plies"]):
+            if kind[t] == 1 and not done[t] and (env != "dog" or z[f"g{gi}_state_phase"][t] == 0):
+                c = int(cp[t])
+                n += int((board[t][40 + 4 * c: 44 + 4 * c] >= 0).all())
+    return n
+
+
+MIN_PLIES = {"det": 30000, "cls": 30000, "dog": 8000}
+
+
+@pytest.mark.parametrize("env", ["det", "cls", "dog"])
+def test_goldens_cover_termination_and_team_proxy(env):
+    """what the file is FOR: every rule set has >= 10 games that reach done; >= 200 team-proxy plies"""
+    z, meta, groups = _groups(env)
+    per_rules = {}
+    for gi, m in enumerate(meta):
+        k = json.dumps(m["rules"], sort_keys=True)
+        per_rules[k] = per_rules.get(k, 0) + int(z[f"g{gi}_done"].any())
+    assert len(per_rules) >= 5 and min(per_rules.values()) >= 10, per_rules
+    assert _proxy_plies(env) >= 200
+
+
+@pytest.mark.parametrize("env", ["det", "cls", "dog"])
+def test_oracle_reproduces_reference_endgames(env):
+    s = replay(env, OracleBackend)
+    assert s["plies"] >= MIN_PLIES[env] and s["done_games"] >= 50
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("env", ["det", "cls", "dog"])
+def test_cuda_reproduces_reference_endgames(env):
+    s = replay(env, CudaBackend, obs_every=4)
+    assert s["plies"] >= MIN_PLIES[env] and s["done_games"] >= 50

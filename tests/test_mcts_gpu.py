@@ -123,6 +123,75 @@ def test_cuda_search_equals_oracle(case):
     assert (vc.sum(1) == S).all() and (vc[:, :A][invalid.astype(bool)] == 0).all()
 
 
+class WideNet:
+    """stand-in network for the real-shape cases (no per-action [E, E] matrices: A x E x E would not fit at E = 258)"""
+
+    def __init__(self, A, Cn, E, seed):
+        g = torch.Generator(device="cuda").manual_seed(seed)
+        self.Wd = torch.randn(E, E, device="cuda", generator=g) * (1.6 / E ** 0.5)
+        self.Wa = torch.randn(A + Cn, E, device="cuda", generator=g)
+        self.P = torch.randn(E, A, device="cuda", generator=g) * (2.0 / E ** 0.5)
+        self.Pc = torch.randn(E, max(Cn, 1), device="cuda", generator=g) * (2.0 / E ** 0.5)
+
+    def __call__(self, action, emb):
+        nxt = torch.tanh(emb @ self.Wd + self.Wa[action])
+        return dict(prior=nxt @ self.P, value=torch.tanh(nxt[:, :8].sum(1)), reward=0.1 * nxt[:, 0],
+                    discount=torch.where(nxt[:, 1] > 0, 1.0, -1.0), emb=nxt, chance=nxt @ self.Pc)
+
+
+REAL_SHAPES = [
+    # (policy, qtransform, A, C, E, sims, depth, games)
+    (2, 1, 4, 6, 258, 64, 50, 4096),    # BASELINE config 3: stochastic MuZero, 4,096 games x 64 sims, embedding 258 (two warp_copy passes)
+    (1, 2, 806, 0, 256, 100, 50, 1024), # BASELINE config 5: Gumbel over DOG's 806 actions, 100 sims, latent 256 (select cache path)
+    (1, 2, 24, 0, 256, 100, 50, 2048),  # det MADN run_muzero_mcts at training shape
+]
+
+
+@pytest.mark.parametrize("case", REAL_SHAPES, ids=lambda c: "-".join(str(x) for x in c))
+def test_cuda_search_equals_oracle_at_real_shapes(case):
+    """the BASELINE shapes, through the PRODUCTION launch sequence (select(0), then expand_select fused launches, a final expand):
+    parent / action of every simulation, every tree array and the policy output bit-equal to the oracle"""
+    from exploring_muzero_on_dog_b200 import mcts
+    policy, qt, A, Cn, E, S, depth, n = case
+    ccfg, ocfg = _mk_cfgs(policy, qt, S, depth, A, Cn, E, dirichlet_fraction=0.25)
+    rng = np.random.default_rng(77 + A)
+    keys = rng.integers(0, 2**32, (n, 2), dtype=np.uint64).astype(np.uint32)
+    prior = rng.standard_normal((n, A)).astype(np.float32) * 2
+    value = rng.uniform(-1, 1, n).astype(np.float32)
+    emb = rng.standard_normal((n, E)).astype(np.float32)
+    invalid = (rng.random((n, A)) < 0.5).astype(np.uint8)
+    invalid[np.arange(n), rng.integers(0, A, n)] = 0
+    noise = rng.dirichlet(np.full(A, 0.3), n).astype(np.float32)
+    net = WideNet(A, Cn, E, 11)
+    s = mcts.Search(ccfg, n)
+    dev = lambda x: torch.as_tensor(x, device="cuda")
+    s.init(torch.from_numpy(keys).cuda(), mcts.RootFnOutput(dev(prior), dev(value), dev(emb)), dev(invalid), dev(noise))
+    otree = O.MctsTree(ocfg, n)
+    O.mcts_init(otree, keys, prior, value, emb, invalid, noise)
+    parent, action, pemb, _ = s.select(0)
+    for sim in range(S):
+        op, oa, oemb, _ = O.mcts_select(otree, sim)
+        assert np.array_equal(parent.cpu().numpy(), op), f"parent differs at sim {sim}"
+        assert np.array_equal(action.cpu().numpy(), oa), f"action differs at sim {sim}: games {np.flatnonzero(action.cpu().numpy() != oa)[:5].tolist()}"
+        assert np.array_equal(pemb.cpu().numpy().view(np.int32), oemb.view(np.int32)), f"embedding differs at sim {sim}"
+        o = net(action.long().clamp(0, A + Cn - 1), pemb)
+        h = {k: v.float().contiguous().cpu().numpy() for k, v in o.items()}
+        step = s.expand_select if sim + 1 < S else s.expand
+        if policy == 2:
+            step(sim, o["prior"], o["value"], o["reward"], o["discount"], o["emb"], o["chance"], o["value"], o["emb"])
+            O.mcts_expand(otree, sim, op, oa, h["prior"], h["value"], h["reward"], h["discount"], h["emb"], h["chance"], h["value"], h["emb"])
+        else:
+            step(sim, o["prior"], o["value"], o["reward"], o["discount"], o["emb"])
+            O.mcts_expand(otree, sim, op, oa, h["prior"], h["value"], h["reward"], h["discount"], h["emb"])
+    _compare_trees(s, otree, "after search")
+    out, root_value = s.policy_output()
+    oact, ow, ov = O.mcts_policy_output(otree)
+    assert np.array_equal(out.action.cpu().numpy(), oact)
+    assert np.array_equal(out.action_weights.cpu().numpy().view(np.int32), ow.view(np.int32))
+    assert np.array_equal(root_value.cpu().numpy().view(np.int32), ov.view(np.int32))
+    assert (s.tree.children_visits[:, 0].sum(1) == S).all()
+
+
 def test_mctx_shaped_policies_run():
     """the drop-in wrappers (same names / kwargs as mctx) on a torch recurrent_fn"""
     import functools

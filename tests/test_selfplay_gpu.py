@@ -170,3 +170,89 @@ def test_dog_selfplay_with_gumbel_search_plays_legal_moves():
             cur[live & has] = getattr(stepped, f)[live & has]
             cur[live & ~has] = getattr(skipped, f)[live & ~has]
     assert_state_equal(s, envs.numpy())
+
+
+def test_split_chain_equals_host_key_chain():
+    """dogstep_random_split_chain: rng_key, *step_keys = split(rng_key, n + 1) with the loop key on the device"""
+    import ctypes as C
+    from exploring_muzero_on_dog_b200 import _lib, jaxrand
+    n = 1000
+    key = jaxrand.split_host(jaxrand.PRNGKey(42))[1]
+    dkey = torch.from_numpy(key.copy()).cuda()
+    out = torch.empty((n, 2), dtype=torch.uint32, device="cuda")
+    for it in range(5):
+        _lib.check(_lib.lib().dogstep_random_split_chain(_lib.ptr(dkey), C.c_int64(n), _lib.ptr(out), _lib.stream()), "split_chain")
+        exp = O.split(key, n + 1)
+        assert np.array_equal(out.cpu().numpy(), exp[1:]) and np.array_equal(dkey.cpu().numpy(), exp[0])
+        key = exp[0]
+
+
+@pytest.mark.parametrize("env_kind", ["det", "cls", "dog"])
+def test_graph_replayed_loop_equals_eager_loop_and_oracle(env_kind):
+    """SelfPlayLoop with cuda_graph=True (one captured iteration replayed, lagging termination poll, run twice on the same
+    buffers) == the eager loop == the NumPy restatement, with a capturable device-side stand-in for the search"""
+    from helpers import DOG_RULES
+    from exploring_muzero_on_dog_b200 import game_agent, jaxrand
+    from exploring_muzero_on_dog_b200.DOG import dog as dg
+    from exploring_muzero_on_dog_b200.MADN import classic_madn as cm, deterministic_madn as dm
+    n = 96
+    max_steps = {"det": 120, "cls": 120, "dog": 260}[env_kind]
+    key = jaxrand.split_host(jaxrand.PRNGKey(17))[1]
+    seeds = O.randint(key, n, 0, 1_000_000)
+    if env_kind == "dog":
+        rules, mod, A, shape = DOG_RULES, dg, 806, (dg.RAW_OBS_SIZE,)
+        ocfg = O.DogCfg(4, 0xF, 10, mask_of(rules))
+    else:
+        rules = dict(TRAIN_RULES, **({} if env_kind == "det" else {"enable_dice_rethrow": True}))
+        mod, A, shape = (dm, 24, (34, 56)) if env_kind == "det" else (cm, 4, (11, 56))
+        ocfg = O.MadnCfg(4, 0xF, 10, mask_of(rules))
+    ar = np.arange(A, dtype=np.int64)
+
+    def host_fn(step_keys, obs, invalid):  # integer hash of the step key: exact on both sides
+        h = (step_keys[:, 0].astype(np.int64) * 7 + step_keys[:, 1].astype(np.int64)) % 1000003
+        score = (h[:, None] + ar[None, :] * 40503) % 1009
+        score[invalid] = -1
+        action = score.argmax(1).astype(np.int32)
+        w = np.where(invalid, 0.0, 1.0).astype(np.float32)
+        w = w / np.maximum(w.sum(1, keepdims=True), 1)
+        value = ((h % 2001).astype(np.float32) / np.float32(1000.0) - np.float32(1.0)).astype(np.float32)
+        return action, w.astype(np.float32), value
+
+    ar_d = torch.arange(A, device="cuda", dtype=torch.int64)
+
+    def dev_fn(params, step_keys, obs, invalid):
+        k = step_keys.to(torch.int64)
+        h = (k[:, 0] * 7 + k[:, 1]) % 1000003
+        score = (h[:, None] + ar_d[None, :] * 40503) % 1009
+        score = torch.where(invalid, torch.full_like(score, -1), score)
+        action = score.argmax(1).to(torch.int32)
+        w = (~invalid).to(torch.float32)
+        w = w / w.sum(1, keepdim=True).clamp(min=1)
+        value = (h % 2001).to(torch.float32) / 1000.0 - 1.0
+        return action, w, value
+
+    def reset(out=None):
+        return mod.env_reset(0, seed=seeds, out=out, **rules)
+
+    if env_kind == "dog":
+        s = O.dog_reset(ocfg, seeds, 0)
+        exp = selfplay_oracle.play_batch_of_games_dog(s, max_steps, key, host_fn, teams=True)
+    else:
+        s = O.madn_reset(ocfg, seeds, 0, det=env_kind == "det")
+        exp = selfplay_oracle.play_batch_of_games(s, max_steps, key, host_fn, teams=True)
+    eager_env = reset()
+    eager = game_agent.play_batch_of_games(eager_env, n, shape, None, key, 0, 0, max_steps, 1.0, search_fn=dev_fn)
+    assert_state_equal(s, eager_env.numpy())
+    for k, v in exp.items():
+        assert np.array_equal(eager[k].cpu().numpy(), v), ("eager", k)
+    genv = reset()
+    loop = game_agent.SelfPlayLoop(genv, n, shape, None, max_steps, search_fn=dev_fn, cuda_graph=True, lookahead=3)
+    for rep in range(2):  # the second run reuses the buffers and the captured graph on the re-seeded env
+        if rep:
+            reset(out=genv)
+        got = loop.run(key)
+        assert_state_equal(s, genv.numpy())
+        for k, v in exp.items():
+            assert np.array_equal(got[k].cpu().numpy(), v), ("graph", rep, k)
+        assert loop.iterations == int(exp["idx"].max()) or not s.done.all()
+        assert loop.enqueued <= min(max_steps, loop.iterations + 2 * 3 + 1)
