@@ -57,11 +57,14 @@ def _profile_facts():
 
 class ClockSampler:
     """SM clock / throttle reasons read through NVML DURING the timed regions (same fields as the nvidia-smi line of
-    B200_PROFILING.md).  Sampled from the main thread while the device works through its queue — no sampler thread: a Python
-    thread waking every few ms takes the GIL from the thread that enqueues the steps (round 1's N = 8 e2e outlier)."""
+    B200_PROFILING.md), from a helper thread (pynvml is ctypes: the GIL is released inside a call).  Inline sampling from the
+    enqueuing thread was measured and dropped: the first NVML query after the GPU leaves idle blocks for ~30 ms (seen in both
+    timed regions), which then sits inside an e2e step.  Period 5 ms; the slowest call is reported (`nvml_call_ms_max`)."""
 
-    def __init__(self, index):
-        self.rows = []
+    def __init__(self, index, period=0.005):
+        import threading
+        self.rows, self.period, self._stop, self.th, self.slowest = [], period, False, None, 0.0
+        self._threading = threading
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -69,25 +72,35 @@ class ClockSampler:
             vis = os.environ.get("CUDA_VISIBLE_DEVICES")
             phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
             self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
         except Exception:
             self.nv = None
 
-    def sample(self):
-        nv = self.nv
-        if nv is None:
-            return
-        try:
-            self.rows.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM),
-                              nv.nvmlDeviceGetCurrentClocksEventReasons(self.h), nv.nvmlDeviceGetPowerUsage(self.h) / 1e3))
-        except Exception:
-            pass
+    def start(self):
+        if self.nv is not None:
+            self.th = self._threading.Thread(target=self._run, daemon=True)
+            self.th.start()
 
-    def sample_until(self, event, period=0.001):
-        while not event.query():
-            self.sample()
-            time.sleep(period)
+    def _run(self):
+        nv = self.nv
+        while not self._stop:
+            t0 = time.perf_counter()
+            try:
+                self.rows.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM), self.max_mhz,
+                                  nv.nvmlDeviceGetCurrentClocksEventReasons(self.h), nv.nvmlDeviceGetPowerUsage(self.h) / 1e3))
+            except Exception:
+                pass
+            self.slowest = max(self.slowest, 1e3 * (time.perf_counter() - t0))
+            time.sleep(self.period)
+
+    def clear(self):
+        self.rows.clear()
+        self.slowest = 0.0
 
     def result(self):
+        self._stop = True
+        if self.th:
+            self.th.join(timeout=1)
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         nv = self.nv
@@ -95,7 +108,8 @@ class ClockSampler:
                  "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
         reasons = sorted(k for k, bit in names.items() if any(r[2] & bit for r in self.rows))
         return {"sm_mhz": statistics.median(r[0] for r in self.rows), "sm_max_mhz": max(r[1] for r in self.rows),
-                "reasons": reasons, "samples": len(self.rows), "power_w_max": max(r[3] for r in self.rows)}
+                "reasons": reasons, "samples": len(self.rows), "power_w_max": max(r[3] for r in self.rows),
+                "nvml_call_ms_max": round(self.slowest, 2)}
 
 
 def pin_cores(local, world):
@@ -155,37 +169,46 @@ class StandInNet:
         self.Wr = rnd(obs_size, E) * (1.0 / obs_size ** 0.5)
         self.Wd, self.Wa = rnd(E, E) * (1.2 / E ** 0.5), rnd(A + chance, E)
         self.Wp, self.Wc = rnd(E, A) * (2.0 / E ** 0.5), rnd(E, max(chance, 1)) * (2.0 / E ** 0.5)
-        self.n = n
+        self.n, self.ones = n, torch.ones(n, device=dev)
+        self.after = torch.zeros((n, E + 2), device=dev)
 
     def root(self, params, obs):
         import torch
         from exploring_muzero_on_dog_b200 import mcts
         e = torch.tanh(obs.reshape(obs.shape[0], -1).float() @ self.Wr)
-        return mcts.RootFnOutput(e @ self.Wp, torch.tanh(e[:, 0] + e[:, 1]), e)
+        return mcts.RootFnOutput(e @ self.Wp, torch.tanh(e[:, 0]), e)
+
+    def _heads(self, e):
+        import torch
+        return 0.1 * e[:, 0], torch.copysign(self.ones, e[:, 1]), torch.tanh(e[:, 2])   # reward, discount (+-1), value
 
     def recurrent(self, params, rng, action, emb):
         import torch
         from exploring_muzero_on_dog_b200 import mcts
         e = torch.tanh(torch.addmm(self.Wa[action], emb, self.Wd))
-        return mcts.RecurrentFnOutput(0.1 * e[:, 0], torch.where(e[:, 1] > 0, 1.0, -1.0), e @ self.Wp, torch.tanh(e[:, 2] + e[:, 3])), e
+        r, d, v = self._heads(e)
+        return mcts.RecurrentFnOutput(r, d, e @ self.Wp, v), e
 
     # stochastic MuZero: afterstate embedding = [latent | reward | discount] like the reference (muzero_classic_madn.py:415-424)
     def decision(self, params, rng, action, emb):
         import torch
         from exploring_muzero_on_dog_b200 import mcts
-        e = torch.tanh(torch.addmm(self.Wa[action], emb, self.Wd))
-        after = torch.cat([e, 0.1 * e[:, :1], torch.where(e[:, 1:2] > 0, 1.0, -1.0)], 1)
-        return mcts.DecisionRecurrentFnOutput(e @ self.Wc, torch.tanh(e[:, 2] + e[:, 3])), after
+        E = self.E
+        after = self.after                                     # preallocated [n, E + 2]
+        torch.tanh(torch.addmm(self.Wa[action], emb, self.Wd), out=after[:, :E])
+        e = after[:, :E]
+        after[:, E] = 0.1 * e[:, 0]
+        torch.copysign(self.ones, e[:, 1], out=after[:, E + 1])
+        return mcts.DecisionRecurrentFnOutput(e @ self.Wc, torch.tanh(e[:, 2])), after
 
     def chance(self, params, rng, outcome, after):
         import torch
         from exploring_muzero_on_dog_b200 import mcts
         E = self.E
         e = torch.tanh(torch.addmm(self.Wa[outcome + self.A], after[:, :E], self.Wd))
-        return mcts.ChanceRecurrentFnOutput(e @ self.Wp, torch.tanh(e[:, 0] - e[:, 1]), after[:, E], after[:, E + 1]), e
+        return mcts.ChanceRecurrentFnOutput(e @ self.Wp, torch.tanh(e[:, 0]), after[:, E], after[:, E + 1]), e
 
 
-# ------------------------------------------------------------------------------------------------ self-play (sims/s)
 def _gather_ranks(dev, world, my_ms, my_units):
     """-> (max ms over ranks, units summed over ranks, per-rank ms list)"""
     import torch
@@ -201,102 +224,167 @@ def _gather_ranks(dev, world, my_ms, my_units):
     return max(per), int(c.item()), per
 
 
-def selfplay_cfg3(dev, rank, world, plies_cap=128):
-    """BASELINE config 3 as a self-play loop (MuZero_Classic_MADN/game_agent_stochastic.py:52-244): 4,096 dice-MADN games per
-    GPU, throw_die -> encode_board -> valid_action -> run_stochastic_muzero_mcts(64 sims, max_depth 50) -> env_step, whole
-    iteration replayed as one CUDA graph, no host synchronisation per iteration."""
+class PrecomputedNet:
+    """callbacks that launch NOTHING: they hand back preallocated random tensors (R sets, cycled).  The loop then costs what the
+    path itself costs — env, observation, legal mask, tree kernels, trajectory rows — which is what `vs_tree_only` is about."""
+
+    def __init__(self, dev, A, E, n, seed=0, chance=0, R=4):
+        import torch
+        g = torch.Generator(device=dev).manual_seed(seed)
+        rnd = lambda *shape: torch.randn(*shape, device=dev, generator=g)
+        self.R, self.k, self.A, self.E = R, 0, A, E
+        self.prior, self.emb = [rnd(n, A) for _ in range(R)], [rnd(n, E) for _ in range(R)]
+        self.val, self.rew = [torch.tanh(rnd(n)) for _ in range(R)], [0.1 * rnd(n) for _ in range(R)]
+        self.disc = [torch.where(rnd(n) > 0, 1.0, -1.0) for _ in range(R)]
+        self.chance = [rnd(n, max(chance, 1)) for _ in range(R)]
+        self.after = [rnd(n, E + 2) for _ in range(R)]
+
+    def _next(self):
+        self.k = (self.k + 1) % self.R
+        return self.k
+
+    def root(self, params, obs):
+        from exploring_muzero_on_dog_b200 import mcts
+        return mcts.RootFnOutput(self.prior[0], self.val[0], self.emb[0])
+
+    def recurrent(self, params, rng, action, emb):
+        from exploring_muzero_on_dog_b200 import mcts
+        k = self._next()
+        return mcts.RecurrentFnOutput(self.rew[k], self.disc[k], self.prior[k], self.val[k]), self.emb[k]
+
+    def decision(self, params, rng, action, emb):
+        from exploring_muzero_on_dog_b200 import mcts
+        k = self._next()
+        return mcts.DecisionRecurrentFnOutput(self.chance[k], self.val[k]), self.after[k]
+
+    def chance_fn(self, params, rng, outcome, after):
+        from exploring_muzero_on_dog_b200 import mcts
+        k = self.k
+        return mcts.ChanceRecurrentFnOutput(self.prior[k], self.val[(k + 1) % self.R], self.rew[k], self.disc[k]), self.emb[k]
+
+
+def make_selfplay(which, dev, rank, world, cuda_graph=True, plies=None, net="standin"):
+    """-> (SelfPlayLoop, loop key, reseed()) for BASELINE config 3 or 5 on this rank's shard of the games"""
+    import functools
     import torch
-    from exploring_muzero_on_dog_b200 import game_agent, jaxrand
+    from exploring_muzero_on_dog_b200 import game_agent, jaxrand, mcts
+    from exploring_muzero_on_dog_b200.DOG import dog as dg
     from exploring_muzero_on_dog_b200.MADN import classic_madn as cm
-    n, S, A, Cn, E = 4096, 64, 4, 6, 256
-    net = StandInNet(dev, 11 * 56, A, E, n, seed=3, chance=Cn)
     key = jaxrand.split_host(jaxrand.PRNGKey(0))[1]
-    all_seeds = jaxrand.randint(key, n * world, 0, 1_000_000, device=dev)
-    seeds = all_seeds[rank * n:(rank + 1) * n].contiguous()
-    envs = cm.env_reset(0, seed=seeds, device=dev, **game_agent.STOCHASTIC_RULES)
-    noise = torch.distributions.Dirichlet(torch.full((A,), 0.3, device=dev)).sample((n,))  # root noise sample: an input (DESIGN 5)
+    if which == "cfg3":
+        n, S, A, Cn, E = 4096, 64, 4, 6, 256
+        plies = plies or 128
+        seeds = jaxrand.randint(key, n * world, 0, 1_000_000, device=dev)[rank * n:(rank + 1) * n].contiguous()
+        reset = lambda out=None: cm.env_reset(0, seed=seeds, device=dev, out=out, **game_agent.STOCHASTIC_RULES)
+        envs = reset()
+        noise = torch.distributions.Dirichlet(torch.full((A,), 0.3, device=dev)).sample((n,))  # root noise sample: an input (DESIGN 5)
+        nn = StandInNet(dev, 11 * 56, A, E, n, seed=3, chance=Cn) if net == "standin" else PrecomputedNet(dev, A, E, n, seed=3, chance=Cn)
+        dec, ch = (nn.decision, nn.chance) if net == "standin" else (nn.decision, nn.chance_fn)
 
-    def search_fn(p, keys, obs, invalid):
-        key2 = game_agent._split_each(keys, 1)
-        out, rv = game_agent.run_stochastic_muzero_mcts(p, key2, obs, invalid, S, 50, 1.0, root_fn=net.root,
-                                                        decision_recurrent_fn=net.decision, chance_recurrent_fn=net.chance,
-                                                        dirichlet_noise=noise)
-        return out.action, out.action_weights, rv
+        def search_fn(p, keys, obs, invalid):
+            key2 = game_agent._split_each(keys, 1)
+            out, rv = game_agent.run_stochastic_muzero_mcts(p, key2, obs, invalid, S, 50, 1.0, root_fn=nn.root, decision_recurrent_fn=dec,
+                                                            chance_recurrent_fn=ch, dirichlet_noise=noise)
+            return out.action, out.action_weights, rv
 
-    loop = game_agent.SelfPlayLoop(envs, n, (11, 56), None, plies_cap, search_fn=search_fn, obs_dtype=torch.int8, cuda_graph=True)
+        loop = game_agent.SelfPlayLoop(envs, n, (11, 56), None, plies, search_fn=search_fn, obs_dtype=torch.int8, cuda_graph=cuda_graph)
+    else:
+        n, S, A, E = 8192, 100, 806, 256
+        plies = plies or 64
+        seeds = jaxrand.randint(key, n * world, 0, 1_000_000, device=dev)[rank * n:(rank + 1) * n].contiguous()
+        reset = lambda out=None: dg.env_reset(0, seed=seeds, device=dev, out=out, **DOG_RULES)
+        envs = reset()
+        nn = StandInNet(dev, dg.RAW_OBS_SIZE, A, E, n, seed=5) if net == "standin" else PrecomputedNet(dev, A, E, n, seed=5)
+
+        def search_fn(p, keys, obs, invalid):
+            key2 = game_agent._split_each(keys, 1)
+            out = mcts.gumbel_muzero_policy(p, key2, nn.root(p, obs), nn.recurrent, S, invalid_actions=invalid, max_depth=50,
+                                            qtransform=functools.partial(mcts.qtransform_completed_by_mix_value, value_scale=0.5),
+                                            gumbel_scale=1.0, max_num_considered_actions=16)
+            return out.action, out.action_weights, out.search_tree.summary().value
+
+        loop = game_agent.SelfPlayLoop(envs, n, (dg.RAW_OBS_SIZE,), None, plies, search_fn=search_fn, obs_dtype=torch.int8,
+                                       cuda_graph=cuda_graph)
+    loop.reseed = lambda: reset(out=envs)
+    loop.shape = dict(n=n, S=S, A=A, E=E)
+    return loop, key
+
+
+def _run_selfplay(which, dev, rank, world, net, plies=None):
+    import torch
+    loop, key = make_selfplay(which, dev, rank, world, cuda_graph=True, plies=plies, net=net)
+    cap = loop.max_steps
     loop.max_steps = 3
     loop.run(key)                                           # untimed: graph capture + first replays
-    loop.max_steps = plies_cap
-    cm.env_reset(0, seed=seeds, device=dev, out=envs, **game_agent.STOCHASTIC_RULES)
+    loop.max_steps = cap
+    loop.reseed()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     buf = loop.run(key)
     e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    plies = loop.enqueued
-    sims = n * plies * S
-    max_ms, all_sims, per = _gather_ranks(dev, world, ms, sims)
-    searched = int((buf["mask"] > 0).sum().item())
-    return {"workload": f"cfg3 self-play: 4,096 dice-MADN games per GPU x 64 sims per move (stochastic MuZero, A=4+6, latent {E}, stand-in "
-                        f"network), {plies} lockstep iterations (cap {plies_cap}); one CUDA graph per iteration, no host sync",
-            "sims": all_sims, "ms": max_ms, "sims_per_s": all_sims / (max_ms / 1e3), "per_rank_ms": per, "iterations": plies,
-            "iterations_needed": loop.iterations, "searched_moves_rank0": searched, "env_steps_rank0": int(buf["idx"].sum().item()),
-            "gpu_launches_per_iteration": "1 graph replay (init, 64 x (tree kernel + network), policy, agent step)"}
+    return loop, key, buf, e0.elapsed_time(e1)
+
+
+def selfplay_cfg3(dev, rank, world, plies_cap=128):
+    """BASELINE config 3 as a self-play loop (MuZero_Classic_MADN/game_agent_stochastic.py:52-244): 4,096 dice-MADN games per
+    GPU, throw_die -> encode_board -> valid_action -> run_stochastic_muzero_mcts(64 sims, max_depth 50) -> env_step, whole
+    iteration replayed as one CUDA graph, no host synchronisation per iteration."""
+    out = {}
+    for net in ("standin", "precomputed"):
+        loop, key, buf, ms = _run_selfplay("cfg3", dev, rank, world, net, plies_cap)
+        n, S, E = loop.shape["n"], loop.shape["S"], loop.shape["E"]
+        plies = loop.enqueued
+        max_ms, all_sims, per = _gather_ranks(dev, world, ms, n * plies * S)
+        r = {"sims": all_sims, "ms": max_ms, "sims_per_s": all_sims / (max_ms / 1e3), "per_rank_ms": per, "iterations": plies,
+             "iterations_needed": loop.iterations, "searched_moves_rank0": int((buf["mask"] > 0).sum().item()),
+             "env_steps_rank0": int(buf["idx"].sum().item())}
+        if net == "standin":
+            out = dict({"workload": f"cfg3 self-play: 4,096 dice-MADN games per GPU x 64 sims per move (stochastic MuZero, A=4+6, latent {E}, "
+                                    f"stand-in network), {plies} lockstep iterations (cap {plies_cap}); one CUDA graph per iteration, no host sync"},
+                       **r, gpu_launches_per_iteration="1 graph replay (key split, throw_die, encode, mask, root net, init, 64 x (tree kernel + network), policy, agent step)")
+        else:
+            out["path_only"] = dict(r, note="same loop with callbacks that launch nothing (precomputed network outputs): the cost of the path itself")
+        del loop, buf
+    return out
 
 
 def selfplay_cfg5(dev, rank, world, plies=64, with_exchange=True):
     """BASELINE config 5: 8,192 DOG games per GPU x 100 Gumbel simulations over 806 actions (latent 256), the det-MADN loop shape
     (MuZero_det_MADN/game_agent.py:50-192) on DOG/dog.py, then the replay shard: save, sample, and the all-gathered global batch."""
     import torch
-    import torch.distributed as dist
-    from exploring_muzero_on_dog_b200 import game_agent, jaxrand, vec_replay_buffer
+    from exploring_muzero_on_dog_b200 import vec_replay_buffer
     from exploring_muzero_on_dog_b200.DOG import dog as dg
-    n, S, A, E = 8192, 100, 806, 256
-    net = StandInNet(dev, dg.RAW_OBS_SIZE, A, E, n, seed=5)
-    key = jaxrand.split_host(jaxrand.PRNGKey(0))[1]
-    all_seeds = jaxrand.randint(key, n * world, 0, 1_000_000, device=dev)
-    seeds = all_seeds[rank * n:(rank + 1) * n].contiguous()
-    envs = dg.env_reset(0, seed=seeds, device=dev, **DOG_RULES)
-    import functools
-    from exploring_muzero_on_dog_b200 import mcts
-
-    def search_fn(p, keys, obs, invalid):
-        key2 = game_agent._split_each(keys, 1)
-        out = mcts.gumbel_muzero_policy(p, key2, net.root(p, obs), net.recurrent, S, invalid_actions=invalid, max_depth=50,
-                                        qtransform=functools.partial(mcts.qtransform_completed_by_mix_value, value_scale=0.5),
-                                        gumbel_scale=1.0, max_num_considered_actions=16)
-        return out.action, out.action_weights, out.search_tree.summary().value
-
-    loop = game_agent.SelfPlayLoop(envs, n, (dg.RAW_OBS_SIZE,), None, plies, search_fn=search_fn, obs_dtype=torch.int8, cuda_graph=True)
-    loop.max_steps = 2
-    loop.run(key)
-    loop.max_steps = plies
-    dg.env_reset(0, seed=seeds, device=dev, out=envs, **DOG_RULES)
-    buf = vec_replay_buffer.VectorizedReplayBuffer(n, 128, 10, 50, obs_shape=(dg.RAW_OBS_SIZE,), action_dim=A, max_episode_length=plies,
-                                                   device=dev, obs_dtype=torch.int8, prioritized=True, seed=rank)
-    torch.cuda.synchronize()
-    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-    e0.record()
-    traj = loop.run(key)
-    e1.record()
-    buf.save_games_from_buffers(traj)
-    batch = buf.sample_batch_prioritized(beta=0.5)
-    if with_exchange and world > 1:
-        batch = vec_replay_buffer.allgather_batch({k: v for k, v in batch.items()})
-    e2.record()
-    torch.cuda.synchronize()
-    ms, ms_rep = e0.elapsed_time(e1), e1.elapsed_time(e2)
-    sims = n * loop.enqueued * S
-    max_ms, all_sims, per = _gather_ranks(dev, world, ms, sims)
-    rep_max, _, _ = _gather_ranks(dev, world, ms_rep, 0)
-    return {"workload": f"cfg5 self-play: 8,192 DOG games per GPU x 100 sims per move (Gumbel MuZero, A=806, latent {E}, stand-in "
-                        f"network), {loop.enqueued} lockstep iterations; one CUDA graph per iteration; then replay save + prioritised "
-                        "sample(batch 128, unroll 10, td 50)" + (" + all-gather of the batch (NCCL)" if world > 1 else ""),
-            "sims": all_sims, "ms": max_ms, "sims_per_s": all_sims / (max_ms / 1e3), "per_rank_ms": per, "iterations": loop.enqueued,
-            "env_steps_rank0": int(traj["idx"].sum().item()), "replay_ms": rep_max, "global_batch": int(batch["actions"].shape[0]),
-            "batch_keys": sorted(batch.keys())}
+    out = {}
+    for net in ("standin", "precomputed"):
+        loop, key, traj, ms = _run_selfplay("cfg5", dev, rank, world, net, plies)
+        n, S, A, E = (loop.shape[k] for k in ("n", "S", "A", "E"))
+        max_ms, all_sims, per = _gather_ranks(dev, world, ms, n * loop.enqueued * S)
+        r = {"sims": all_sims, "ms": max_ms, "sims_per_s": all_sims / (max_ms / 1e3), "per_rank_ms": per, "iterations": loop.enqueued,
+             "env_steps_rank0": int(traj["idx"].sum().item())}
+        if net == "standin":
+            buf = vec_replay_buffer.VectorizedReplayBuffer(n, 128, 10, 50, obs_shape=(dg.RAW_OBS_SIZE,), action_dim=A, max_episode_length=plies,
+                                                           device=dev, obs_dtype=torch.int8, prioritized=True, seed=rank)
+            e1, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e1.record()
+            buf.save_games_from_buffers(traj)
+            batch = buf.sample_batch_prioritized(beta=0.5)
+            if with_exchange and world > 1:
+                batch = vec_replay_buffer.allgather_batch(batch)
+            e2.record()
+            torch.cuda.synchronize()
+            rep_max, _, _ = _gather_ranks(dev, world, e1.elapsed_time(e2), 0)
+            out = dict({"workload": f"cfg5 self-play: 8,192 DOG games per GPU x 100 sims per move (Gumbel MuZero, A=806, latent {E}, stand-in "
+                                    f"network), {loop.enqueued} lockstep iterations; one CUDA graph per iteration; then replay save + prioritised "
+                                    "sample(batch 128, unroll 10, td 50)" + (" + all-gather of the batch (NCCL)" if world > 1 else "")},
+                       **r, replay_ms=rep_max, global_batch=int(batch["actions"].shape[0]), batch_keys=sorted(batch.keys()))
+            del buf, batch
+        else:
+            out["path_only"] = dict(r, note="same loop with callbacks that launch nothing (precomputed network outputs): the cost of the path itself")
+        del loop, traj
+        torch.cuda.empty_cache()
+    return out
 
 
 def dog_cfg4(dev, rank, world, peak):
@@ -420,12 +508,12 @@ def side_measurements(dev, key, peak):
     for rep in range(2):
         dm.env_reset(0, seed=seeds2, device=dev, out=env2, **RULES)
         act.zero_()
-        k = np.asarray(key, dtype=np.uint32)
+        k = jaxrand.KeyChain(key)          # rng_key, *step_keys = split(rng_key, N + 1): element 0, advanced on the host
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for t in range(iters):
             dm.random_step(env2, k, active_count=act)
-            k = jaxrand.split_host(k)[0]
+            k.advance()
         e1.record()
         torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
@@ -434,6 +522,25 @@ def side_measurements(dev, key, peak):
                                  "env_steps": steps2, "ms": ms, "env_steps_per_s": steps2 / (ms / 1e3), "gpu_launches": iters,
                                  "all_done": bool(env2.raw("done").all()),
                                  "roofline": _roofline("k_madn_det_random_step", steps2, BYTES_PER_STEP, ms, peak)}
+    # the same host loop with 32 lockstep iterations per launch (random_steps: the state stays in registers inside a chunk)
+    chunk = 32
+    tot2 = torch.zeros(1, dtype=torch.int64, device=dev)
+    for rep in range(2):
+        dm.env_reset(0, seed=seeds2, device=dev, out=env2, **RULES)
+        tot2.zero_()
+        k = np.asarray(key, dtype=np.uint32)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for t in range(0, iters + chunk - 1, chunk):
+            k = dm.random_steps(env2, k, chunk, total_steps=tot2)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    steps3 = int(tot2.item())
+    out["madn_cfg2_chunked"] = {"workload": f"cfg2 driven from the host {chunk} lockstep iterations per launch (random_steps), 65,536 games",
+                                "env_steps": steps3, "ms": ms, "env_steps_per_s": steps3 / (ms / 1e3), "gpu_launches": (iters + chunk - 1) // chunk,
+                                "all_done": bool(env2.raw("done").all()), "same_steps_as_per_call": steps3 == steps2,
+                                "roofline": _roofline("k_madn_det_play_cta", steps3, BYTES_PER_STEP, ms, peak, bound="issue")}
     # evaluation loop: rule-based team against random team, one fused launch per lockstep iteration
     n3 = 16384
     seeds3 = jaxrand.randint(key, n3, 0, 1_000_000, device=dev)
@@ -659,6 +766,7 @@ def main():
         torch.cuda.synchronize()
 
     clocks = ClockSampler(local)
+    clocks.start()  # before the warm-up: NVML initialisation and the first (slow) queries stay out of the timed regions
     for _ in range(max(args.warmup, 3)):
         one_step(seeds)
     barrier()
@@ -667,6 +775,7 @@ def main():
     total.zero_()
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     barrier()
+    clocks.clear()  # keep only the samples taken during the two timed regions
     # the whole region is enqueued behind a ~20 ms spin kernel, so the device runs the K steps back to back from its queue and
     # a host hiccup (GC, another tenant on the box) cannot leave it idle between a reset and its play kernel
     torch.cuda._sleep(40_000_000)
@@ -678,7 +787,6 @@ def main():
         ev[s][1].record()
         dm.play_random(env, key, max_steps=MAX_STEPS, game_offset=offset, game_len=glen, total_steps=total)
         ev[s][2].record()
-    clocks.sample_until(ev[-1][2])  # NVML samples from this thread while the device drains its queue
     barrier()
     step_ms = [ev[s][0].elapsed_time(ev[s][2]) for s in range(args.steps)]
     play_ms = [ev[s][1].elapsed_time(ev[s][2]) for s in range(args.steps)]
@@ -731,7 +839,6 @@ def main():
             consumed[b].synchronize()  # results of step s - 2 have arrived on the host before their buffers are reused
         e2e_step(b)
         e2e_ev[s].record()
-        clocks.sample()                # one NVML sample per step, from this thread
         host_t.append(1e3 * (time.perf_counter() - h0))
     torch.cuda.current_stream().wait_stream(copy_stream)
     t1.record()
@@ -777,6 +884,7 @@ def main():
         for cfgk, loopk in (("mcts_cfg3_tree_only", "selfplay_cfg3"), ("mcts_cfg5_tree_only", "selfplay_cfg5")):
             if loopk in extras:
                 extras[loopk]["vs_tree_only"] = extras[loopk]["sims_per_s"] / extras[cfgk]["sims_per_s"]
+                extras[loopk]["path_only"]["vs_tree_only"] = extras[loopk]["path_only"]["sims_per_s"] / extras[cfgk]["sims_per_s"]
     if world == 1 and want("side"):
         extras.update(side_measurements(dev, key, peak))
 

@@ -268,10 +268,14 @@ def map_action_to_card(action):
 
 def random_step(env, rng_key, game_offset=0, active_count=None):
     """one fused lockstep iteration of the random-legal-policy driver over the 806 actions, in place"""
-    cfg, st = env.cfg(), env.cstate()
-    _lib.check(_lib.lib().dogstep_dog_random_step(C.byref(st), C.c_int64(env.n), C.byref(cfg), _lib.host_key(rng_key),
-                                                 C.c_int64(game_offset), _lib.ptr(active_count), _lib.stream()),
-               "dog_random_step")
+    ac = None if active_count is None else active_count.data_ptr()
+    prep = env.memo(("random_step", game_offset, ac), lambda: _lib.Prepared(
+        _lib.lib().dogstep_dog_random_step,
+        [C.byref(env.cstate()), C.c_int64(env.n), C.byref(env.cfg()), None, C.c_int64(game_offset), _lib.ptr(active_count), _lib.stream()]))
+    prep.args[3] = _lib.host_key(rng_key)
+    rc = prep()
+    if rc:
+        _lib.check(rc, "dog_random_step")
     return env
 
 

@@ -186,11 +186,24 @@ def map_action(action_index):
 def random_step(env, rng_key, game_offset=0, active_count=None):
     """One fused lockstep iteration of the random-legal-policy driver
     (MuZero_det_MADN/evaluate_agent.py:733-930, do_random), in place."""
-    cfg, st = env.cfg(), env.cstate()
-    _lib.check(_lib.lib().dogstep_madn_det_random_step(C.byref(st), C.c_int64(env.n), C.byref(cfg), _lib.host_key(rng_key),
-                                                      C.c_int64(game_offset), _lib.ptr(active_count), _lib.stream()),
-               "madn_det_random_step")
+    ac = None if active_count is None else active_count.data_ptr()
+    prep = env.memo(("random_step", game_offset, ac), lambda: _lib.Prepared(
+        _lib.lib().dogstep_madn_det_random_step,
+        [C.byref(env.cstate()), C.c_int64(env.n), C.byref(env.cfg()), None, C.c_int64(game_offset), _lib.ptr(active_count), _lib.stream()]))
+    prep.args[3] = _lib.host_key(rng_key)   # a jaxrand.KeyChain is passed as its buffer: no per-call conversion
+    rc = prep()
+    if rc:
+        _lib.check(rc, "madn_det_random_step")
     return env
+
+
+def random_steps(env, rng_key, iterations, game_offset=0, game_len=None, total_steps=None):
+    """`iterations` lockstep iterations of the random-legal-policy driver in ONE launch (the state stays in registers between
+    them), in place -> the loop key to continue with.  A host loop that calls this with 16-64 iterations at a time pays one
+    launch + one state round trip per chunk instead of per iteration (random_step)."""
+    play_random(env, rng_key, max_steps=iterations, game_offset=game_offset, game_len=game_len, total_steps=total_steps)
+    from .. import jaxrand
+    return jaxrand.key_chain_host(rng_key, iterations)
 
 
 def play_random(env, rng_key, max_steps=2000, game_offset=0, game_len=None, total_steps=None):

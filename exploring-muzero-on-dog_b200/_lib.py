@@ -75,6 +75,41 @@ class _Entry:
             return self.fn(*[s if a is _STREAM else a for a in args])
 
 
+class Prepared:
+    """An entry point with its argument list built ONCE (structs, sizes, pointers): a call that is repeated every lockstep
+    iteration on the same buffers then costs the C call plus one current-stream lookup instead of rebuilding ~8 ctypes
+    objects and re-deriving the device.  `args` may be edited between calls (e.g. the host key slot)."""
+    __slots__ = ("fn", "args", "stream_slots", "dev", "name")
+
+    def __init__(self, entry, args):
+        self.fn, self.name, self.args = entry.fn, entry.name, list(args)
+        self.stream_slots = [i for i, a in enumerate(args) if a is _STREAM]
+        dev = None
+        for a in args:
+            d = getattr(a, "dev", None)
+            if d is None:
+                o = getattr(a, "_obj", None)
+                if o is not None:
+                    d = getattr(o, "dev", None)
+            if d is not None:
+                if dev is not None and d != dev:
+                    raise DogstepError(f"{self.name}: arguments live on different GPUs (cuda:{dev} and cuda:{d})")
+                dev = d
+        self.dev = dev
+
+    def __call__(self):
+        if self.dev is not None and self.dev != torch.cuda.current_device():
+            with torch.cuda.device(self.dev):
+                return self._go()
+        return self._go()
+
+    def _go(self):
+        s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        for i in self.stream_slots:
+            self.args[i] = s
+        return self.fn(*self.args)
+
+
 class _Lib:
     def __init__(self, cdll):
         self._cdll = cdll
@@ -129,8 +164,16 @@ def stream():
     return _STREAM
 
 
+_U32x2 = C.c_uint32 * 2
+
+
 def host_key(key):
-    """uint32[2] host array from a tensor / ndarray / sequence"""
+    """uint32[2] host array from a tensor / ndarray / sequence (a jaxrand.KeyChain or a ctypes array is used as it is)"""
+    if isinstance(key, _U32x2):
+        return key
+    buf = getattr(key, "buf", None)
+    if isinstance(buf, _U32x2):
+        return buf
     if isinstance(key, torch.Tensor):
         key = key.detach().cpu().tolist()
     k = [int(x) & 0xFFFFFFFF for x in list(key)]

@@ -1317,6 +1317,28 @@ int dogstep_madn_cls_eval_step(const dogstep_madn_cls_state* s, int64_t n, const
   return check_launch();
 }
 
+// host-side scalar key arithmetic (no device work): jax.random.split(key, num) for small num, and the loop-key chain
+// rng <- split(rng, N + 1)[0] applied `steps` times (element 0 of a split does not depend on N) — what a host driver that
+// launches k lockstep iterations at a time needs between launches
+int dogstep_host_split(const uint32_t* key, int32_t num, uint32_t* out) {
+  if (!key || !out || num < 0) return DOGSTEP_ERR_INVALID_ARG;
+  const Key2 k{key[0], key[1]};
+  for (int32_t i = 0; i < num; ++i) {
+    const Key2 o = split_i(k, (uint32_t)i);
+    out[2 * i] = o.a;
+    out[2 * i + 1] = o.b;
+  }
+  return DOGSTEP_OK;
+}
+int dogstep_host_key_chain(const uint32_t* key, int32_t steps, uint32_t* out) {
+  if (!key || !out || steps < 0) return DOGSTEP_ERR_INVALID_ARG;
+  Key2 k{key[0], key[1]};
+  for (int32_t i = 0; i < steps; ++i) k = split_i(k, 0u);
+  out[0] = k.a;
+  out[1] = k.b;
+  return DOGSTEP_OK;
+}
+
 int dogstep_random_split_chain(uint32_t* key, int64_t n, uint32_t* step_keys, void* stream) {
   if (!key || !step_keys || n < 0 || n >= 0xFFFFFFFFll) return DOGSTEP_ERR_INVALID_ARG;
   if (n) k_random_split_chain_keys<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(key, n, step_keys);

@@ -40,8 +40,66 @@ def PRNGKey(seed):
 
 
 def split_host(key, num=2):
-    """jax.random.split(key, num) for small num, on the host -> uint32 [num, 2]"""
-    return np.array([threefry2x32(key, 0, i) for i in range(num)], dtype=np.uint32)
+    """jax.random.split(key, num) for small num, on the host (libdogstep's host-side Threefry, ~1 us) -> uint32 [num, 2]"""
+    out = np.empty((num, 2), dtype=np.uint32)
+    k = key if (isinstance(key, np.ndarray) and key.dtype == np.uint32 and key.flags.c_contiguous) else np.ascontiguousarray(key, dtype=np.uint32)
+    rc = _host_fn("dogstep_host_split")(k.ctypes.data, num, out.ctypes.data)
+    if rc:
+        _lib.check(rc, "host_split")
+    return out
+
+
+class KeyChain:
+    """The loop key of a host-driven lockstep loop, kept in a ctypes buffer: `rng_key, *step_keys = split(rng_key, N + 1)` every
+    iteration (game_agent.py:60, evaluate_agent.py:741) needs only element 0 on the host, and advance() computes it in place
+    in ~1 us (a NumPy round trip per iteration costs more than the kernel launch it feeds).  Accepted wherever a host key is."""
+
+    def __init__(self, key):
+        k = np.asarray(key, dtype=np.uint32).reshape(2)
+        self.buf = (C.c_uint32 * 2)(int(k[0]), int(k[1]))
+        self._fn = _host_fn("dogstep_host_key_chain")
+        self._p = C.addressof(self.buf)
+
+    def advance(self, steps=1):
+        self._fn(self._p, steps, self._p)
+        return self
+
+    def numpy(self):
+        return np.array([self.buf[0], self.buf[1]], dtype=np.uint32)
+
+    def __iter__(self):
+        return iter((self.buf[0], self.buf[1]))
+
+    def __len__(self):
+        return 2
+
+    def __getitem__(self, i):
+        return self.buf[i]
+
+
+_HOST = {}
+
+
+def _host_fn(name):
+    """raw ctypes function with argtypes set (no per-call argument objects): the host-side key arithmetic sits in per-iteration
+    host loops, its cost is all call overhead"""
+    f = _HOST.get(name)
+    if f is None:
+        f = getattr(_lib.lib()._cdll, name)
+        f.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        f.restype = C.c_int
+        _HOST[name] = f
+    return f
+
+
+def key_chain_host(key, steps):
+    """the loop key after `steps` lockstep iterations: rng <- split(rng, N + 1)[0], `steps` times (game_agent.py:60)"""
+    out = np.empty(2, dtype=np.uint32)
+    k = key if (isinstance(key, np.ndarray) and key.dtype == np.uint32 and key.flags.c_contiguous) else np.ascontiguousarray(key, dtype=np.uint32)
+    rc = _host_fn("dogstep_host_key_chain")(k.ctypes.data, int(steps), out.ctypes.data)
+    if rc:
+        _lib.check(rc, "host_key_chain")
+    return out
 
 
 def split(key, num, device="cuda"):

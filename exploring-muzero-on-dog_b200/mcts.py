@@ -49,20 +49,28 @@ def _resolve_qt(qt):
 
 
 class Tree:
-    """mctx.Tree-shaped view of the device buffers ([games, nodes, actions])."""
+    """mctx.Tree-shaped view of the device buffers ([games, nodes, actions]).
+
+    Wide Gumbel trees (DOG's 806 actions) are SPARSE on the device: the search initialises and reads only the root rows and the
+    children that have visits (include/dogstep.h, dogstep_mcts_materialize).  Reading one of the dense per-child arrays or
+    `embeddings` through this object first fills in the defaults, so what the caller sees always equals the dense mctx.Tree;
+    the root-only accessors (summary(), qvalues(0)) and the search itself never pay for that."""
 
     ROOT_INDEX, NO_PARENT, UNVISITED = 0, -1, -1
+    _DENSE = ("children_index", "children_prior_logits", "children_visits", "children_rewards", "children_discounts",
+              "children_values", "embeddings")
 
     def __init__(self, n, num_simulations, num_actions, num_chance, embed_dim, policy, device):
         N, A = num_simulations + 1, num_actions + num_chance
         i32, f32 = torch.int32, torch.float32
         e = functools.partial(torch.empty, device=device)
+        b = self._buf = {}
         self.node_visits, self.raw_values, self.node_values = e((n, N), dtype=i32), e((n, N), dtype=f32), e((n, N), dtype=f32)
         self.parents, self.action_from_parent = e((n, N), dtype=i32), e((n, N), dtype=i32)
-        self.children_index, self.children_visits = e((n, N, A), dtype=i32), e((n, N, A), dtype=i32)
-        self.children_prior_logits, self.children_rewards = e((n, N, A), dtype=f32), e((n, N, A), dtype=f32)
-        self.children_discounts, self.children_values = e((n, N, A), dtype=f32), e((n, N, A), dtype=f32)
-        self.embeddings = e((n, N, embed_dim), dtype=f32)
+        b["children_index"], b["children_visits"] = e((n, N, A), dtype=i32), e((n, N, A), dtype=i32)
+        b["children_prior_logits"], b["children_rewards"] = e((n, N, A), dtype=f32), e((n, N, A), dtype=f32)
+        b["children_discounts"], b["children_values"] = e((n, N, A), dtype=f32), e((n, N, A), dtype=f32)
+        b["embeddings"] = e((n, N, embed_dim), dtype=f32)
         self.is_decision = e((n, N), dtype=torch.uint8) if policy == STOCHASTIC else None
         self.root_invalid_actions = e((n, A), dtype=torch.uint8)
         self.root_gumbel = e((n, A), dtype=f32) if policy == GUMBEL else None
@@ -72,23 +80,45 @@ class Tree:
         self.select_aux = (torch.zeros((n, N + 1, 36), dtype=torch.uint32, device=device)
                            if policy == GUMBEL and num_chance == 0 and 32 < A <= 832 else None)
         self.num_actions, self.num_chance, self.n = num_actions, num_chance, n
+        self._cfg = None  # set by Search: the configuration the kernels run this tree with
+
+    def __getattr__(self, name):
+        # only reached for names that are not instance attributes: the dense per-child arrays
+        if name in Tree._DENSE:
+            buf = self.__dict__["_buf"]
+            self.materialize()
+            return buf[name]
+        raise AttributeError(name)
+
+    def raw(self, name):
+        """the device buffer as the kernels see it (sparse for wide Gumbel trees: only root rows and visited children defined)"""
+        return self._buf[name] if name in self._buf else getattr(self, name)
+
+    def materialize(self):
+        """fill in the rows / entries a sparse search never wrote (no-op for dense trees)"""
+        cfg = self.__dict__.get("_cfg")
+        if cfg is None or self.select_aux is None:
+            return
+        ct = self.cstruct()
+        _lib.check(_lib.lib().dogstep_mcts_materialize(C.byref(ct), C.c_int64(self.n), C.byref(cfg), _lib.stream()), "mcts_materialize")
 
     def cstruct(self):
-        return _lib.tag(_lib.MctsTree(*[None if getattr(self, k) is None else C.c_void_p(getattr(self, k).data_ptr())
+        return _lib.tag(_lib.MctsTree(*[None if self.raw(k) is None else C.c_void_p(self.raw(k).data_ptr())
                                         for k in _lib.MCTS_TREE_FIELDS]), self.node_visits.device)
 
     def qvalues(self, indices=0):
-        return self.children_rewards[:, indices] + self.children_discounts[:, indices] * self.children_values[:, indices]
+        src = self._buf if isinstance(indices, int) and indices == 0 else {k: getattr(self, k) for k in ("children_rewards", "children_discounts", "children_values")}
+        return src["children_rewards"][:, indices] + src["children_discounts"][:, indices] * src["children_values"][:, indices]
 
     def summary(self):
-        """mctx Tree.summary() restricted to the decision actions"""
+        """mctx Tree.summary() restricted to the decision actions (root rows only: always defined)"""
         A = self.num_actions
         value = self.node_values[:, 0]
-        vc = self.children_visits[:, 0, :A].to(torch.float32)
+        visits = self._buf["children_visits"][:, 0, :A]
+        vc = visits.to(torch.float32)
         tot = vc.sum(-1, keepdim=True)
         probs = torch.where(tot > 0, vc / tot.clamp(min=1), torch.full_like(vc, 1.0 / A))
-        return SearchSummary(visit_counts=self.children_visits[:, 0, :A], visit_probs=probs, value=value,
-                             qvalues=self.qvalues(0)[:, :A])
+        return SearchSummary(visit_counts=visits, visit_probs=probs, value=value, qvalues=self.qvalues(0)[:, :A])
 
 
 def _cfg(policy, qtransform, num_simulations, max_depth, A, Cn, E, **kw):
@@ -109,6 +139,7 @@ class Search:
     def __init__(self, cfg, n, device="cuda"):
         self.cfg, self.n, self.device = cfg, n, torch.device(device)
         self.tree = Tree(n, cfg.num_simulations, cfg.num_actions, cfg.num_chance, cfg.embed_dim, cfg.policy, self.device)
+        self.tree._cfg = cfg
         self._ct = self.tree.cstruct()
         self.parent = torch.empty(n, dtype=torch.int32, device=self.device)
         self.action = torch.empty(n, dtype=torch.int32, device=self.device)
@@ -172,7 +203,7 @@ def _run(search, params, root, recurrent_fn, invalid_actions, keys, dirichlet_no
     S = search.cfg.num_simulations
     _, action, emb, _ = search.select(0)
     for sim in range(S):
-        out, nxt = recurrent_fn(params, search.expand_key, action.long(), emb)
+        out, nxt = recurrent_fn(params, search.expand_key, action, emb)  # action: int32 [games] (a valid torch index dtype)
         step = search.expand_select if sim + 1 < S else search.expand  # expand(sim) + select(sim + 1) fused into one launch
         step(sim, out.prior_logits, out.value, out.reward, out.discount, nxt.reshape(search.n, -1))
     return search.policy_output()[0]
@@ -313,12 +344,26 @@ def stochastic_muzero_policy(params, rng_key, root, decision_recurrent_fn, chanc
     def search_loop(s, st):
         s.init(st["keys"], RootFnOutput(st["prior"], st["value"], st["emb"]), st["invalid"], st["noise"])
         _, action, emb, is_dec = s.select(0)
+        # per simulation the glue around the two callbacks is 5 small launches: two action clamps (decision / chance index of
+        # the selected edge) and the copies of the next state / afterstate embeddings into their zero-padded rows
+        a_dec = torch.empty(n, dtype=torch.int32, device=dev)
+        a_ch = torch.empty(n, dtype=torch.int32, device=dev)
+        nxt_pad = torch.zeros((n, E), dtype=torch.float32, device=dev) if Es < E else None
+        after_pad = torch.zeros((n, E), dtype=torch.float32, device=dev) if Ea < E else None
         for sim in range(num_simulations):
-            a = action.long()
-            dec, after = decision_recurrent_fn(params, None, a.clamp(max=A - 1), emb[:, :Es])
-            ch, nxt = chance_recurrent_fn(params, None, (a - A).clamp(min=0, max=Cn - 1), emb[:, :Ea])
+            torch.clamp(action, max=A - 1, out=a_dec)
+            torch.clamp(action - A, min=0, max=Cn - 1, out=a_ch)
+            dec, after = decision_recurrent_fn(params, None, a_dec, emb[:, :Es])
+            ch, nxt = chance_recurrent_fn(params, None, a_ch, emb[:, :Ea])
+            nxt, after = nxt.reshape(n, -1), after.reshape(n, -1)
+            if nxt_pad is not None:
+                nxt_pad[:, :Es].copy_(nxt)
+                nxt = nxt_pad
+            if after_pad is not None:
+                after_pad[:, :Ea].copy_(after)
+                after = after_pad
             step = s.expand_select if sim + 1 < num_simulations else s.expand
-            step(sim, ch.action_logits, ch.value, ch.reward, ch.discount, pad(nxt), dec.chance_logits, dec.afterstate_value, pad(after))
+            step(sim, ch.action_logits, ch.value, ch.reward, ch.discount, nxt, dec.chance_logits, dec.afterstate_value, after)
         return s.policy_output()[0]
 
     inputs = dict(keys=rng_key, prior=root.prior_logits.float(), value=root.value.float(), emb=pad(state_emb),

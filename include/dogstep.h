@@ -251,6 +251,16 @@ typedef struct {
 int dogstep_mcts_init(const dogstep_mcts_tree* t, int64_t n, const dogstep_mcts_cfg* cfg, const uint32_t* keys,
                       const float* root_prior_logits, const float* root_value, const float* root_embedding,
                       const uint8_t* invalid_actions, const float* dirichlet_noise, void* stream);
+/* Wide Gumbel trees that carry a select cache (select_aux != NULL, 32 < A' <= 832, qtransform_completed_by_mix_value) are SPARSE:
+ * mcts_init writes only the root rows of the six [n, N, A'] child arrays (mctx's search.py instantiate_tree_from_root zero-fills
+ * all of them: 16.9 GB per search at BASELINE config 5); every kernel of that path reads a child entry only where the cache's
+ * bitmap marks a child with visits.  dogstep_mcts_is_sparse tells (1 / 0) whether a (tree, cfg) pair runs that way;
+ * dogstep_mcts_materialize writes the defaults (index -1, zero visits / reward / discount / value; zero prior row and embedding
+ * of nodes that were never created) so that the buffers equal the dense mctx.Tree — only needed by callers that read non-root
+ * rows; a no-op for every other tree.  Idempotent. */
+int dogstep_mcts_is_sparse(const dogstep_mcts_tree* t, const dogstep_mcts_cfg* cfg);
+int dogstep_mcts_materialize(const dogstep_mcts_tree* t, int64_t n, const dogstep_mcts_cfg* cfg, void* stream);
+
 /* simulate(): descend from the root to (parent, action) for simulation `sim`; gathers the parent's embedding.
  * parent_out i32 [n], action_out i32 [n], embedding_out f32 [n,E], is_decision_out u8 [n] (may be NULL),
  * expand_key_out u32 [n,2] (may be NULL): the `expand_key` mctx hands to recurrent_fn for this simulation. */
@@ -435,6 +445,11 @@ int dogstep_random_split(const uint32_t* host_key, int64_t n, uint32_t* out, voi
 int dogstep_random_randint(const uint32_t* host_key, int64_t n, int32_t lo, int32_t hi, int32_t* out, void* stream);
 /* jax.random.uniform(key, (n,), float32, lo, hi) */
 int dogstep_random_uniform(const uint32_t* host_key, int64_t n, float lo, float hi, float* out, void* stream);
+/* HOST-side scalar key arithmetic (plain CPU code, no stream): out uint32 [num,2] = jax.random.split(key, num); and the loop-key
+ * chain rng <- split(rng, N + 1)[0] applied `steps` times (out uint32 [2]) — what a driver that launches k lockstep iterations
+ * per call (play_random with max_steps = k) advances its key by between launches. */
+int dogstep_host_split(const uint32_t* key, int32_t num, uint32_t* out);
+int dogstep_host_key_chain(const uint32_t* key, int32_t steps, uint32_t* out);
 /* rng_key, *step_keys = jax.random.split(rng_key, n + 1) (MuZero_det_MADN/game_agent.py:60) with the loop key uint32 [2] ON
  * THE DEVICE: step_keys uint32 [n,2] = split(key, n + 1)[1:], then key <- split(key, n + 1)[0] in place.  No host value is
  * baked into the launch, so a lockstep iteration that starts with this call can be captured once and replayed as a CUDA graph. */

@@ -215,7 +215,7 @@ def test_graph_replayed_loop_equals_eager_loop_and_oracle(env_kind):
         action = score.argmax(1).astype(np.int32)
         w = np.where(invalid, 0.0, 1.0).astype(np.float32)
         w = w / np.maximum(w.sum(1, keepdims=True), 1)
-        value = ((h % 2001).astype(np.float32) / np.float32(1000.0) - np.float32(1.0)).astype(np.float32)
+        value = ((h % 2001) - 1000).astype(np.float32) / np.float32(1024.0)  # power-of-two scale: exact however it is evaluated
         return action, w.astype(np.float32), value
 
     ar_d = torch.arange(A, device="cuda", dtype=torch.int64)
@@ -228,7 +228,7 @@ def test_graph_replayed_loop_equals_eager_loop_and_oracle(env_kind):
         action = score.argmax(1).to(torch.int32)
         w = (~invalid).to(torch.float32)
         w = w / w.sum(1, keepdim=True).clamp(min=1)
-        value = (h % 2001).to(torch.float32) / 1000.0 - 1.0
+        value = ((h % 2001) - 1000).to(torch.float32) / 1024.0
         return action, w, value
 
     def reset(out=None):
