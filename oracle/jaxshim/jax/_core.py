@@ -34,7 +34,10 @@ def _norm_index(idx, shape, clamp):
     if not isinstance(idx, tuple):
         idx = (idx,)
     out, ok, dim = [], True, 0
-    # expand Ellipsis is not needed by the reference code
+    if any(i is Ellipsis for i in idx):  # expand `...` into full slices (the loop files index obs[None, ...])
+        k = next(j for j, i in enumerate(idx) if i is Ellipsis)
+        consumed = sum(1 for i in idx if i is not None and i is not Ellipsis)
+        idx = idx[:k] + (slice(None),) * (len(shape) - consumed) + idx[k + 1:]
     for i in idx:
         if i is None:
             out.append(None)
