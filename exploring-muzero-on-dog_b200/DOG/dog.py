@@ -84,6 +84,22 @@ def raw_observation(env):
     return torch.cat([t["board"].reshape(n, -1), own, misc], 1).to(torch.int8).contiguous()
 
 
+def obs_planes(env):
+    """number of planes of encode_board: 8 + 3 * num_players + 14 (34 for four players)"""
+    return 8 + 3 * env.static["num_players"] + 14
+
+
+def encode_board(env):
+    """Observation of the seat to move, int8 [n, obs_planes, total_board_size].  NOT a reference function: DOG/dog.py:1264-1272
+    is a TODO and the reference has no DOG networks; the layout continues the MADN encoders (mover's frame, scalar facts as
+    planes, only what the mover may know — its own hand, the others' hand sizes).  Plane list: include/dogstep.h."""
+    obs = torch.empty((env.n, obs_planes(env), env.static["total_board_size"]), dtype=torch.int8, device=env.device)
+    cfg, st = env.cfg(), env.cstate()
+    _lib.check(_lib.lib().dogstep_dog_encode_board(C.byref(st), C.c_int64(env.n), C.byref(cfg), _lib.ptr(obs), _lib.stream()),
+               "dog_encode_board")
+    return _out(env, obs)
+
+
 def get_play_action_size(env):
     return int(2 * (4 * (12 + 1 + env.static["total_board_size"]) + 120))
 

@@ -64,6 +64,17 @@ inline int dog_make_geom(const dogstep_madn_cfg* cfg, DogGeom* g) {
   return DOGSTEP_OK;
 }
 
+// what the rules read of a position, for the (team-proxied) mover
+struct Dog4View {
+  int pid, cp;
+  int cur[4];        // the mover's pins
+  uint64_t occ[4];   // occ[p] bit c  <=>  board[c] == p
+  uint64_t any;      // board[c] != -1
+  uint64_t later;    // pins of players > cp (they win a shared cell on any rebuilt board)
+  uint32_t posmask;  // bit q: board[start[q]] == q
+  uint32_t lane;     // bit k: board[goal[cp][k]] == cp
+};
+
 // per-warp shared record
 struct alignas(16) DogS {
   int32_t pins[4][4];
@@ -77,6 +88,7 @@ struct alignas(16) DogS {
   uint16_t items[2 * (4 * (13 + 64) + 120) + kNCard + 2];
   int scratch[8];
   uint64_t pbits[4];  // bit c of pbits[p]: a pin of player p stands on cell c (kept by the dog_fast.cuh path)
+  Dog4View view;      // the mover's view of this turn (dog4_mask_flags): the mask tasks of ANY warp read it instead of rebuilding it
 };
 
 #define DG_RULE(g, bit) (((g).rules & (bit)) != 0u)

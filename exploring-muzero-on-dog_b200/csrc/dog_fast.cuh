@@ -34,16 +34,7 @@ DS_FN Dog4Rules dg4_rules(uint32_t r) {
                    (r & DOGSTEP_RULE_MUST_TRAVERSE_START) != 0u};
 }
 
-// what the rules read of a position, for the (team-proxied) mover
-struct Dog4View {
-  int pid, cp;
-  int cur[4];        // the mover's pins
-  uint64_t occ[4];   // occ[p] bit c  <=>  board[c] == p
-  uint64_t any;      // board[c] != -1
-  uint64_t later;    // pins of players > cp (they win a shared cell on any rebuilt board)
-  uint32_t posmask;  // bit q: board[start[q]] == q
-  uint32_t lane;     // bit k: board[goal[cp][k]] == cp
-};
+// struct Dog4View: dog_core.cuh (it is part of the per-warp record)
 
 DS_FN uint64_t dg4_pin_bits(const int32_t* pins4) {
   uint64_t b = 0;
@@ -333,16 +324,21 @@ DS_FN void dg4_capture_and_place(const Dog4Rules& R, const Dog4View& v, int32_t 
 }
 
 // one play-phase action on the pins: returns invalid flag (pins untouched when invalid)
+// TRUSTED: the action was drawn from this position's own legal mask (the random-policy drivers), so the validity tests — the
+// same dg4_val_* calls that built the mask — cannot fail and are skipped; an arbitrary caller-supplied action is never trusted.
+template <bool TRUSTED = false>
 DS_FN bool dg4_apply_play_action(const Dog4Rules& R, const Dog4View& v, int32_t (*pins)[4], const int mv[6]) {
   const int cp = v.cp, target = dg4_target(cp), g0 = dg4_goal(cp);
   const int* d = mv + 2;
   if (mv[1] == 1) {  // step_swap (:755-788)
     const int pi = (d[0] >= 0) ? 0 : (d[1] >= 0) ? 1 : (d[2] >= 0) ? 2 : (d[3] >= 0) ? 3 : 0;
     const int sp = d[pi] < 0 ? d[pi] + 56 : d[pi];  // gather index: negative wraps once (only -1 can occur)
-    uint32_t pin_ok;
-    uint64_t cell_ok;
-    dg4_val_swap(R, v, pin_ok, cell_ok);
-    if (!(((pin_ok >> pi) & 1u) && ((cell_ok >> sp) & 1ull))) return true;
+    if (!TRUSTED) {
+      uint32_t pin_ok;
+      uint64_t cell_ok;
+      dg4_val_swap(R, v, pin_ok, cell_ok);
+      if (!(((pin_ok >> pi) & 1u) && ((cell_ok >> sp) & 1ull))) return true;
+    }
     int swapped = -1;
 #pragma unroll
     for (int p = 0; p < 4; ++p) swapped = dg4_bit(v.occ[p], sp) ? p : swapped;
@@ -354,7 +350,7 @@ DS_FN bool dg4_apply_play_action(const Dog4Rules& R, const Dog4View& v, int32_t 
     return false;
   }
   if (d[0] + d[1] + d[2] + d[3] == 7) {  // step_hot_7 (:913-984)
-    if (!dg4_val_7(R, v, d)) return true;
+    if (!TRUSTED && !dg4_val_7(R, v, d)) return true;
     int moved[4], nw[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) moved[i] = v.cur[i] + d[i];
@@ -425,11 +421,11 @@ DS_FN bool dg4_apply_play_action(const Dog4Rules& R, const Dog4View& v, int32_t 
   const int pi = (d[0] != 0) ? 0 : (d[1] != 0) ? 1 : (d[2] != 0) ? 2 : (d[3] != 0) ? 3 : 0;
   const int move = d[pi], pos = v.cur[pi];
   if (move < 0) {  // step_neg_move (:861-911)
-    if (!dg4_val_neg(R, v, pi, move)) return true;
+    if (!TRUSTED && !dg4_val_neg(R, v, pi, move)) return true;
     dg4_capture_and_place(R, v, pins, pi, dg4_mod40(pos + move));
     return false;
   }
-  if (!dg4_val_normal(R, v, pi, move)) return true;  // step_normal_move (:790-859)
+  if (!TRUSTED && !dg4_val_normal(R, v, pi, move)) return true;  // step_normal_move (:790-859)
   const int moved = pos + move;
   const int x = moved - target - (int)R.mts;
   const bool ig = dg4_in_goal(cp, pos);
@@ -512,13 +508,17 @@ DS_FN int dg4_next_with_cards(const DogS& s, int from, int& all_empty, int& any_
 
 // env_step_play_phase (:987-1062) for a canonical state and action in [0, 792): pins, hands, cur, reward, done are
 // updated; s.board is NOT (the caller rebuilds it from the pins before anything reads it).  Returns "deal next".
+template <bool TRUSTED = false>
 DS_FN int dg4_play_phase(const Dog4Rules& R, DogS& s, int action, int& reward_out, int& done_out) {
-  Dog4View v;
+  Dog4View local;
+  if (!TRUSTED) {
 #ifdef __CUDA_ARCH__
-  dg4_view_bits(R, s.pbits, s.pins, s.cur, v);  // kept current by dog4_rebuild_board_warp
+    dg4_view_bits(R, s.pbits, s.pins, s.cur, local);  // kept current by dog4_rebuild_board_warp
 #else
-  dg4_view(R, s.pins, s.cur, v);
+    dg4_view(R, s.pins, s.cur, local);
 #endif
+  }
+  const Dog4View& v = TRUSTED ? s.view : local;  // TRUSTED: the mask of this very position was just built, and with it s.view
   const int pid = s.cur, cp = v.cp;
   int mv[6];
   dg4_map_action_to_move(action, mv);
@@ -526,7 +526,7 @@ DS_FN int dg4_play_phase(const Dog4Rules& R, DogS& s, int action, int& reward_ou
   const int ci = card < 0 ? (card + kNCard < 0 ? 0 : card + kNCard) : (card > kNCard - 1 ? kNCard - 1 : card);
   int reward, done;
   if (s.hands[cp][ci] > 0) {
-    const bool invalid = dg4_apply_play_action(R, v, s.pins, mv);
+    const bool invalid = dg4_apply_play_action<TRUSTED>(R, v, s.pins, mv);
     const uint32_t w = dg4_winner_mask(R, dg4_any_bits(s.pins));
     done = s.done || (w != 0u);
     reward = s.done ? 0 : (invalid ? -1 : (int)((w >> cp) & 1u));
@@ -619,6 +619,7 @@ __device__ __forceinline__ void dog4_build_mask(const Dog4Rules& R, DogS& s, int
   }
   Dog4View v;
   dg4_view_bits(R, s.pbits, s.pins, s.cur, v);
+  if (lane == 0) s.view = v;  // a TRUSTED transition of this position reads it (dg4_play_phase)
   const int8_t* hand = s.hands[v.cp];
   const bool joker = hand[0] > 0;
   if (joker || hand[1] > 0) {  // swaps: pin_ok x cell_ok
@@ -661,17 +662,18 @@ __device__ __forceinline__ void dog4_build_mask(const Dog4Rules& R, DogS& s, int
 // shared out to warps whose own game has a light hand (k_dog_play_random).  sub 0..3 = the hot-seven chunks, 4..5 = the normal
 // moves (the second chunk also carries the four -4 moves), 6 = swaps.  `flags` (dog4_mask_flags): bit 0 swaps, bit 1 hot
 // seven, bit 2 moves.  s must be a canonical record in the play phase with s.mask zeroed.
-__device__ __forceinline__ int dog4_mask_flags(const Dog4Rules& R, const DogS& s) {
+__device__ __forceinline__ int dog4_mask_flags(const Dog4Rules& R, DogS& s, int lane) {
   Dog4View v;
   dg4_view_bits(R, s.pbits, s.pins, s.cur, v);
+  if (lane == 0) s.view = v;  // read by dog4_mask_task, whichever warp runs it (the caller's barrier publishes it)
+  __syncwarp();
   const int8_t* hand = s.hands[v.cp];
   const bool joker = hand[0] > 0;
   return ((joker || hand[1] > 0) ? 1 : 0) | ((joker || hand[7] > 0) ? 2 : 0) | 4;
 }
 
 __device__ __forceinline__ void dog4_mask_task(const Dog4Rules& R, DogS& s, int sub, int lane) {
-  Dog4View v;
-  dg4_view_bits(R, s.pbits, s.pins, s.cur, v);
+  const Dog4View& v = s.view;
   const int8_t* hand = s.hands[v.cp];
   const bool joker = hand[0] > 0;
   if (sub < 4) {  // hot seven: splits 32 sub .. 32 sub + 31
@@ -714,6 +716,7 @@ __device__ __forceinline__ void dog4_mask_task(const Dog4Rules& R, DogS& s, int 
 // env_step (dog.py:1117-1131) for a canonical record: the swap phase and the deal are the generic code (they do not
 // touch the board), the play phase runs on the bitboards; the board bytes are rebuilt from the pins afterwards.
 // All lanes call; lane 0 applies the move, all lanes deal if needed.
+template <bool TRUSTED = false>
 __device__ __forceinline__ void dog4_env_step(const Dog4Rules& R, const DogGeom& g, DogS& s, int lane, int action, int& reward_out,
                                               int& done_out) {
   __syncwarp();
@@ -726,7 +729,7 @@ __device__ __forceinline__ void dog4_env_step(const Dog4Rules& R, const DogGeom&
   if (lane == 0) {
     if (play) {
       int reward, done;
-      s.scratch[0] = dg4_play_phase(R, s, action, reward, done);
+      s.scratch[0] = dg4_play_phase<TRUSTED>(R, s, action, reward, done);
       s.scratch[1] = reward;
       s.scratch[2] = done;
     } else {

@@ -61,8 +61,9 @@ __device__ __forceinline__ void dog_build_mask_any(const DogGeom& g, DogS& s, in
   else dog_build_mask(g, s, lane);
 }
 
+template <bool TRUSTED = false>
 __device__ __forceinline__ void dog_env_step_any(const DogGeom& g, DogS& s, int lane, int action, int& r, int& d) {
-  if (s.scratch[7]) dog4_env_step(dg4_rules(g.rules), g, s, lane, action, r, d);
+  if (s.scratch[7]) dog4_env_step<TRUSTED>(dg4_rules(g.rules), g, s, lane, action, r, d);
   else dog_env_step(g, s, lane, action, r, d);
 }
 
@@ -216,6 +217,58 @@ __global__ void __launch_bounds__(kDogThreads) k_dog_valid_actions(const __grid_
   for (int a = lane; a < g.num_actions; a += 32) out[a] = (uint8_t)((s.mask[a >> 5] >> (a & 31)) & 1u);
 }
 
+// DOG observation encoder — DESIGN WORK, no reference counterpart: DOG/dog.py:1264-1272 leaves encode_board as a TODO and the
+// DOG networks are stubs (MuZero_DOG/muzero_dog.py:85-99).  The layout continues the MADN encoders the reference does have
+// (deterministic_madn.py:395-438: everything rolled into the mover's frame, scalar facts broadcast over a plane), restricted
+// to what the seat to move may know (its own hand, not the others'; hand SIZES are public).  int8 [8 + 3n + 14, total]:
+//   [0, n)        occupancy of seat (cur + r) % n, ring rolled so that the mover's start is cell 0, goal lanes rotated alike
+//   n, n + 1      own side / other side sums of those planes (teams: seats r even / odd; else mover / everyone else)
+//   [n+2, 2n+2)   pins at home of seat (cur + r) % n
+//   [2n+2, 2n+16) the mover's own hand: count of card c (0 joker, 1 swap, 2..13)
+//   [2n+16, 3n+16) cards in hand of seat (cur + r) % n (a count: public)
+//   3n+16 ..      phase (1 = partner swap), hand_size of the NEXT deal, (round_starter - cur) mod n or -1, the card the mover has
+//                 put aside for its partner + 1 (0 = none), and two planes of zeros reserved for the discard pile
+__global__ void __launch_bounds__(kDogThreads) k_dog_encode_board(const __grid_constant__ DogGeom g, DogPtrs p, int64_t n,
+                                                                  int8_t* __restrict__ obs) {
+  DOG_KERNEL_PROLOGUE
+  if (i >= n) return;
+  dog_load(g, p, i, s, lane);
+  const int N = g.n, T = g.total, bs = g.bs;
+  const int cur = d_gidx(s.cur, N);
+  const int planes = 8 + 3 * N + kNCard;
+  int8_t* out = obs + i * (int64_t)planes * T;
+  // per-seat scalars
+  int home[4], hsz[4];
+  for (int r = 0; r < N; ++r) {
+    const int q = (cur + r) % N;
+    int h = 0, c = 0;
+    for (int k = 0; k < 4; ++k) h += s.pins[q][k] == -1;
+    for (int k = 0; k < kNCard; ++k) c += s.hands[q][k];
+    home[r] = h;
+    hsz[r] = c;
+  }
+  const bool teams = DG_RULE(g, DOGSTEP_RULE_TEAMS);
+  const int rs_rel = s.round_starter < 0 ? -1 : d_fmod(s.round_starter - cur, N);
+  for (int e = lane; e < planes * T; e += 32) {
+    const int plane = e / T, k = e - plane * T;
+    const int src = k < bs ? (k + g.d * cur) % bs : bs + (k - bs + 4 * cur) % 16;   // jnp.roll(x, -shift)[k] = x[(k + shift) % len]
+    const int owner = s.board[src];                                                   // -1 or seat
+    const int rel = owner < 0 ? -1 : d_fmod(owner - cur, N);
+    int v;
+    if (plane < N) v = rel == plane;
+    else if (plane == N) v = rel >= 0 && (teams ? (rel % 2 == 0) : rel == 0);
+    else if (plane == N + 1) v = rel >= 0 && (teams ? (rel % 2 == 1) : rel != 0);
+    else if (plane < 2 * N + 2) v = home[plane - N - 2];
+    else if (plane < 2 * N + 2 + kNCard) v = s.hands[cur][plane - 2 * N - 2];
+    else if (plane < 3 * N + 2 + kNCard) v = hsz[plane - 2 * N - 2 - kNCard];
+    else {
+      const int m = plane - (3 * N + 2 + kNCard);
+      v = m == 0 ? s.phase : m == 1 ? s.hand_size : m == 2 ? rs_rel : m == 3 ? s.swap_choices[cur] + 1 : 0;
+    }
+    out[e] = (int8_t)v;
+  }
+}
+
 __global__ void __launch_bounds__(kDogThreads) k_dog_step(const __grid_constant__ DogGeom g, DogPtrs p, int64_t n,
                                                           const int32_t* __restrict__ action, int8_t* __restrict__ reward,
                                                           uint8_t* __restrict__ done) {
@@ -349,7 +402,7 @@ __device__ __forceinline__ void dog_random_turn(const DogGeom& g, DogS& s, int l
   int a = dog_categorical(g, s, lane, key);
   if (a >= 0) {
     int r, d;
-    dog_env_step_any(g, s, lane, a, r, d);
+    dog_env_step_any<true>(g, s, lane, a, r, d);  // drawn from the mask just built: no second validation
   } else {
     dog_no_step(g, s, lane);
   }
@@ -445,7 +498,7 @@ __global__ void __launch_bounds__(kSyncWarps * 32, 1) k_dog_play_random(const __
       shared_mask = s.phase == 0 && s.scratch[7] != 0;
       if (shared_mask) {
         for (int w = lane; w < kDogMaskWords; w += 32) s.mask[w] = 0u;
-        flags = dog4_mask_flags(R4, s);
+        flags = dog4_mask_flags(R4, s, lane);
         if (lane == 0 && (flags & 2)) {
           const int pos = atomicAdd(&q[1], 4);
           for (int k = 0; k < 4; ++k) q[2 + pos + k] = warp * 4 + k;
@@ -483,7 +536,7 @@ __global__ void __launch_bounds__(kSyncWarps * 32, 1) k_dog_play_random(const __
       __syncwarp();
       if (a >= 0) {
         int r, d;
-        dog_env_step_any(g, s, lane, a, r, d);
+        dog_env_step_any<true>(g, s, lane, a, r, d);  // drawn from the mask just built: no second validation
       } else {
         dog_no_step(g, s, lane);
       }
@@ -554,6 +607,19 @@ int dogstep_dog_valid_actions(const dogstep_dog_state* s, int64_t n, const dogst
   DOG_PROLOGUE
   if (!mask) return DOGSTEP_ERR_INVALID_ARG;
   k_dog_valid_actions<<<dog_blocks(n), kDogThreads, 0, st>>>(g, p, n, mask);
+  return check_launch();
+}
+
+int dogstep_dog_obs_planes(const dogstep_dog_cfg* cfg) {
+  DogGeom g;
+  if (int rc = dog_make_geom(cfg, &g)) return rc;
+  return 8 + 3 * g.n + kNCard;
+}
+
+int dogstep_dog_encode_board(const dogstep_dog_state* s, int64_t n, const dogstep_dog_cfg* cfg, int8_t* obs, void* stream) {
+  DOG_PROLOGUE
+  if (!obs) return DOGSTEP_ERR_INVALID_ARG;
+  k_dog_encode_board<<<dog_blocks(n), kDogThreads, 0, st>>>(g, p, n, obs);
   return check_launch();
 }
 

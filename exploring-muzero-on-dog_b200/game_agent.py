@@ -129,6 +129,7 @@ class SelfPlayLoop:
         self.det = self.dog or isinstance(envs, dm.deterministic_MADN)
         self.mod = dm if self.det else cm
         dev = self.dev = envs.raw("done").device
+        self.raw_dog_obs = self.dog and tuple(input_shape) == (dg.RAW_OBS_SIZE,)
         action_dim = dg.get_play_action_size(envs) + 14 if self.dog else (24 if self.det else 4)
         self.traj = Trajectories(num_envs, max_steps, input_shape, action_dim, not self.det, dev, obs_dtype)
         self.loop_key = torch.zeros(2, dtype=torch.uint32, device=dev)
@@ -150,8 +151,10 @@ class SelfPlayLoop:
             cfg, st = envs.cfg(), envs.cstate()
             _lib.check(_lib.lib().dogstep_madn_cls_throw_die_active(C.byref(st), C.c_int64(n), C.byref(cfg), _lib.stream()),
                        "throw_die_active")
-        if self.dog:  # the reference has no DOG encoder (DOG/dog.py:1264-1272): see dog.encode_observation
-            obs, valid = dg.raw_observation(envs), dg.valid_actions(envs)
+        if self.dog:  # the reference has no DOG encoder (DOG/dog.py:1264-1272): dog.encode_board is this repo's design, the raw
+            # 74-byte mover view remains for callers that ask for it by shape
+            obs = dg.raw_observation(envs) if self.raw_dog_obs else dg.encode_board(envs)
+            valid = dg.valid_actions(envs)
         else:
             obs, valid = self.mod.encode_board(envs), self.mod.valid_action(envs).reshape(n, -1)
         action, weights, value = self.search_fn(self.params, self.step_keys, obs, ~valid)
@@ -263,7 +266,7 @@ def play_n_games_v3_stochastic(params, rng_key, input_shape, num_envs, num_simul
 
 def play_n_dog_games(params, rng_key, num_envs, num_simulation, max_depth, max_steps, temp, *, root_fn, recurrent_fn, rules=DOG_RULES,
                      obs_dtype=torch.int8, device="cuda", max_num_considered_actions=16, graph_cache=None, cuda_graph=False,
-                     return_loop=False):
+                     return_loop=False, encoded_obs=False):
     """BASELINE config 5: play_n_games_v3's shape (game_agent.py:185-192) on the DOG env (MuZero_DOG/game_agent.py:12-44 rules and
     batch_reset), Gumbel MuZero search over the 806 DOG actions (MuZero_DOG/muzero_dog.py:101-136).  The reference's DOG
     networks are stubs, so root_fn / recurrent_fn are the caller's."""
@@ -280,7 +283,7 @@ def play_n_dog_games(params, rng_key, num_envs, num_simulation, max_depth, max_s
                                         **({} if graph_cache is None else {"graph_cache": graph_cache}))
         return out.action, out.action_weights, out.search_tree.summary().value
 
-    loop = SelfPlayLoop(envs, num_envs, (dg.RAW_OBS_SIZE,), params, max_steps, search_fn=search_fn, obs_dtype=obs_dtype,
-                        cuda_graph=cuda_graph)
+    loop = SelfPlayLoop(envs, num_envs, (dg.obs_planes(envs), envs.static["total_board_size"]) if encoded_obs else (dg.RAW_OBS_SIZE,),
+                        params, max_steps, search_fn=search_fn, obs_dtype=obs_dtype, cuda_graph=cuda_graph)
     buffers = loop.run(subkey)
     return (envs, buffers, loop) if return_loop else (envs, buffers)

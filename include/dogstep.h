@@ -159,6 +159,13 @@ int dogstep_dog_reset(const dogstep_dog_state* s, int64_t n, const dogstep_dog_c
                       int32_t starting_player, void* stream);
 /* valid_actions — DOG/dog.py:693-711 (valid_step_actions :618-691).  mask: uint8 [n, num_actions] */
 int dogstep_dog_valid_actions(const dogstep_dog_state* s, int64_t n, const dogstep_dog_cfg* cfg, uint8_t* mask, void* stream);
+/* Observation encoder for the DOG env — NOT a reference function: DOG/dog.py:1264-1272 is a TODO and the DOG networks are stubs
+ * (MuZero_DOG/muzero_dog.py:85-99); SURVEY 8(f).4 calls it design work.  Same conventions as the MADN encoders the reference has
+ * (MADN/deterministic_madn.py:395-438): mover's frame, scalar facts broadcast over planes, only what the seat to move may know.
+ * obs int8 [n, dogstep_dog_obs_planes(cfg), total_board_size]; planes = 8 + 3 * num_players + 14 (34 for four players), laid out as
+ * documented at k_dog_encode_board (csrc/dog_kernels.cu). */
+int dogstep_dog_obs_planes(const dogstep_dog_cfg* cfg);
+int dogstep_dog_encode_board(const dogstep_dog_state* s, int64_t n, const dogstep_dog_cfg* cfg, int8_t* obs, void* stream);
 /* env_step — DOG/dog.py:1117-1131.  action: int32 [n] */
 int dogstep_dog_step(const dogstep_dog_state* s, int64_t n, const dogstep_dog_cfg* cfg, const int32_t* action, int8_t* reward,
                      uint8_t* done, void* stream);

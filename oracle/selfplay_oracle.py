@@ -86,6 +86,38 @@ def dog_raw_observation(state):
     return np.concatenate([state.board, own, misc], 1).astype(np.int8)
 
 
+def dog_encode_board(state):
+    """NumPy twin of DOG.dog.encode_board (this repo's design, see include/dogstep.h: the reference has no DOG encoder) — a
+    checker for the CUDA kernel, written from the plane list, not from the kernel"""
+    cfg = state.cfg
+    n, N, T, bs, d = state.n, cfg.num_players, cfg.total, 4 * cfg.distance, cfg.distance
+    teams = bool(cfg.rules & 1)
+    P = 8 + 3 * N + 14
+    obs = np.zeros((n, P, T), np.int8)
+    for g in range(n):
+        cur = int(np.clip(state.current_player[g] + (N if state.current_player[g] < 0 else 0), 0, N - 1))
+        board = state.board[g].astype(np.int64)
+        rolled = np.concatenate([np.roll(board[:bs], -d * cur), np.roll(board[bs:bs + 16], -4 * cur)])
+        rel = np.where(rolled < 0, -1, (rolled - cur) % N)
+        for r in range(N):
+            obs[g, r] = rel == r
+        own = (rel >= 0) & ((rel % 2 == 0) if teams else (rel == 0))
+        oth = (rel >= 0) & ((rel % 2 == 1) if teams else (rel != 0))
+        obs[g, N], obs[g, N + 1] = own, oth
+        for r in range(N):
+            q = (cur + r) % N
+            obs[g, N + 2 + r] = int((state.pins[g, q] == -1).sum())
+            obs[g, 2 * N + 16 + r] = int(state.hands[g, q].sum())
+        for c in range(14):
+            obs[g, 2 * N + 2 + c] = state.hands[g, cur, c]
+        m = 3 * N + 16
+        rs = int(state.round_starter[g])
+        obs[g, m], obs[g, m + 1] = state.phase[g], state.hand_size[g]
+        obs[g, m + 2] = -1 if rs < 0 else (rs - cur) % N
+        obs[g, m + 3] = int(state.swap_choices[g, cur]) + 1
+    return obs
+
+
 def play_batch_of_games_dog(state, max_steps, rng_key, search_fn, teams):
     """do_active_step of MuZero_det_MADN/game_agent.py:64-148 applied to the DOG env oracle (BASELINE config 5; the reference
     has no DOG self-play loop, MuZero_DOG/muzero_dog.py:85-99).  state: O.DogState."""

@@ -197,3 +197,34 @@ def test_play_random_ragged_sizes_caps_and_resume(n):
         olen, _, _ = O.dog_play_random(s, key, cap, game_offset=3, nthreads=8)
         assert_state_equal(s, env.numpy())
         assert np.array_equal(olen, glen.cpu().numpy())
+
+
+def test_encode_board_matches_the_plane_list():
+    """dog.encode_board (this repo's design: the reference has no DOG encoder) vs its NumPy twin, on states from the middle of
+    random games (swap phase, play phase, finished players) for 4 / 3 / 2 players, plus the information boundary: the planes
+    do not change when the OTHER seats' hands are permuted among card types"""
+    dog = _dog()
+    from oracle import selfplay_oracle
+    from exploring_muzero_on_dog_b200 import jaxrand
+    key = jaxrand.split_host(jaxrand.PRNGKey(2))[1]
+    for num_players, rules in ((4, DOG_RULES), (3, dict(DOG_RULES, enable_teams=False)), (2, dict(DOG_RULES, enable_teams=False))):
+        n = 256
+        seeds = O.randint(key, n, 0, 1_000_000)
+        cfg = O.DogCfg(num_players, 0xF, 10, mask_of(dict(rules, enable_teams=rules["enable_teams"] and num_players == 4)))
+        s = O.dog_reset(cfg, seeds, -1)
+        env = dog.env_reset(0, num_players=num_players, seed=seeds, starting_player=-1, **rules)
+        for cap in (0, 3, 40, 400):
+            O.dog_play_random(s, key, cap, nthreads=8)
+            dog.play_random(env, key, max_steps=cap)
+            got = dog.encode_board(env).cpu().numpy()
+            exp = selfplay_oracle.dog_encode_board(s)
+            assert got.shape == (n, dog.obs_planes(env), 56) and np.array_equal(got, exp), (num_players, cap, np.argwhere(got != exp)[:3].tolist())
+    # information boundary (4 players): shuffling the card TYPES inside another seat's hand leaves the observation unchanged
+    st = env4 = dog.env_reset(0, seed=O.randint(key, 64, 0, 1_000_000), **DOG_RULES)
+    dog.play_random(env4, key, max_steps=30)
+    hands = env4.raw("hands").clone()
+    cur = env4.raw("current_player").long()
+    other = (cur + 1) % 4
+    idx = torch.arange(64, device="cuda")
+    hands[idx, other] = hands[idx, other].flip(-1)
+    assert torch.equal(dog.encode_board(env4), dog.encode_board(env4.replace(hands=hands)))
