@@ -502,19 +502,25 @@ __host__ __device__ inline void dog_step_hot7(const DogGeom& g, DogS& s, const i
 
 // first seat after `from` that still holds cards; all_empty = all(hand_cards == 0)
 DS_FN int dog_next_with_cards(const DogGeom& g, const DogS& s, int from, int& all_empty, int& any_left) {
-  int sums[4];
+  int sums[4] = {0, 0, 0, 0};  // fixed trip counts and a select chain: the array stays in registers (no local memory)
   int nz = 0, pos = 0;
-  for (int q = 0; q < g.n; ++q) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
     int sum = 0;
-    for (int k = 0; k < kNCard; ++k) sum += s.hands[q][k];
+    if (q < g.n)
+      for (int k = 0; k < kNCard; ++k) sum += s.hands[q][k];
     sums[q] = sum;
     nz |= (sum != 0);
     pos |= (sum > 0);
   }
   int next = -1;
-  for (int i = 0; i < g.n; ++i) {
-    int cand = d_fmod(from + i + 1, g.n);
-    if (next == -1 && sums[cand] > 0) next = cand;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (i < g.n) {
+      const int cand = d_fmod(from + i + 1, g.n);
+      const int sc = cand == 0 ? sums[0] : cand == 1 ? sums[1] : cand == 2 ? sums[2] : sums[3];
+      if (next == -1 && sc > 0) next = cand;
+    }
   }
   all_empty = !nz;
   any_left = pos;

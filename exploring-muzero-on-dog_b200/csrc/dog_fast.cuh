@@ -595,6 +595,13 @@ __device__ __forceinline__ void dog4_rebuild_board_warp(DogS& s, int lane) {
   }
 }
 
+// the bitboards alone (what the dog_fast.cuh rules read); the board BYTES are then stale until dog4_rebuild_board_warp
+__device__ __forceinline__ void dog4_refresh_pbits(DogS& s, int lane) {
+  __syncwarp();
+  if (lane < 4) s.pbits[lane] = dg4_pin_bits(s.pins[lane]);
+  __syncwarp();
+}
+
 __device__ __forceinline__ void dog4_set_pair(DogS& s, int b, bool joker, bool card) {
   if (joker) atomicOr(&s.mask[b >> 5], 1u << (b & 31));
   if (card) {
@@ -716,7 +723,9 @@ __device__ __forceinline__ void dog4_mask_task(const Dog4Rules& R, DogS& s, int 
 // env_step (dog.py:1117-1131) for a canonical record: the swap phase and the deal are the generic code (they do not
 // touch the board), the play phase runs on the bitboards; the board bytes are rebuilt from the pins afterwards.
 // All lanes call; lane 0 applies the move, all lanes deal if needed.
-template <bool TRUSTED = false>
+// LAZY_BOARD (the persistent play kernel): only the bitboards follow the move; the caller rebuilds the board bytes before it
+// stores the game (nothing on the canonical path reads them in between).
+template <bool TRUSTED = false, bool LAZY_BOARD = false>
 __device__ __forceinline__ void dog4_env_step(const Dog4Rules& R, const DogGeom& g, DogS& s, int lane, int action, int& reward_out,
                                               int& done_out) {
   __syncwarp();
@@ -746,7 +755,8 @@ __device__ __forceinline__ void dog4_env_step(const Dog4Rules& R, const DogGeom&
     __syncwarp();
     return;
   }
-  dog4_rebuild_board_warp(s, lane);
+  if (LAZY_BOARD) dog4_refresh_pbits(s, lane);
+  else dog4_rebuild_board_warp(s, lane);
   if (s.scratch[0] && !s.scratch[6]) dog_distribute_cards(g, s, lane);  // scratch[6]: the caller deals (k_dog_play_random)
   reward_out = s.scratch[1];
   done_out = s.scratch[2];

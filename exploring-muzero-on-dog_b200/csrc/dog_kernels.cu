@@ -61,9 +61,9 @@ __device__ __forceinline__ void dog_build_mask_any(const DogGeom& g, DogS& s, in
   else dog_build_mask(g, s, lane);
 }
 
-template <bool TRUSTED = false>
-__device__ __forceinline__ void dog_env_step_any(const DogGeom& g, DogS& s, int lane, int action, int& r, int& d) {
-  if (s.scratch[7]) dog4_env_step<TRUSTED>(dg4_rules(g.rules), g, s, lane, action, r, d);
+template <bool TRUSTED = false, bool LAZY_BOARD = false>
+__device__ __forceinline__ void dog_env_step_any(const DogGeom& g, const Dog4Rules& R4, DogS& s, int lane, int action, int& r, int& d) {
+  if (s.scratch[7]) dog4_env_step<TRUSTED, LAZY_BOARD>(R4, g, s, lane, action, r, d);
   else dog_env_step(g, s, lane, action, r, d);
 }
 
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(kDogThreads) k_dog_step(const __grid_constant_
   if (i >= n) return;
   dog_load(g, p, i, s, lane);
   int r, d;
-  dog_env_step_any(g, s, lane, action[i], r, d);
+  dog_env_step_any(g, dg4_rules(g.rules), s, lane, action[i], r, d);
   dog_store(g, p, i, s, lane);
   if (lane == 0) {
     if (reward) reward[i] = (int8_t)r;
@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(kDogThreads) k_dog_agent_step(const __grid_con
   if (has_valid) {
     int r, d;
     act = action[i];
-    dog_env_step_any(g, s, lane, act, r, d);
+    dog_env_step_any(g, dg4_rules(g.rules), s, lane, act, r, d);
     __syncwarp();
     const int next = s.cur;
     const int next_team = teams ? (((next % 2) + 2) % 2) : -1;
@@ -402,7 +402,7 @@ __device__ __forceinline__ void dog_random_turn(const DogGeom& g, DogS& s, int l
   int a = dog_categorical(g, s, lane, key);
   if (a >= 0) {
     int r, d;
-    dog_env_step_any<true>(g, s, lane, a, r, d);  // drawn from the mask just built: no second validation
+    dog_env_step_any<true>(g, dg4_rules(g.rules), s, lane, a, r, d);  // drawn from the mask just built: no second validation
   } else {
     dog_no_step(g, s, lane);
   }
@@ -536,7 +536,7 @@ __global__ void __launch_bounds__(kSyncWarps * 32, 1) k_dog_play_random(const __
       __syncwarp();
       if (a >= 0) {
         int r, d;
-        dog_env_step_any<true>(g, s, lane, a, r, d);  // drawn from the mask just built: no second validation
+        dog_env_step_any<true, true>(g, R4, s, lane, a, r, d);  // drawn from the mask just built: no second validation
       } else {
         dog_no_step(g, s, lane);
       }
@@ -550,6 +550,7 @@ __global__ void __launch_bounds__(kSyncWarps * 32, 1) k_dog_play_random(const __
       __syncwarp();
       if (finished) {
         if (need_deal) dog_distribute_cards(g, s, lane);            // the state written back is the reference's: dealt
+        if (s.scratch[7]) dog4_rebuild_board_warp(s, lane);         // the board bytes were left stale by the lazy transitions
         dog_store(g, p, i, s, lane);
         if (lane == 0 && game_len) game_len[i] = len;
         __syncwarp();
