@@ -191,12 +191,13 @@ class MctsCfg(C.Structure):
                 ("max_num_considered_actions", C.c_int32), ("q_min", C.c_float), ("q_max", C.c_float),
                 ("value_scale", C.c_float), ("maxvisit_init", C.c_float), ("epsilon", C.c_float), ("pb_c_init", C.c_float),
                 ("pb_c_base", C.c_float), ("dirichlet_fraction", C.c_float), ("temperature", C.c_float),
-                ("gumbel_scale", C.c_float)]
+                ("gumbel_scale", C.c_float), ("state_embed_dim", C.c_int32), ("afterstate_embed_dim", C.c_int32)]
 
 
 MCTS_TREE_FIELDS = ("node_visits", "raw_values", "node_values", "parents", "action_from_parent", "children_index",
                     "children_prior_logits", "children_visits", "children_rewards", "children_discounts", "children_values",
-                    "embeddings", "is_decision", "root_invalid_actions", "root_gumbel", "search_key", "policy_key", "path", "select_aux")
+                    "embeddings", "is_decision", "root_invalid_actions", "root_gumbel", "search_key", "policy_key", "path", "select_aux",
+                    "select_action_decision", "select_action_chance")
 
 
 class MctsTree(C.Structure):

@@ -79,6 +79,9 @@ class Tree:
         # per-node select cache of the wide Gumbel path (DOG's 806 actions): 144 B per node
         self.select_aux = (torch.zeros((n, N + 1, 36), dtype=torch.uint32, device=device)
                            if policy == GUMBEL and num_chance == 0 and 32 < A <= 832 else None)
+        # stochastic: the two action indices the callbacks are evaluated with, written by select (no clamp launches per simulation)
+        self.select_action_decision = e((n,), dtype=i32) if policy == STOCHASTIC else None
+        self.select_action_chance = e((n,), dtype=i32) if policy == STOCHASTIC else None
         self.num_actions, self.num_chance, self.n = num_actions, num_chance, n
         self._cfg = None  # set by Search: the configuration the kernels run this tree with
 
@@ -339,31 +342,22 @@ def stochastic_muzero_policy(params, rng_key, root, decision_recurrent_fn, chanc
         dirichlet_noise = torch.distributions.Dirichlet(torch.full((A,), float(dirichlet_alpha), device=dev)).sample((n,))
     cfg = _cfg(STOCHASTIC, qtransform, num_simulations, max_depth, A, Cn, E, pb_c_init=pb_c_init, pb_c_base=pb_c_base,
                dirichlet_fraction=dirichlet_fraction, temperature=temperature)
+    cfg.state_embed_dim, cfg.afterstate_embed_dim = Es, Ea
     noise = dirichlet_noise if dirichlet_fraction > 0 else None
 
     def search_loop(s, st):
         s.init(st["keys"], RootFnOutput(st["prior"], st["value"], st["emb"]), st["invalid"], st["noise"])
         _, action, emb, is_dec = s.select(0)
-        # per simulation the glue around the two callbacks is 5 small launches: two action clamps (decision / chance index of
-        # the selected edge) and the copies of the next state / afterstate embeddings into their zero-padded rows
-        a_dec = torch.empty(n, dtype=torch.int32, device=dev)
-        a_ch = torch.empty(n, dtype=torch.int32, device=dev)
-        nxt_pad = torch.zeros((n, E), dtype=torch.float32, device=dev) if Es < E else None
-        after_pad = torch.zeros((n, E), dtype=torch.float32, device=dev) if Ea < E else None
+        # the select kernel also writes the two indices the callbacks are evaluated with (decision action / chance outcome of the
+        # selected edge, clamped like mctx's where()), and expand takes the state / afterstate embeddings at their own widths and
+        # zero-fills the stored row: no clamp or pad launch per simulation on this side
+        a_dec, a_ch = s.tree.select_action_decision, s.tree.select_action_chance
         for sim in range(num_simulations):
-            torch.clamp(action, max=A - 1, out=a_dec)
-            torch.clamp(action - A, min=0, max=Cn - 1, out=a_ch)
             dec, after = decision_recurrent_fn(params, None, a_dec, emb[:, :Es])
             ch, nxt = chance_recurrent_fn(params, None, a_ch, emb[:, :Ea])
-            nxt, after = nxt.reshape(n, -1), after.reshape(n, -1)
-            if nxt_pad is not None:
-                nxt_pad[:, :Es].copy_(nxt)
-                nxt = nxt_pad
-            if after_pad is not None:
-                after_pad[:, :Ea].copy_(after)
-                after = after_pad
             step = s.expand_select if sim + 1 < num_simulations else s.expand
-            step(sim, ch.action_logits, ch.value, ch.reward, ch.discount, nxt, dec.chance_logits, dec.afterstate_value, after)
+            step(sim, ch.action_logits, ch.value, ch.reward, ch.discount, nxt.reshape(n, -1), dec.chance_logits, dec.afterstate_value,
+                 after.reshape(n, -1))
         return s.policy_output()[0]
 
     inputs = dict(keys=rng_key, prior=root.prior_logits.float(), value=root.value.float(), emb=pad(state_emb),

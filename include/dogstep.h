@@ -221,6 +221,11 @@ typedef struct {
   float dirichlet_fraction;           /* muzero / stochastic root noise mix; the Dirichlet SAMPLE is an input */
   float temperature;                  /* final sampling temperature (muzero / stochastic) */
   float gumbel_scale;                 /* gumbel */
+  int32_t state_embed_dim;            /* stochastic: floats per row of the `embedding` argument of expand (0 = embed_dim) */
+  int32_t afterstate_embed_dim;       /* stochastic: floats per row of `afterstate_embedding` (0 = embed_dim).  mctx pads the
+                                       * narrower of the two embeddings to the wider one in its tree; with these widths the
+                                       * caller hands over the unpadded rows and expand zero-fills, instead of a pad copy per
+                                       * simulation on the caller's side */
 } dogstep_mcts_cfg;
 
 typedef struct {
@@ -250,6 +255,11 @@ typedef struct {
                                    * level reads the prior row plus the few visited children instead of five dense rows.
                                    * Written by init / expand, read by select; results are identical with and without it.
                                    * If given, every call on this tree (init, select, expand, expand_select) must get it. */
+  int32_t* select_action_decision; /* [n] optional output of select (stochastic): min(action, A - 1), the index the
+                                   * decision_recurrent_fn is evaluated with */
+  int32_t* select_action_chance;  /* [n] optional output of select (stochastic): clamp(action - A, 0, C - 1), the chance
+                                   * outcome the chance_recurrent_fn is evaluated with (mctx evaluates both callbacks on every
+                                   * simulation and picks by node type) */
 } dogstep_mcts_tree;
 
 /* policy prologue + instantiate_tree_from_root.  keys: uint32 [n,2] = the rng_key each game hands to the mctx policy.

@@ -235,6 +235,50 @@ def test_mctx_shaped_policies_run():
     assert out.search_tree.children_visits.shape[-1] == 10
 
 
+def test_stochastic_policy_with_unpadded_embeddings_equals_the_padded_search():
+    """stochastic_muzero_policy hands the state / afterstate embeddings to expand at their own widths (cfg.state_embed_dim /
+    afterstate_embed_dim: the kernel zero-fills) and takes the callbacks' action indices from select: same tree and policy
+    output as the explicit loop that clamps the actions and pads both embeddings on the caller's side (what mctx does)"""
+    from exploring_muzero_on_dog_b200 import mcts
+    n, A, Cn, Es, S = 160, 4, 6, 24, 40
+    Ea = Es + 2
+    net4 = Net(A, Cn, Es, 5)
+    g = torch.Generator(device="cuda").manual_seed(4)
+    root = mcts.RootFnOutput(torch.randn(n, A, device="cuda", generator=g), torch.rand(n, device="cuda", generator=g) * 2 - 1,
+                             torch.randn(n, Es, device="cuda", generator=g))
+    keys = torch.randint(0, 2**31, (n, 2), device="cuda", generator=g).to(torch.uint32)
+    invalid = torch.rand(n, A, device="cuda", generator=g) < 0.4
+    invalid[:, 1] = False
+    noise = torch.distributions.Dirichlet(torch.full((A,), 0.3, device="cuda")).sample((n,))
+
+    def dec(params, rng_key, action, embedding):
+        o = net4(action.long(), embedding)
+        return mcts.DecisionRecurrentFnOutput(o["chance"], o["value"]), torch.cat([o["emb"], o["reward"][:, None], o["discount"][:, None]], 1)
+
+    def ch(params, rng_key, outcome, afterstate):
+        o = net4(outcome.long() + A, afterstate[:, :-2])
+        return mcts.ChanceRecurrentFnOutput(o["prior"], o["value"], afterstate[:, -2], afterstate[:, -1]), o["emb"]
+
+    out = mcts.stochastic_muzero_policy(None, keys, root, dec, ch, S, invalid_actions=invalid, max_depth=50, dirichlet_noise=noise)
+    # the explicit loop: padded rows of width E = max(Es, Ea), clamps on the caller's side
+    E = Ea
+    cfg = mcts._cfg(mcts.STOCHASTIC, mcts.qtransform_by_parent_and_siblings, S, 50, A, Cn, E)
+    s = mcts.Search(cfg, n)
+    pad = lambda x: torch.nn.functional.pad(x, (0, E - x.shape[1]))
+    s.init(keys, mcts.RootFnOutput(root.prior_logits, root.value, pad(root.embedding)), invalid, noise)
+    _, action, emb, _ = s.select(0)
+    for sim in range(S):
+        a = action.long()
+        d, after = dec(None, None, a.clamp(max=A - 1), emb[:, :Es])
+        c, nxt = ch(None, None, (a - A).clamp(min=0, max=Cn - 1), emb[:, :Ea])
+        step = s.expand_select if sim + 1 < S else s.expand
+        step(sim, c.action_logits, c.value, c.reward, c.discount, pad(nxt), d.chance_logits, d.afterstate_value, pad(after))
+    ref, _ = s.policy_output()
+    assert torch.equal(out.action, ref.action) and torch.equal(out.action_weights, ref.action_weights)
+    for k in ("children_visits", "children_values", "node_values", "embeddings", "children_index"):
+        assert torch.equal(getattr(out.search_tree, k), getattr(s.tree, k)), k
+
+
 def test_cuda_graph_replay_equals_eager_search():
     """mcts.GraphCache: the captured search replayed with new inputs gives bit-identical outputs to the eager loop, for the
     three policies (launch-bound loops are replayed as one graph)"""
