@@ -567,7 +567,11 @@ def side_measurements(dev, key, peak):
     ms, moves = e0.elapsed_time(e1), int(plies.sum().item())
     out["ttt_cfg1"] = {"workload": "cfg1: TicTacToeV2 self-play, 512 lockstep games x 50 sims per ply (muzero_policy on the true env with rollouts), "
                                    "to termination; each ply's search replayed as one CUDA graph",
-                       "searched_moves": moves, "ms": ms, "sims_per_s": moves * 50 / (ms / 1e3), "env_steps_per_s": moves / (ms / 1e3)}
+                       "searched_moves": moves, "ms": ms, "sims_per_s": moves * 50 / (ms / 1e3), "env_steps_per_s": moves / (ms / 1e3),
+                       "roofline": _roofline("k_ttt_recurrent_fn (rollout) + k_mcts_expand_select<10,1>", moves * 50, 800, ms, peak, bound="latency",
+                                             note="SURVEY 8(d) cfg 1: 0.8 KB per simulation at depth 3.  512 games are 55 threads per SM and every "
+                                                  "expansion runs a random rollout whose key chain is serial (one Threefry per rollout ply): the "
+                                                  "configuration is bound by the latency of one game's instruction stream, not by bytes or launches")}
     return out
 
 

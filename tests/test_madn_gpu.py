@@ -282,3 +282,26 @@ def test_det_play_random_non_canonical_games_take_the_generic_rules():
     olen, _, _ = O.madn_det_play_random(s, key, 2000)
     assert_state_equal(s, env.numpy())
     assert np.array_equal(olen, glen.cpu().numpy())
+
+
+def test_entry_points_follow_the_device_of_their_tensors():
+    """an env created with device='cuda:1' while cuda:0 is current must run on GPU 1, on GPU 1's current stream
+    (needs two GPUs; the one-GPU test box skips it, `gpurun --gpus 2` runs it)"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from exploring_muzero_on_dog_b200 import jaxrand
+    from exploring_muzero_on_dog_b200.MADN import deterministic_madn as dm
+    torch.cuda.set_device(0)
+    key = jaxrand.split_host(jaxrand.PRNGKey(0))[1]
+    seeds = O.randint(key, 512, 0, 1_000_000)
+    env = dm.env_reset(0, seed=torch.as_tensor(seeds, device="cuda:1"), device="cuda:1", **TRAIN_RULES)
+    assert env.raw("board").device.index == 1 and torch.cuda.current_device() == 0
+    mask = dm.valid_action(env)
+    _, glen = dm.play_random(env, key, max_steps=2000)
+    torch.cuda.synchronize(1)
+    s = O.madn_reset(O.MadnCfg(4, 0xF, 10, mask_of(TRAIN_RULES)), seeds, 0)
+    assert np.array_equal(O.madn_det_valid_action(s), mask.cpu().numpy())
+    olen, _, _ = O.madn_det_play_random(s, key, 2000)
+    assert_state_equal(s, env.numpy())
+    assert np.array_equal(olen, glen.cpu().numpy()) and glen.device.index == 1
