@@ -558,20 +558,29 @@ def side_measurements(dev, key, peak):
                                        "team_1_3_wins": int(win3[:, 1].sum().item())}
     # config 1: TicTacToeV2, 512 lockstep games x 50 simulations per ply, true-env callbacks with rollout, PUCT (TicTacToe/mcts.py:9-23)
     cache = mcts.GraphCache()
-    for rep in range(3):
+    for rep in range(3):  # the per-call path: root_fn / init / 50 x (select, recurrent_fn, expand) launches per move, as one CUDA graph
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         _, plies = tm.play_mcts_games(512, jaxrand.PRNGKey(rep), num_simulations=50, limit=30, variant=1, device=dev, graph_cache=cache)
         e1.record()
         torch.cuda.synchronize()
+    ms_calls = e0.elapsed_time(e1)
+    fused = {}
+    for rep in range(3):  # the whole search of a move as ONE launch, one game per warp (dogstep_ttt_search)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _, plies = tm.play_mcts_games(512, jaxrand.PRNGKey(rep), num_simulations=50, limit=30, variant=1, device=dev, fused=fused)
+        e1.record()
+        torch.cuda.synchronize()
     ms, moves = e0.elapsed_time(e1), int(plies.sum().item())
     out["ttt_cfg1"] = {"workload": "cfg1: TicTacToeV2 self-play, 512 lockstep games x 50 sims per ply (muzero_policy on the true env with rollouts), "
-                                   "to termination; each ply's search replayed as one CUDA graph",
+                                   "to termination; each move's whole search is one launch, one game per warp (k_ttt_search)",
+                       "per_call_path_ms": ms_calls, "per_call_path_sims_per_s": moves * 50 / (ms_calls / 1e3),
                        "searched_moves": moves, "ms": ms, "sims_per_s": moves * 50 / (ms / 1e3), "env_steps_per_s": moves / (ms / 1e3),
-                       "roofline": _roofline("k_ttt_recurrent_fn (rollout) + k_mcts_expand_select<10,1>", moves * 50, 800, ms, peak, bound="latency",
-                                             note="SURVEY 8(d) cfg 1: 0.8 KB per simulation at depth 3.  512 games are 55 threads per SM and every "
-                                                  "expansion runs a random rollout whose key chain is serial (one Threefry per rollout ply): the "
-                                                  "configuration is bound by the latency of one game's instruction stream, not by bytes or launches")}
+                       "roofline": _roofline("k_ttt_search", moves * 50, 800, ms, peak, bound="latency",
+                                             note="SURVEY 8(d) cfg 1: 0.8 KB per simulation at depth 3.  512 games are 512 warps on 148 SMs and "
+                                                  "every expansion runs a random rollout whose key chain is serial (one Threefry per rollout "
+                                                  "ply): bound by the latency of one game's instruction stream, not by bytes")}
     return out
 
 

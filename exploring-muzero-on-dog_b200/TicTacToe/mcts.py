@@ -26,22 +26,66 @@ def _root(env, rng_key):
 _QT = functools.partial(_mcts.qtransform_by_min_max, min_value=-1, max_value=1)
 
 
-def run_mcts(rng_key, env, num_simulations, graph_cache=None):
-    """run_mcts (:10-23); rng_key uint32 [games, 2].  graph_cache: optional mcts.GraphCache — the 3 x num_simulations
-    launches of one move are then replayed as one CUDA graph (the loop is launch-bound at 512 games)."""
+class FusedSearch:
+    """The whole true-env search of one move as ONE launch (dogstep_ttt_search): root_fn, init, num_simulations x (select,
+    recurrent_fn with its rollout, expand), policy output — one game per warp, no synchronisation between games.  Driven
+    simulation by simulation, every simulation waits for the longest rollout of the batch (86 % of config 1); bit-identical to
+    that path.  Buffers (tree + per-game work rows) are allocated once and reused move after move."""
+
+    def __init__(self, policy, n, num_simulations, device):
+        cfg = _mcts._cfg(policy, _QT, num_simulations, 9, 9, 0, 18, dirichlet_fraction=0.0)
+        self.search = _mcts.Search(cfg, n, device)
+        f = lambda *shape: torch.empty(shape, dtype=torch.float32, device=device)
+        self.rows = dict(prior_logits=f(n, 9), value=f(n), reward=f(n), discount=f(n), next_embedding=f(n, 18), root_prior_logits=f(n, 9),
+                         root_value=f(n), root_embedding=f(n, 18))
+        s = self.search
+        self.scratch = _lib.tag(_lib.TttSearchScratch(*[C.c_void_p(t.data_ptr()) for t in (
+            s.parent, s.action, s.embedding, s.expand_key, self.rows["prior_logits"], self.rows["value"], self.rows["reward"],
+            self.rows["discount"], self.rows["next_embedding"], self.rows["root_prior_logits"], self.rows["root_value"],
+            self.rows["root_embedding"])]), s.parent.device)
+        self.action = torch.empty(n, dtype=torch.int32, device=device)
+        self.weights = torch.empty((n, 9), dtype=torch.float32, device=device)
+        self.value = torch.empty(n, dtype=torch.float32, device=device)
+
+    def __call__(self, env, rng_key):
+        key1, key2 = _split_each(rng_key, 0), _split_each(rng_key, 1)   # key1, key2 = split(rng_key)              (mcts.py:12)
+        root_keys = _split_each(key2, 0)                                 # split(key2, batch_size = 1)[0]           (:15)
+        s, st = self.search, env.cstate()
+        _lib.check(_lib.lib().dogstep_ttt_search(C.byref(st), C.c_int64(env.n), C.c_int32(env.static["variant"]), C.byref(s._ct),
+                                                C.byref(s.cfg), _lib.ptr(key1), _lib.ptr(root_keys), C.byref(self.scratch),
+                                                _lib.ptr(self.action), _lib.ptr(self.weights), _lib.ptr(self.value), _lib.stream()),
+                   "ttt_search")
+        return _mcts.PolicyOutput(action=self.action, action_weights=self.weights, search_tree=s.tree)
+
+
+def _fused(cache, policy, env, num_simulations):
+    key = (policy, env.n, num_simulations, str(env.device))
+    fs = cache.get(key)
+    if fs is None:
+        fs = cache[key] = FusedSearch(policy, env.n, num_simulations, env.device)
+    return fs
+
+
+def run_mcts(rng_key, env, num_simulations, graph_cache=None, fused=None):
+    """run_mcts (:10-23); rng_key uint32 [games, 2].  fused: a dict the caller keeps (one launch per move, see FusedSearch);
+    graph_cache: optional mcts.GraphCache — the 3 x num_simulations launches of one move replayed as one CUDA graph."""
+    if fused is not None:
+        return _fused(fused, _mcts.MUZERO, env, num_simulations)(env, rng_key)
     key1, root = _root(env, rng_key)
     return _mcts.muzero_policy(None, key1, root, game.make_recurrent_fn(env.static["variant"]), num_simulations, max_depth=9,
                                qtransform=_QT, dirichlet_fraction=0.0, graph_cache=graph_cache)
 
 
-def run_gumbel(rng_key, env, num_simulations, graph_cache=None):
+def run_gumbel(rng_key, env, num_simulations, graph_cache=None, fused=None):
     """run_gumbel (:25-38)"""
+    if fused is not None:
+        return _fused(fused, _mcts.GUMBEL, env, num_simulations)(env, rng_key)
     key1, root = _root(env, rng_key)
     return _mcts.gumbel_muzero_policy(None, key1, root, game.make_recurrent_fn(env.static["variant"]), num_simulations, max_depth=9,
                                       qtransform=_QT, graph_cache=graph_cache)
 
 
-def play_mcts_games(n, rng_key, num_simulations=50, limit=30, variant=1, device="cuda", search=run_mcts, graph_cache=None):
+def play_mcts_games(n, rng_key, num_simulations=50, limit=30, variant=1, device="cuda", search=run_mcts, graph_cache=None, fused=None):
     """BASELINE config 1: n lockstep games, both sides pick run_mcts(...).action every ply, until all are done or `limit`
     plies (TicTacToe/eval.py:97-125 with get_mcts_action on both seats).  Returns (env, plies played per game)."""
     env = game.env_reset(0, n=n, device=device, variant=variant)
@@ -52,7 +96,8 @@ def play_mcts_games(n, rng_key, num_simulations=50, limit=30, variant=1, device=
         if not bool(live.any()):
             break
         key, sub = jaxrand.split_host(key)                            # rng_key, action_key = split(rng_key)
-        out = search(jaxrand.split(sub, n, device=device), env, num_simulations, **({} if graph_cache is None else {"graph_cache": graph_cache}))
+        kw = {"fused": fused} if fused is not None else ({} if graph_cache is None else {"graph_cache": graph_cache})
+        out = search(jaxrand.split(sub, n, device=device), env, num_simulations, **kw)
         stepped, _, _ = game.env_step(env, out.action.to(torch.int8))
         merged = {k: torch.where(live.reshape((-1,) + (1,) * (stepped.raw(k).ndim - 1)), stepped.raw(k), env.raw(k))
                   for k in ("board", "current_player", "reward", "done", "memory")}

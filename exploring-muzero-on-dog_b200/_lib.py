@@ -216,5 +216,10 @@ class ReplayBatch(C.Structure):
                                           "discount_targets", "dice_outcomes", "dice_probs")]
 
 
+class TttSearchScratch(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("parent", "action", "embedding", "expand_key", "prior_logits", "value", "reward", "discount",
+                                          "next_embedding", "root_prior_logits", "root_value", "root_embedding")]
+
+
 class TttState(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("board", "current_player", "reward", "done", "memory")]

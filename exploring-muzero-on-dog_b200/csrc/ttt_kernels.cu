@@ -7,119 +7,9 @@
 #include "../../include/dogstep.h"
 #include "common.cuh"
 #include "jaxrand.cuh"
+#include "ttt_core.cuh"
 
 namespace dogstep {
-
-struct Ttt {
-  int8_t board[9];
-  int8_t cur, reward, done;
-  int8_t memory[6];
-};
-
-__device__ __forceinline__ float t_log(float x) { return (float)log((double)x); }
-__device__ __forceinline__ int t_floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
-__device__ __forceinline__ int t_mod(int a, int b) { int r = a % b; return r < 0 ? r + b : r; }
-__device__ __forceinline__ int t_wrap(int i, int n) { i = i < 0 ? i + n : i; return min(max(i, 0), n - 1); }
-
-__device__ __forceinline__ int ttt_winner(const int8_t* b) {
-  int w = 0, neg = 0;
-#define TTT_LINE(a, c, d) { int s = b[a] + b[c] + b[d]; w |= (s == 3); neg |= (s == -3); }
-  TTT_LINE(0, 1, 2) TTT_LINE(3, 4, 5) TTT_LINE(6, 7, 8) TTT_LINE(0, 3, 6) TTT_LINE(1, 4, 7) TTT_LINE(2, 5, 8) TTT_LINE(0, 4, 8) TTT_LINE(2, 4, 6)
-#undef TTT_LINE
-  return neg ? -1 : w;
-}
-
-__device__ void ttt_step(int variant, Ttt& e, int action_in) {
-  const int action = (int)(int8_t)action_in;
-  const int cell = t_wrap(t_floordiv(action, 3), 3) * 3 + t_wrap(t_mod(action, 3), 3);
-  const int invalid = e.board[cell] != 0;
-  const int keep = e.done || invalid;
-  int8_t board[9];
-#pragma unroll
-  for (int k = 0; k < 9; ++k) board[k] = e.board[k];
-  if (!keep) board[cell] = e.cur;
-  if (variant == 1) {
-    int8_t* m = e.memory + 3 * (e.cur < 0);
-    const int removed = m[0];
-    // ((done | invalid) | removed_action) == -1 in int8 arithmetic (TicTacToeV2.py:66)
-    const int keep_removed = (int8_t)((int8_t)keep | (int8_t)removed) == -1;
-    const int rc = t_wrap(t_floordiv(removed, 3), 3) * 3 + t_wrap(t_mod(removed, 3), 3);
-    if (!keep_removed) board[rc] = 0;
-    if (!keep) { m[0] = m[1]; m[1] = m[2]; m[2] = (int8_t)action; }
-  }
-  const int reward = e.done ? 0 : (invalid ? -1 : ttt_winner(board) * e.cur);
-  int full = 1;
-#pragma unroll
-  for (int k = 0; k < 9; ++k) full &= board[k] != 0;
-  int done;
-  if (variant == 1) done = (int)(int8_t)((int8_t)e.done | (int8_t)reward) != (0 | invalid | full);  // (:70)
-  else done = e.done || reward != 0 || invalid || full;
-#pragma unroll
-  for (int k = 0; k < 9; ++k) e.board[k] = board[k];
-  e.cur = (int8_t)(done ? e.cur : -e.cur);
-  e.done = (int8_t)done;
-  e.reward = (int8_t)reward;
-}
-
-// policy_function (TicTacToe.py / TicTacToeV2.py): logit of ONE action
-__device__ float ttt_policy_a(int variant, const Ttt& e, int a) {
-  float v = (!e.done && e.board[a] == 0) ? 100.0f : 0.0f;
-  for (int side = 0; side < 2; ++side) {
-    Ttt t = e;
-    t.cur = (int8_t)(side == 0 ? -e.cur : e.cur);
-    ttt_step(variant, t, a);
-    if (t.reward == 1) v = __fadd_rn(v, side == 0 ? 200.0f : 300.0f);
-  }
-  return v;
-}
-
-__device__ void ttt_policy(int variant, const Ttt& e, float logits[9]) {
-  for (int a = 0; a < 9; ++a) logits[a] = ttt_policy_a(variant, e, a);
-}
-
-// rollout to termination with the heuristic policy (categorical over its logits), by a GROUP of 16 lanes that all hold the
-// same game: lane `sub` < 9 evaluates action `sub` (policy logit, Gumbel draw), the argmax is a 4-step butterfly inside the
-// group (largest value, lowest action on ties = the sequential first-maximum), every lane applies the move.  One thread per
-// game walked the nine actions one after the other: 1.2 ms per call for 512 games on four SMs (rollouts of the memory
-// variant run for > 100 plies).
-__device__ float ttt_rollout_group(int variant, const Ttt& e0, Key2 key, int sub, uint32_t gmask) {
-  Ttt e = e0;
-  // key chain of the rollout: key_{t+1}, sub_t = split(key_t).  The group keeps sub_t and key_{t+1}; every iteration is ONE
-  // Threefry pass over the lanes: lanes 0..8 draw their action's uniform from sub_t, lane 9 derives key_{t+2} and lane 10
-  // sub_{t+1} from key_{t+1} (three dependent Threefry calls per ply otherwise).
-  const int base = (threadIdx.x & 31) & 16;  // first lane of this group inside the warp
-  Key2 sk = split_i(key, 1), kn = split_i(key, 0);
-  for (int it = 0; it < 100000 && !e.done; ++it) {
-    const Key2 k = sub < 9 ? sk : kn;
-    const uint32_t ctr = sub < 9 ? (uint32_t)sub : (sub == 10 ? 1u : 0u);
-    const Key2 o = threefry2x32(k, 0u, ctr);
-    const Key2 kn2{__shfl_sync(gmask, o.a, base + 9), __shfl_sync(gmask, o.b, base + 9)};
-    const Key2 sk1{__shfl_sync(gmask, o.a, base + 10), __shfl_sync(gmask, o.b, base + 10)};
-    float v = 0.0f;
-    int a = sub;
-    if (sub < 9) {
-      const float lg = ttt_policy_a(variant, e, sub);
-      const float f = bits_to_unit_float(o.a ^ o.b);  // uniform(sub_t, minval = tiny, maxval = 1)[sub], as uniform_i
-      const float u = fmaxf(1.17549435e-38f, __fadd_rn(__fmul_rn(f, __fsub_rn(1.0f, 1.17549435e-38f)), 1.17549435e-38f));
-      v = __fadd_rn(-t_log(-t_log(u)), lg);
-    } else {
-      a = 0x7FFF;  // never wins: handled by the validity flag below
-    }
-    bool has = sub < 9;
-#pragma unroll
-    for (int o2 = 8; o2; o2 >>= 1) {
-      const float ov = __shfl_xor_sync(gmask, v, o2);
-      const int oa = __shfl_xor_sync(gmask, a, o2);
-      const bool oh = __shfl_xor_sync(gmask, (int)has, o2) != 0;
-      const bool take = oh && (!has || ov > v || (ov == v && oa < a));
-      if (take) { v = ov; a = oa; has = true; }
-    }
-    ttt_step(variant, e, a);
-    sk = sk1;
-    kn = kn2;
-  }
-  return (float)(int8_t)(e.reward * e.cur * e0.cur);
-}
 
 struct TttPtrs { int8_t* board; int8_t* cur; int8_t* reward; uint8_t* done; int8_t* memory; };
 
@@ -133,17 +23,6 @@ __device__ __forceinline__ void ttt_store(const TttPtrs& p, int64_t g, const Ttt
   p.cur[g] = e.cur; p.reward[g] = e.reward; p.done[g] = (uint8_t)e.done;
   for (int k = 0; k < 6; ++k) p.memory[6 * g + k] = e.memory[k];
 }
-__device__ __forceinline__ void ttt_to_emb(const Ttt& e, float* f) {
-  for (int k = 0; k < 9; ++k) f[k] = (float)e.board[k];
-  f[9] = (float)e.cur; f[10] = (float)e.reward; f[11] = (float)e.done;
-  for (int k = 0; k < 6; ++k) f[12 + k] = (float)e.memory[k];
-}
-__device__ __forceinline__ void ttt_from_emb(Ttt& e, const float* f) {
-  for (int k = 0; k < 9; ++k) e.board[k] = (int8_t)f[k];
-  e.cur = (int8_t)f[9]; e.reward = (int8_t)f[10]; e.done = (int8_t)f[11];
-  for (int k = 0; k < 6; ++k) e.memory[k] = (int8_t)f[12 + k];
-}
-
 __global__ void k_ttt_reset(TttPtrs p, int64_t n) {
   int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n) return;

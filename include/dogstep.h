@@ -453,6 +453,32 @@ int dogstep_ttt_recurrent_fn(int64_t n, int32_t variant, const uint32_t* keys, c
                              float* prior_logits, float* value, float* reward, float* discount, float* embedding_out,
                              void* stream);
 
+/* run_mcts / run_gumbel of TicTacToe/mcts.py:9-38 as ONE launch per move: root_fn, tree init, num_simulations x (select ->
+ * recurrent_fn on the true env, incl. its random rollout -> expand + backup) and the policy output, one game per warp with no
+ * synchronisation between games (a simulation driven from the host waits for the longest rollout of the whole batch).  Same
+ * device code, keys and order of operations as dogstep_ttt_root_fn / dogstep_mcts_init / _select / dogstep_ttt_recurrent_fn /
+ * _expand / _policy_output called in sequence: bit-identical results.  search_keys u32 [n,2] = the rng_key handed to
+ * mctx.muzero_policy (mcts.py:12 key1), root_keys u32 [n,2] = the key root_fn's rollout gets (split(key2, 1)[0], :15);
+ * the scratch rows are per-game work buffers the caller allocates once; outputs as dogstep_mcts_policy_output.
+ * cfg: num_actions 9, num_chance 0, embed_dim 18, dirichlet_fraction 0 (else DOGSTEP_ERR_UNSUPPORTED). */
+typedef struct {
+  int32_t* parent;          /* [n] */
+  int32_t* action;          /* [n] */
+  float* embedding;         /* [n, 18] parent embedding of the current simulation */
+  uint32_t* expand_key;     /* [n, 2] */
+  float* prior_logits;      /* [n, 9] */
+  float* value;             /* [n] */
+  float* reward;            /* [n] */
+  float* discount;          /* [n] */
+  float* next_embedding;    /* [n, 18] */
+  float* root_prior_logits; /* [n, 9] */
+  float* root_value;        /* [n] */
+  float* root_embedding;    /* [n, 18] */
+} dogstep_ttt_search_scratch;
+int dogstep_ttt_search(const dogstep_ttt_state* s, int64_t n, int32_t variant, const dogstep_mcts_tree* t, const dogstep_mcts_cfg* cfg,
+                       const uint32_t* search_keys, const uint32_t* root_keys, const dogstep_ttt_search_scratch* scratch,
+                       int32_t* action_out, float* action_weights_out, float* root_value_out, void* stream);
+
 /* ---------------------------------------------------------------- jax.random on device
  * Stand-ins for the jax.random calls the self-play drivers make around the env functions
  * (game_agent.py:60,187-188).  keys are raw uint32[2]. */

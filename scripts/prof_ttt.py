@@ -1,14 +1,31 @@
-"""BASELINE config 1 timing: TicTacToe, 512 lockstep games x 50 simulations per ply (profiling helper)"""
-import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import torch
-from exploring_muzero_on_dog_b200 import jaxrand, mcts
-from exploring_muzero_on_dog_b200.TicTacToe import mcts as tm
-n, S = 512, 50
-for name, cache in (("eager", None), ("graph", mcts.GraphCache())):
-    for rep in range(3):
-        torch.cuda.synchronize(); t0 = time.perf_counter()
-        env, plies = tm.play_mcts_games(n, jaxrand.PRNGKey(rep), num_simulations=S, limit=30, variant=1, graph_cache=cache)
-        torch.cuda.synchronize(); dt = time.perf_counter() - t0
-        moves = int(plies.sum().item())
-        print(f"{name}: {moves} searched moves x {S} sims in {dt*1e3:.1f} ms -> {moves*S/dt/1e6:.2f} M sims/s, {moves/dt/1e3:.1f} k env steps/s")
+#!/usr/bin/env python
+"""Kernel-time breakdown of BASELINE config 1 (TicTacToeV2 self-play, 512 games x 50 sims per ply), eager launches, through
+torch.profiler.  python scripts/prof_ttt.py [games]"""
+import collections
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+from torch.profiler import ProfilerActivity, profile  # noqa: E402
+
+from exploring_muzero_on_dog_b200 import jaxrand  # noqa: E402
+from exploring_muzero_on_dog_b200.TicTacToe import mcts as tm  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+tm.play_mcts_games(n, jaxrand.PRNGKey(0), num_simulations=50, limit=30, variant=1)
+torch.cuda.synchronize()
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    _, plies = tm.play_mcts_games(n, jaxrand.PRNGKey(1), num_simulations=50, limit=30, variant=1)
+    torch.cuda.synchronize()
+tot, cnt = collections.Counter(), collections.Counter()
+for e in prof.events():
+    if e.device_type == torch.autograd.DeviceType.CUDA:
+        tot[e.name] += e.device_time_total
+        cnt[e.name] += 1
+total = sum(tot.values())
+moves = int(plies.sum().item())
+print(f"{n} games, {moves} searched moves, {int(plies.max())} plies, {total / 1e3:.1f} ms of kernel time, {moves * 50 / (total / 1e6) / 1e6:.2f} M sims/s on kernel time")
+for name, us in tot.most_common(12):
+    print(f"{us / 1e3:9.2f} ms  {cnt[name]:6d} launches  {us / cnt[name]:8.1f} us each  {name[:100]}")

@@ -165,3 +165,42 @@ def test_config1_graph_replay_plays_the_same_games():
         assert torch.equal(pa, pb)
         for k, v in a.numpy().items():
             assert np.array_equal(v, b.numpy()[k]), k
+
+
+@pytest.mark.gpu
+def test_fused_search_equals_the_per_call_search():
+    """dogstep_ttt_search (the whole search of a move as one launch, one game per warp) == the same search driven simulation
+    by simulation through root_fn / init / select / recurrent_fn / expand / policy_output: action, weights, every tree array"""
+    import torch
+    from exploring_muzero_on_dog_b200 import jaxrand
+    from exploring_muzero_on_dog_b200.TicTacToe import TicTacToeV2 as g
+    from exploring_muzero_on_dog_b200.TicTacToe import mcts as tm
+    n = 200
+    rng = np.random.default_rng(5)
+    for variant, search in ((0, tm.run_mcts), (1, tm.run_mcts), (1, tm.run_gumbel)):
+        s = O.TttState(n, variant)
+        for t in range(4):
+            O.ttt_step(s, rng.integers(0, 9, n))
+        s.done[::7] = 1                                  # finished games are searched too (the reference does not mask them)
+        env = g.env_reset(0, n=n, variant=variant).replace(board=s.board, current_player=s.current_player, reward=s.reward,
+                                                            done=s.done.astype(bool), memory=s.memory)
+        keys = jaxrand.split(jaxrand.PRNGKey(variant + 3), n)
+        a = search(keys, env, 50)
+        b = search(keys, env, 50, fused={})
+        assert torch.equal(a.action, b.action) and torch.equal(a.action_weights, b.action_weights)
+        for k in ("node_visits", "raw_values", "node_values", "parents", "action_from_parent", "children_index", "children_prior_logits",
+                  "children_visits", "children_rewards", "children_discounts", "children_values", "embeddings"):
+            assert torch.equal(getattr(a.search_tree, k), getattr(b.search_tree, k)), (variant, k)
+
+
+@pytest.mark.gpu
+def test_config1_fused_plays_the_same_games():
+    import torch
+    from exploring_muzero_on_dog_b200 import jaxrand
+    from exploring_muzero_on_dog_b200.TicTacToe import mcts as tm
+    for variant, search in ((0, tm.run_mcts), (1, tm.run_gumbel), (1, tm.run_mcts)):
+        a, pa = tm.play_mcts_games(512, jaxrand.PRNGKey(3), num_simulations=50, limit=30, variant=variant, search=search)
+        b, pb = tm.play_mcts_games(512, jaxrand.PRNGKey(3), num_simulations=50, limit=30, variant=variant, search=search, fused={})
+        assert torch.equal(pa, pb)
+        for k, v in a.numpy().items():
+            assert np.array_equal(v, b.numpy()[k]), k
