@@ -15,6 +15,7 @@
 #include "jaxrand.cuh"
 #include "madn_core.cuh"
 #include "madn_fast.cuh"
+#include "madn_track.cuh"
 
 namespace dogstep {
 
@@ -502,26 +503,16 @@ __global__ void __launch_bounds__(kThreads) k_madn_eval_step(const __grid_consta
 // [32 games x 24 actions] mantissa table in shared memory.
 constexpr int kPlayWarps = kThreads / 32;
 
-__global__ void __launch_bounds__(kThreads) k_madn_det_play_random(const __grid_constant__ MadnGeom g, MadnPtrs p, int64_t n,
-                                                                   Key2 rng0, int64_t game_offset, int max_steps,
-                                                                   int32_t* __restrict__ game_len,
-                                                                   unsigned long long* __restrict__ total_steps) {
-  __shared__ uint16_t s_items[kPlayWarps][32 * 24];
-  __shared__ uint32_t s_mant[kPlayWarps][32 * 24];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// One warp, one game per lane, to the end (generic rules: any player count / distance / state).  `items` [32 * 24] and
+// `mant` [32 * 24] are this warp's shared work arrays.  Also the fallback of the specialised kernel below for CTAs that hold
+// a state outside the specialised rules' domain — a separate function with its own register allocation.
+__device__ __noinline__ void play_random_warp(const MadnGeom& g, const MadnPtrs& p, int64_t i, bool have, MadnRegs& s, Key2 rng,
+                                              uint32_t my, int max_steps, int32_t* __restrict__ game_len,
+                                              unsigned long long* __restrict__ total_steps, uint16_t* items, uint32_t* mant) {
+  const int lane = threadIdx.x & 31;
   const uint32_t FULL = 0xFFFFFFFFu;
-  int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   int len = 0;
-  MadnRegs s;
-  bool alive = false;
-  if (i < n) {
-    load_state<true>(g, p, i, s);
-    alive = !s.done;
-  }
-  Key2 rng = rng0;
-  const uint32_t my = (uint32_t)(game_offset + i + 1);
-  uint16_t* items = s_items[warp];
-  uint32_t* mant = s_mant[warp];
+  bool alive = have && !s.done;
   for (int t = 0; t < max_steps; ++t) {
     if (!__any_sync(FULL, alive)) break;
     const Key2 key = split_i(rng, my);  // split(rng, N+1)[j+1]
@@ -566,7 +557,7 @@ __global__ void __launch_bounds__(kThreads) k_madn_det_play_random(const __grid_
     }
     __syncwarp();
   }
-  if (i < n) {
+  if (have) {
     store_det_all(g, p, i, s);
     if (game_len) game_len[i] = len;
   }
@@ -576,6 +567,20 @@ __global__ void __launch_bounds__(kThreads) k_madn_det_play_random(const __grid_
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
     if (lane == 0 && v) atomicAdd(total_steps, (unsigned long long)v);
   }
+}
+
+__global__ void __launch_bounds__(kThreads) k_madn_det_play_random(const __grid_constant__ MadnGeom g, MadnPtrs p, int64_t n,
+                                                                   Key2 rng0, int64_t game_offset, int max_steps,
+                                                                   int32_t* __restrict__ game_len,
+                                                                   unsigned long long* __restrict__ total_steps) {
+  __shared__ uint16_t s_items[kPlayWarps][32 * 24];
+  __shared__ uint32_t s_mant[kPlayWarps][32 * 24];
+  const int warp = threadIdx.x >> 5;
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  MadnRegs s;
+  if (i < n) load_state<true>(g, p, i, s);
+  play_random_warp(g, p, i, i < n, s, rng0, (uint32_t)(game_offset + i + 1), max_steps, game_len, total_steps, s_items[warp],
+                   s_mant[warp]);
 }
 
 // Persistent lockstep loop for 4 players, distance 10 — every configuration of the reference (the generic kernel above
@@ -595,24 +600,120 @@ __global__ void __launch_bounds__(kThreads) k_madn_det_play_random(const __grid_
 // A CTA that loaded a non-canonical game (see madn_fast.cuh) runs the generic rules of madn_core.cuh instead.
 #ifdef DOGSTEP_TRACE
 __device__ unsigned long long g_play_trace[128];
+__device__ int g_play_trace_block;
 #endif
 constexpr int kPlayRound = 64;  // 24 / 32 / 48 / 64: 2.21 / 2.19 / 2.18 / 2.175 ms on config 2 (with key ring and tail mode)
 constexpr int kPlayMaxThreads = 512;  // game threads per CTA (+ 32: the producer warp)
-constexpr int kXWords = 23;  // occ 8, pins 4, action set 8, cur|reward, len, game index
+constexpr int kXWords = 23;  // cur|reward, len, game index + PlayState::kWords (at most 20: occ 8, pins 4, action set 8)
 
 constexpr int kRingMax = 64;  // longest round the key ring holds
+// draw-ahead mode (see the kernel): at most kPSlots live games on four warps, the other warps draw kPChunk iterations ahead
+constexpr int kPEnter = 64;   // live games per CTA at which the mode is entered (<= kPSlots)
+constexpr int kPSlots = 128, kPChunk = 4, kPStride = 28;  // 24 draws per (iteration, game) row, padded: conflict-free 16-byte reads
 // `threads` = game threads (the CTA has one more warp, the key-chain producer)
 static size_t play_smem_bytes(int threads) {
   return (size_t)(threads / 32) * (24 * 32 * 2 + 32 * 4 + 32 * 8) + (size_t)kXWords * threads * 4 + 2 * 34 * 4 +
-         2 * (kRingMax + 2) * 8;
+         2 * (kRingMax + 2) * 8 + (size_t)2 * kPChunk * kPSlots * (kPStride * 4 + 8) + kPSlots * 4;
 }
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {
+  __threadfence_block();
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+// The four warp schedulers of an SM take the warps of a CTA round robin (warp w -> scheduler w % 4) and every one of them is
+// bound by its own integer pipe, so a round lasts as long as the scheduler with the most games needs: L live games go to the
+// fewest warps that can hold them with the SAME number on every scheduler (4 * ceil(L / 128) warps), spread evenly — 443
+// games are 16 warps of 27-28 instead of 13 of 32 and one of 27 (schedulers 0 and 1 then carried 128 games against 96 and
+// 91).  The odd games go to the highest warps: scheduler 0 also runs the key-chain producer.
+struct PlayShare {
+  int wa, base, first_big;  // warps in use, games per warp, first warp that holds base + 1
+  __device__ PlayShare(int L, int W) {
+    wa = min(4 * ((L + 127) >> 7), W);
+    base = L / wa;
+    first_big = wa - (L - base * wa);
+  }
+  __device__ int count(int w) const { return w < wa ? base + (w >= first_big) : 0; }
+  __device__ int start(int w) const { return w * base + max(0, w - first_big); }
+};
+
+// What the persistent kernel keeps of a game, per rule program.  Run-time rule mask: the bitboard registers and branch-free
+// rules of madn_fast.cuh (23 words).  The training rule dict: the track state of madn_track.cuh (8 words, no board).
+template <uint32_t CT>
+struct PlayState {
+  static constexpr int kWords = 20;
+  MadnRegs s;
+  __device__ bool from_regs(const MadnRegs& r) { s = r; return is_canonical4(r, r.occ); }
+  __device__ void to_regs(const MadnGeom&, MadnRegs& r) const { r = s; }
+  __device__ bool done() const { return s.done != 0; }
+  __device__ uint32_t mask(const RuleSet<CT> R, const MadnGeom& g, int& cp) const { return det_valid_mask4(R, g, s, cp); }
+  __device__ void step(const RuleSet<CT> R, int cp, int a) { det_step4(R, s, cp, a); }
+  __device__ void no_step() { det_no_step4(s); }
+  __device__ void pack(uint32_t* x, int T) const {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      x[(2 * q) * T] = (uint32_t)s.occ[q];
+      x[(2 * q + 1) * T] = (uint32_t)(s.occ[q] >> 32);
+      x[(8 + q) * T] = s.pins[q];
+      x[(12 + 2 * q) * T] = (uint32_t)s.as[q];
+      x[(13 + 2 * q) * T] = (uint32_t)(s.as[q] >> 32);
+    }
+  }
+  __device__ void unpack(const uint32_t* x, int T) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      s.occ[q] = (uint64_t)x[(2 * q) * T] | ((uint64_t)x[(2 * q + 1) * T] << 32);
+      s.pins[q] = x[(8 + q) * T];
+      s.as[q] = (uint64_t)x[(12 + 2 * q) * T] | ((uint64_t)x[(13 + 2 * q) * T] << 32);
+    }
+    s.done = 0;
+    s.die = 0;
+  }
+  __device__ int& cur() { return s.cur; }
+  __device__ int& reward() { return s.reward; }
+};
+
+template <>
+struct PlayState<kTrainRules> {
+  static constexpr int kWords = 8;
+  Track4 s;
+  __device__ bool from_regs(const MadnRegs& r) { return track_from_regs(r, s); }
+  __device__ void to_regs(const MadnGeom& g, MadnRegs& r) const { track_to_regs(g, s, r); }
+  __device__ bool done() const { return s.done != 0; }
+  __device__ uint32_t mask(const RuleSet<kTrainRules>, const MadnGeom&, int& cp) const { return track_valid_mask(s, cp); }
+  __device__ void step(const RuleSet<kTrainRules>, int cp, int a) { track_step(s, cp, a); }
+  __device__ void no_step() { track_no_step(s); }
+  __device__ void pack(uint32_t* x, int T) const {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      x[q * T] = s.pins[q];
+      x[(4 + q) * T] = s.as[q];
+    }
+  }
+  __device__ void unpack(const uint32_t* x, int T) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      s.pins[q] = x[q * T];
+      s.as[q] = x[(4 + q) * T];
+    }
+    s.done = 0;
+  }
+  __device__ int& cur() { return s.cur; }
+  __device__ int& reward() { return s.reward; }
+};
 
 template <uint32_t CT>
 __global__ void __launch_bounds__(kPlayMaxThreads + 32) k_madn_det_play_cta(const __grid_constant__ MadnGeom g, MadnPtrs p, int64_t n,
                                                                       Key2 rng0, int64_t game_offset, int max_steps,
                                                                       int32_t* __restrict__ game_len,
                                                                       unsigned long long* __restrict__ total_steps, int round_len,
-                                                                      int games_per_cta) {
+                                                                      int games_per_cta, int p_enter) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int T = blockDim.x - 32, W = T >> 5;  // game threads / warps; the CTA's last warp produces the key chain
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -624,14 +725,19 @@ __global__ void __launch_bounds__(kPlayMaxThreads + 32) k_madn_det_play_cta(cons
   uint32_t* s_x = reinterpret_cast<uint32_t*>(smem_raw + (size_t)W * 1920);                     // [kXWords][T]
   uint32_t* s_cnt = s_x + (size_t)kXWords * T;                                                  // 2 x [34] counts
   uint2* s_ring = reinterpret_cast<uint2*>(s_cnt + 2 * 34);                                     // 2 x [kRingMax + 2] keys
+  uint32_t* s_draw = reinterpret_cast<uint32_t*>(s_ring + 2 * (kRingMax + 2));                  // [2][kPChunk][kPSlots][kPStride]
+  uint2* s_pkey = reinterpret_cast<uint2*>(s_draw + 2 * kPChunk * kPSlots * kPStride);          // [2][kPSlots * kPChunk] step keys
+  uint32_t* s_pmy = reinterpret_cast<uint32_t*>(s_pkey + 2 * kPChunk * kPSlots);                // [kPSlots] split index of the game
   const uint32_t FULL = 0xFFFFFFFFu;
   const int64_t cta_base = (int64_t)blockIdx.x * games_per_cta;  // games_per_cta <= T: the games are spread over ALL SMs
-  int gi = threadIdx.x;  // game held by this lane, relative to cta_base
+  const int games_here = (int)max((int64_t)0, min((int64_t)games_per_cta, n - cta_base));
+  int gi = 0;  // game held by this lane, relative to cta_base
   const RuleSet<CT> R{g.rules};
   int len = 0;
   unsigned steps_done = 0;
-  MadnRegs s;
-  bool alive = false, canon = true;
+  PlayState<CT> s;
+  MadnRegs r0;  // as loaded (only live until the rule program is chosen)
+  bool alive = false, canon = true, have = false;
   if (producer) {
     // The loop key chain rng_{t+1} = split(rng_t, N + 1)[0] (game_agent.py:60) is the same for every game: one warp per CTA
     // computes it, a round ahead, into a double-buffered ring (ring[i] = rng_{t0 + i}, i = 0..round_len + 1) instead of
@@ -643,83 +749,94 @@ __global__ void __launch_bounds__(kPlayMaxThreads + 32) k_madn_det_play_cta(cons
       r = split_i(r, 0u);
       if (lane == 0) s_ring[i] = make_uint2(r.a, r.b);
     }
-  } else if (gi < games_per_cta && cta_base + gi < n) {
-    load_state<true>(g, p, cta_base + gi, s);
-    canon = is_canonical4(s, s.occ);
-    alive = !s.done;
-    if (!alive && game_len) game_len[cta_base + gi] = 0;
+  } else if (games_here > 0 && lane < PlayShare(games_here, W).count(warp)) {
+    gi = PlayShare(games_here, W).start(warp) + lane;
+    have = true;
+    load_state<true>(g, p, cta_base + gi, r0);
+    alive = !r0.done;
+    canon = s.from_regs(r0) || !alive;  // a finished game is left as it is, whatever it holds
   }
-  const bool fast = !__syncthreads_or(!canon);
+  if (__syncthreads_or(!canon)) {
+    // some game of this CTA is outside the specialised rules' domain (see madn_fast.cuh / madn_track.cuh): the whole CTA plays
+    // with the generic rules, warp by warp; same keys, same results
+    if (!producer) {
+      MadnRegs tmp = r0;  // the callee takes it by reference: a copy, so that r0 itself can stay in registers
+      play_random_warp(g, p, cta_base + gi, have, tmp, rng0, (uint32_t)(game_offset + cta_base + gi + 1), max_steps, game_len,
+                       total_steps, s_items, s_draw + (size_t)warp * (32 * 24));
+    }
+    return;
+  }
+  if (have && !alive && game_len) game_len[cta_base + gi] = 0;
   const uint32_t lane_hi = (uint32_t)lane << 8;
   if (!producer) s_best[lane] = 0u;
   int t = 0, round = 0;
-  bool tail = false;  // CTA-uniform: one game per WARP from here on (see below)
+#ifdef DOGSTEP_TRACE
+  long long tr_last = 0;
+#endif
+  bool pmode = false;  // CTA-uniform: draw-ahead mode (see below)
   while (true) {
     // ---- compaction point
     // (counts and ring are double-buffered by round parity: an empty warp can reach the next point while others still read)
     const uint32_t ab = __ballot_sync(FULL, alive);
     const int par = round & 1;
     uint32_t* cnt = s_cnt + par * 34;
-    if (lane == 0 && !producer) cnt[warp] = tail ? (ab != 0u) : (uint32_t)__popc(ab);
+    // (bit 16: the live lanes are not the lowest ones — the packed order of the draw-ahead mode needs them to be)
+    if (lane == 0 && !producer) cnt[warp] = (uint32_t)__popc(ab) | ((ab & (ab + 1u)) ? 0x10000u : 0u);
     ++round;
     __syncthreads();
     int before = 0, live = 0, nonempty = 0;
     for (int w = 0; w < W; ++w) {
-      const int c = (int)cnt[w];
+      const int c = (int)(cnt[w] & 0xFFFFu);
       before += (w < warp) ? c : 0;
       live += c;
       nonempty += (c > 0);
     }
+    const PlayShare share(max(live, 1), W);
+    bool uneven = false;  // CTA-uniform: some warp does not hold its even share (in its lowest lanes)
+    for (int w = 0; w < W; ++w) uneven = uneven || (int)cnt[w] != share.count(w);
 #ifdef DOGSTEP_TRACE
-    if (blockIdx.x == 0 && threadIdx.x == 0 && round <= 64) {
+    if ((int)blockIdx.x == g_play_trace_block && threadIdx.x == 0 && round <= 64) {
       unsigned long long now;
       asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
       g_play_trace[2 * (round - 1)] = now;
-      g_play_trace[2 * (round - 1) + 1] = (unsigned long long)live | ((unsigned long long)nonempty << 32);
+      g_play_trace[2 * (round - 1) + 1] = (unsigned long long)live | ((unsigned long long)nonempty << 32) | ((unsigned long long)t << 48);
     }
 #endif
     if (live == 0 || t >= max_steps) break;
-    // Tail: once the CTA is down to one game per warp or fewer, the lockstep iteration is bound by the latency of ONE warp's
-    // instruction stream (~1.2 us), not by issue slots.  From then on every warp holds ONE game, replicated in all lanes:
-    // lane a draws action a's Threefry bits one iteration ahead (they do not depend on the state), the legal mask and
-    // the move are computed redundantly by all lanes, and the argmax is one redux — no scan, no item list, no atomics.
-    const bool enter_tail = fast && !tail && live <= W;
-    if (enter_tail || (!tail && ((live + 31) >> 5) < nonempty)) {  // CTA-uniform: packing frees at least one warp
+    // Draw-ahead mode.  Below ~100 live games the SM is no longer short of issue slots: an iteration lasts as long as ONE
+    // warp's chain mask -> item list -> Threefry passes -> argmax -> move (~3 k cycles).  The draws do not depend on the
+    // state — bits(split(rng_t, N+1)[j+1], a) is a function of (iteration, game, action) — so from here on the live games sit
+    // on four warps (one per scheduler, one game per lane) that only run mask -> masked max -> move, and every other warp
+    // computes, kPChunk iterations ahead, the draws of ALL 24 actions of every live game into a double-buffered table
+    // (named barriers: full[b] helpers -> players, empty[b] players -> helpers).
+    const bool enter_p = !pmode && live <= p_enter && W >= 8;
+    if (enter_p || uneven) {  // CTA-uniform
       if (alive) {
         const int slot = before + __popc(ab & ((1u << lane) - 1u));
         uint32_t* x = s_x + slot;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          x[(2 * q) * T] = (uint32_t)s.occ[q];
-          x[(2 * q + 1) * T] = (uint32_t)(s.occ[q] >> 32);
-          x[(8 + q) * T] = s.pins[q];
-          x[(12 + 2 * q) * T] = (uint32_t)s.as[q];
-          x[(13 + 2 * q) * T] = (uint32_t)(s.as[q] >> 32);
-        }
-        x[20 * T] = (uint32_t)(s.cur & 0xFF) | ((uint32_t)(s.reward & 0xFF) << 8);
-        x[21 * T] = (uint32_t)len;
-        x[22 * T] = (uint32_t)gi;
+        s.pack(x + 3 * T, T);
+        x[0] = (uint32_t)(s.cur() & 0xFF) | ((uint32_t)(s.reward() & 0xFF) << 8);
+        x[T] = (uint32_t)len;
+        x[2 * T] = (uint32_t)gi;
       }
       __syncthreads();
-      tail = tail || enter_tail;
-      alive = (tail ? warp : (int)threadIdx.x) < live && !producer;
+      alive = lane < share.count(warp) && !producer;
       if (alive) {
-        const uint32_t* x = s_x + (tail ? warp : (int)threadIdx.x);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          s.occ[q] = (uint64_t)x[(2 * q) * T] | ((uint64_t)x[(2 * q + 1) * T] << 32);
-          s.pins[q] = x[(8 + q) * T];
-          s.as[q] = (uint64_t)x[(12 + 2 * q) * T] | ((uint64_t)x[(13 + 2 * q) * T] << 32);
-        }
-        const uint32_t misc = x[20 * T];
-        s.cur = (int)(int8_t)(misc & 0xFFu);
-        s.reward = (int)(int8_t)((misc >> 8) & 0xFFu);
-        s.done = 0;
-        s.die = 0;
-        len = (int)x[21 * T];
-        gi = (int)x[22 * T];
+        const uint32_t* x = s_x + share.start(warp) + lane;
+        s.unpack(x + 3 * T, T);
+        const uint32_t misc = x[0];
+        s.cur() = (int)(int8_t)(misc & 0xFFu);
+        s.reward() = (int)(int8_t)((misc >> 8) & 0xFFu);
+        len = (int)x[T];
+        gi = (int)x[2 * T];
       }
       // the next write to s_x happens after the next round's first barrier, i.e. after every read above
+    }
+    pmode = pmode || enter_p;
+    const int q = share.start(warp) + lane;  // slot of this lane's game in the packed order (draw-ahead mode: warps 0..3)
+    if (pmode) {
+      if (alive) s_pmy[q] = (uint32_t)(game_offset + cta_base + gi + 1);
+      __syncthreads();
     }
     // ---- kPlayRound lockstep iterations
     const int tend = min(t + round_len, max_steps);
@@ -736,46 +853,112 @@ __global__ void __launch_bounds__(kPlayMaxThreads + 32) k_madn_det_play_cta(cons
       t = tend;
       continue;
     }
-    const uint32_t my = (uint32_t)(game_offset + cta_base + gi + 1);
-    Key2 key = split_i(Key2{rk[0].x, rk[0].y}, my);  // split(rng, N+1)[j+1]   (game_agent.py:60 / evaluate_agent.py:336)
-    int ri = 0;
-    if (tail) {
-      uint32_t mant = bits_i(key, (uint32_t)lane) >> 9;  // lane a: the draw of action a (lanes >= 24 unused)
-      Key2 key1 = split_i(Key2{rk[1].x, rk[1].y}, my);   // step key of the NEXT iteration
-      const uint32_t tag = lane < 24 ? 23u - (uint32_t)lane : 0u;
-#pragma unroll 1
-      for (; t < tend && alive; ++t) {
-        ++ri;
-        // two independent Threefry chains per iteration, both with inputs known at the top of the loop: the draws of
-        // iteration t + 1 (from its key) and the key of iteration t + 2 — they overlap each other and the state-dependent
-        // chain below (mask -> argmax -> move)
-        const uint2 rn = rk[ri + 1];
-        const uint32_t mant_next = bits_i(key1, (uint32_t)lane) >> 9;
-        const Key2 key2 = split_i(Key2{rn.x, rn.y}, my);
-        int cp = 0;
-        const uint32_t m = det_valid_mask4(R, g, s, cp);
-        if (m) {
-          const uint32_t v = ((m >> lane) & 1u) ? ((mant << 5) | tag) : 0u;  // m has 24 bits: lanes >= 24 contribute 0
-          const int a = 23 - (int)(__reduce_max_sync(FULL, v) & 31u);
-          det_step4(R, s, cp, a);
-        } else {
-          det_no_step4(s);
-        }
-        ++len;
-        steps_done += (lane == 0);
-        if (s.done) {
-          alive = false;
-          if (lane == 0) {
-            store_det_all(g, p, cta_base + gi, s);
-            if (game_len) game_len[cta_base + gi] = len;
+    if (pmode) {
+      const int n_it = tend - t, nc = (n_it + kPChunk - 1) / kPChunk;
+      if (warp >= 4) {  // ---- helpers: the draws of chunk c (iterations c * kPChunk ..) into buffer c & 1
+        const int h = (int)threadIdx.x - 128, H = T - 128;
+        const int pairs = live * kPChunk;  // pair = slot * kPChunk + iteration in the chunk
+        for (int c = 0; c < nc + 2; ++c) {
+          const int b = c & 1;
+          if (c >= 2) named_bar_sync(3 + b, T);  // the players have consumed chunk c - 2
+          if (c >= nc) continue;
+          uint2* pk = s_pkey + b * (kPSlots * kPChunk);
+          for (int j = h; j < pairs; j += H) {  // step keys: split(rng_t, N+1)[game + 1]
+            const int it = c * kPChunk + (j & (kPChunk - 1));
+            const uint2 r = rk[min(it, round_len)];
+            const Key2 k = split_i(Key2{r.x, r.y}, s_pmy[j / kPChunk]);
+            pk[j] = make_uint2(k.a, k.b);
           }
+          named_bar_sync(5, H);
+          uint32_t* dr = s_draw + b * (kPChunk * kPSlots * kPStride);
+          const int items = pairs * 24;
+          for (int j0 = h; j0 < items; j0 += 2 * H) {  // two independent Threefry chains per thread
+            const int j1 = j0 + H;
+            const bool h1 = j1 < items;
+            const int p0 = j0 / 24, a0 = j0 - 24 * p0, p1 = h1 ? j1 / 24 : 0, a1 = h1 ? j1 - 24 * p1 : 0;
+            const uint2 k0 = pk[p0], k1 = pk[p1];
+            const uint32_t v0 = bits_i(Key2{k0.x, k0.y}, (uint32_t)a0) >> 9, v1 = bits_i(Key2{k1.x, k1.y}, (uint32_t)a1) >> 9;
+            dr[((p0 & (kPChunk - 1)) * kPSlots + p0 / kPChunk) * kPStride + a0] = (v0 << 5) | (uint32_t)(23 - a0);
+            if (h1) dr[((p1 & (kPChunk - 1)) * kPSlots + p1 / kPChunk) * kPStride + a1] = (v1 << 5) | (uint32_t)(23 - a1);
+          }
+          named_bar_arrive(1 + b, T);
         }
-        mant = mant_next;
-        key1 = key2;
+      } else {  // ---- players
+        for (int c = 0; c < nc; ++c) {
+          const int b = c & 1;
+          named_bar_sync(1 + b, T);
+          const uint32_t dr = (uint32_t)__cvta_generic_to_shared(s_draw + (b * kPChunk * kPSlots + q) * kPStride);
+          uint4 v[6];  // this iteration's 24 draws; the next row is fetched while the rules run (the loads are pinned: left to
+                       // itself the compiler sinks them behind the legal mask, 6 x 30 cycles on the critical path)
+#pragma unroll
+          for (int k = 0; k < 6; ++k) v[k] = lds128(dr + 16 * k);
+#pragma unroll
+          for (int ii = 0; ii < kPChunk; ++ii) {
+            uint4 nv[6];
+            if (ii + 1 < kPChunk) {
+#pragma unroll
+              for (int k = 0; k < 6; ++k) nv[k] = lds128(dr + (ii + 1) * (kPSlots * kPStride * 4) + 16 * k);
+            }
+            if (c * kPChunk + ii < n_it && alive) {
+#ifdef DOGSTEP_TRACE
+              const long long c0 = clock64();
+#endif
+              int cp = 0;
+              const uint32_t m = s.mask(R, g, cp);
+#ifdef DOGSTEP_TRACE
+              const long long c1 = clock64();
+              long long c2 = c1;
+#endif
+              if (m) {
+                // largest 23-bit mantissa among the legal actions, lowest action index on ties; six independent chains
+                uint32_t pm[6];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                  const uint32_t mk = m >> (4 * k);
+                  pm[k] = max(max((mk & 1u) ? v[k].x : 0u, (mk & 2u) ? v[k].y : 0u), max((mk & 4u) ? v[k].z : 0u, (mk & 8u) ? v[k].w : 0u));
+                }
+                const uint32_t best = max(max(pm[0], pm[1]), max(max(pm[2], pm[3]), max(pm[4], pm[5])));
+#ifdef DOGSTEP_TRACE
+                c2 = clock64() + (best & 0u);
+#endif
+                s.step(R, cp, 23 - (int)(best & 31u));
+              } else {
+                s.no_step();
+              }
+              ++len;
+              ++steps_done;
+#ifdef DOGSTEP_TRACE
+              if ((int)blockIdx.x == g_play_trace_block && live == 1) {
+                const long long c3 = clock64() + (s.cur() & 0);
+                atomicAdd(&g_play_trace[120], (unsigned long long)(c1 - c0));
+                atomicAdd(&g_play_trace[121], (unsigned long long)(c2 - c1));
+                atomicAdd(&g_play_trace[122], (unsigned long long)(c3 - c2));
+                atomicAdd(&g_play_trace[123], 1ull);
+                if (tr_last) atomicAdd(&g_play_trace[124], (unsigned long long)(c0 - tr_last));
+                tr_last = c3;
+              }
+#endif
+              if (s.done()) {
+                alive = false;
+                s.to_regs(g, r0);
+                store_det_all(g, p, cta_base + gi, r0);
+                if (game_len) game_len[cta_base + gi] = len;
+              }
+            }
+            if (ii + 1 < kPChunk) {
+#pragma unroll
+              for (int k = 0; k < 6; ++k) v[k] = nv[k];
+            }
+          }
+          named_bar_arrive(3 + b, T);
+        }
       }
       t = tend;
       continue;
     }
+    const uint32_t my = (uint32_t)(game_offset + cta_base + gi + 1);
+    Key2 key = split_i(Key2{rk[0].x, rk[0].y}, my);  // split(rng, N+1)[j+1]   (game_agent.py:60 / evaluate_agent.py:336)
+    int ri = 0;
 #pragma unroll 1
     for (; t < tend; ++t) {
       if (!__any_sync(FULL, alive)) break;
@@ -783,7 +966,7 @@ __global__ void __launch_bounds__(kPlayMaxThreads + 32) k_madn_det_play_cta(cons
       const uint2 rn = rk[ri];  // split(rng, N+1)[0] of this iteration = the loop key of the next
       int cp = 0;
       uint32_t m = 0u;
-      if (alive) m = fast ? det_valid_mask4(R, g, s, cp) : madn_det_valid_mask(g, s);
+      if (alive) m = s.mask(R, g, cp);
       s_key[lane] = make_uint2(key.a, key.b);
       const int cnt = __popc(m);
       int incl = cnt;
@@ -834,17 +1017,16 @@ __global__ void __launch_bounds__(kPlayMaxThreads + 32) k_madn_det_play_cta(cons
       if (alive) {
         if (m) {
           const int a = 23 - (int)(s_best[lane] & 31u);
-          if (fast) det_step4(R, s, cp, a);
-          else madn_det_step(g, s, a / 6, a % 6 + 1, m);  // map_action (deterministic_madn.py:469-479)
+          s.step(R, cp, a);  // map_action (deterministic_madn.py:469-479) is inside
         } else {
-          if (fast) det_no_step4(s);
-          else madn_det_no_step(g, s);
+          s.no_step();
         }
         ++len;
         ++steps_done;
-        if (s.done) {  // finished: write the game back now, the lane is free from here on
+        if (s.done()) {  // finished: write the game back now, the lane is free from here on
           alive = false;
-          store_det_all(g, p, cta_base + gi, s);
+          s.to_regs(g, r0);
+          store_det_all(g, p, cta_base + gi, r0);
           if (game_len) game_len[cta_base + gi] = len;
         }
       }
@@ -854,8 +1036,9 @@ __global__ void __launch_bounds__(kPlayMaxThreads + 32) k_madn_det_play_cta(cons
     }
     t = tend;
   }
-  if (alive && (!tail || lane == 0)) {  // max_steps reached with the game still running
-    store_det_all(g, p, cta_base + gi, s);
+  if (alive) {  // max_steps reached with the game still running
+    s.to_regs(g, r0);
+    store_det_all(g, p, cta_base + gi, r0);
     if (game_len) game_len[cta_base + gi] = len;
   }
   if (total_steps) {
@@ -867,8 +1050,6 @@ __global__ void __launch_bounds__(kPlayMaxThreads + 32) k_madn_det_play_cta(cons
 }
 
 // MuZero_det_MADN/game_agent.py:12-22 — the rule dict of every training / benchmark configuration gets its own program
-constexpr uint32_t kTrainRules = DOGSTEP_RULE_TEAMS | DOGSTEP_RULE_INITIAL_FREE_PIN | DOGSTEP_RULE_JUMP_IN_GOAL |
-                                 DOGSTEP_RULE_START_ON_1 | DOGSTEP_RULE_BONUS_TURN_ON_6;
 
 __global__ void __launch_bounds__(kThreads) k_madn_cls_throw_die(const __grid_constant__ MadnGeom g, MadnPtrs p, int64_t n,
                                                                  float* __restrict__ probs, int write_die, int only_active) {
@@ -1177,6 +1358,14 @@ int dogstep_madn_det_play_random(const dogstep_madn_det_state* s, int64_t n, con
   DS_PROLOGUE(det_ptrs)
   if (!host_rng_key || max_steps < 0) return DOGSTEP_ERR_INVALID_ARG;
   Key2 rng{host_rng_key[0], host_rng_key[1]};
+#ifdef DOGSTEP_TRACE
+  if (const char* tb = getenv("DOGSTEP_PLAY_TRACE")) {
+    const int b = atoi(tb);
+    unsigned long long z[128] = {0};
+    cudaMemcpyToSymbol(g_play_trace_block, &b, sizeof(b));
+    cudaMemcpyToSymbol(g_play_trace, z, sizeof(z));
+  }
+#endif
   if (g.n == 4 && g.d == 10) {
     // the games are spread evenly over the SMs (config 2: 65,536 games -> 148 CTAs of 443), at most 512 per CTA
     int dev = 0, sms = 0;
@@ -1186,16 +1375,21 @@ int dogstep_madn_det_play_random(const dogstep_madn_det_state* s, int64_t n, con
     int64_t per = (n + sms - 1) / sms;
     if (per > kPlayMaxThreads) per = kPlayMaxThreads;
     const int gpc = (int)per;                          // games per CTA (config 2: 443 on each of the 148 SMs)
-    const int threads = ((gpc + 31) / 32) * 32;
+    // game warps: a multiple of the four schedulers (see PlayShare), at least eight (four players + helpers of the draw-ahead mode)
+    const int threads = gpc > 128 ? ((gpc + 127) / 128) * 128 : 256;
+    int p_enter = kPEnter;
+#ifdef DOGSTEP_TRACE
+    if (const char* e = getenv("DOGSTEP_PENTER")) p_enter = atoi(e);
+#endif
     const size_t smem = play_smem_bytes(threads);
     const unsigned blocks = blocks_for(n, gpc);
     const int round_len = kPlayRound;  // <= kRingMax
     if (g.rules == kTrainRules) {
       cudaFuncSetAttribute(k_madn_det_play_cta<kTrainRules>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      k_madn_det_play_cta<kTrainRules><<<blocks, threads + 32, smem, st>>>(g, p, n, rng, game_offset, max_steps, game_len, total_steps, round_len, gpc);
+      k_madn_det_play_cta<kTrainRules><<<blocks, threads + 32, smem, st>>>(g, p, n, rng, game_offset, max_steps, game_len, total_steps, round_len, gpc, p_enter);
     } else {
       cudaFuncSetAttribute(k_madn_det_play_cta<kRulesRuntime>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      k_madn_det_play_cta<kRulesRuntime><<<blocks, threads + 32, smem, st>>>(g, p, n, rng, game_offset, max_steps, game_len, total_steps, round_len, gpc);
+      k_madn_det_play_cta<kRulesRuntime><<<blocks, threads + 32, smem, st>>>(g, p, n, rng, game_offset, max_steps, game_len, total_steps, round_len, gpc, p_enter);
     }
   } else {
     k_madn_det_play_random<<<blocks_for(n, kThreads), kThreads, 0, st>>>(g, p, n, rng, game_offset, max_steps, game_len,
@@ -1206,9 +1400,12 @@ int dogstep_madn_det_play_random(const dogstep_madn_det_state* s, int64_t n, con
     cudaStreamSynchronize(st);
     unsigned long long h[128];
     cudaMemcpyFromSymbol(h, g_play_trace, sizeof(h));
-    for (int r = 0; r < 64 && h[2 * r]; ++r)
-      fprintf(stderr, "round %2d (%d)  +%8.1f us  live %5llu  warps %3llu\n", r, r, (h[2 * r] - h[0]) / 1e3,
-              h[2 * r + 1] & 0xFFFFFFFFull, h[2 * r + 1] >> 32);
+    if (h[123])
+      fprintf(stderr, "draw-ahead player, one live game: mask %.0f  max %.0f  step %.0f  between iterations %.0f cycles (%llu iterations)\n",
+              (double)h[120] / h[123], (double)h[121] / h[123], (double)h[122] / h[123], (double)h[124] / h[123], h[123]);
+    for (int r = 0; r < 60 && h[2 * r]; ++r)
+      fprintf(stderr, "round %2d  t %4llu  +%8.1f us  live %5llu  warps %3llu\n", r, h[2 * r + 1] >> 48, (h[2 * r] - h[0]) / 1e3,
+              h[2 * r + 1] & 0xFFFFFFFFull, (h[2 * r + 1] >> 32) & 0xFFFFull);
   }
 #endif
   return check_launch();

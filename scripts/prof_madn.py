@@ -17,5 +17,9 @@ for rep in range(reps):
     env = dm.env_reset(0, seed=seeds, **R)
     tot = torch.zeros(1, dtype=torch.int64, device="cuda")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(); dm.play_random(env, key, max_steps=2000, total_steps=tot); e1.record(); torch.cuda.synchronize()
+    e0.record(); env2, glen = dm.play_random(env, key, max_steps=2000, total_steps=tot); e1.record(); torch.cuda.synchronize()
+    if os.environ.get('DOGSTEP_PLAY_TRACE') is not None:  # trace the CTA that holds the longest game next
+        per = -(-n // 148)
+        os.environ['DOGSTEP_PLAY_TRACE'] = str(int(glen.argmax().item()) // per)
+        print("longest game", int(glen.max().item()), "in CTA", os.environ['DOGSTEP_PLAY_TRACE'])
     print("steps", int(tot.item()), "ms", e0.elapsed_time(e1), "Gsteps/s", tot.item() / e0.elapsed_time(e1) / 1e6)

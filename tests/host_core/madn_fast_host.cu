@@ -3,7 +3,7 @@
 // tests/test_madn_fast_core.py can compare them with the oracle without a GPU.
 #include <cstdint>
 #include <cstring>
-#include "../../exploring-muzero-on-dog_b200/csrc/madn_fast.cuh"
+#include "../../exploring-muzero-on-dog_b200/csrc/madn_track.cuh"
 
 using namespace dogstep;
 
@@ -80,6 +80,51 @@ int hostcore_det_step4(int64_t n, uint32_t rules, int8_t* board, int8_t* cur, in
     }
     stepped[i] = 1;
     store(g, i, board, cur, pins, reward, done, aset, s);
+  }
+  return 0;
+}
+
+// the track-coordinate rules of csrc/madn_track.cuh (training rule set only): covered[i] = track_from_regs accepted the state;
+// mask_out[i] = its 24-bit valid mask
+int hostcore_track_valid_mask(int64_t n, const int8_t* board, const int8_t* cur, const int8_t* pins, const int8_t* reward,
+                              const uint8_t* done, const int8_t* aset, uint32_t* mask_out, uint8_t* covered) {
+  dogstep_madn_cfg cfg{4, 0xF, 10, kTrainRules};
+  MadnGeom g;
+  if (madn_make_geom(&cfg, &g)) return -1;
+  for (int64_t i = 0; i < n; ++i) {
+    MadnRegs s; uint64_t ob[4];
+    load(g, i, board, cur, pins, reward, done, aset, s, ob);
+    Track4 t;
+    covered[i] = track_from_regs(s, t);
+    int cp = 0;
+    mask_out[i] = covered[i] ? track_valid_mask(t, cp) : 0u;
+  }
+  return 0;
+}
+
+// in-place: regs -> track -> step (valid action) / no_step -> regs, for covered live games; others untouched (stepped[i] = 0)
+int hostcore_track_step(int64_t n, int8_t* board, int8_t* cur, int8_t* pins, int8_t* reward, uint8_t* done, int8_t* aset,
+                        const int32_t* action, uint8_t* stepped) {
+  dogstep_madn_cfg cfg{4, 0xF, 10, kTrainRules};
+  MadnGeom g;
+  if (madn_make_geom(&cfg, &g)) return -1;
+  for (int64_t i = 0; i < n; ++i) {
+    MadnRegs s; uint64_t ob[4];
+    load(g, i, board, cur, pins, reward, done, aset, s, ob);
+    stepped[i] = 0;
+    Track4 t;
+    if (!track_from_regs(s, t) || s.done) continue;
+    int cp = 0;
+    const uint32_t m = track_valid_mask(t, cp);
+    if (m == 0u) track_no_step(t);
+    else {
+      if (!((m >> action[i]) & 1u)) return -2;
+      track_step(t, cp, action[i]);
+    }
+    MadnRegs r;
+    track_to_regs(g, t, r);
+    stepped[i] = 1;
+    store(g, i, board, cur, pins, reward, done, aset, r);
   }
   return 0;
 }

@@ -19,7 +19,7 @@ CSRC = os.path.join(os.path.dirname(HERE), "exploring-muzero-on-dog_b200", "csrc
 
 @pytest.fixture(scope="module")
 def hc():
-    deps = [SRC, os.path.join(CSRC, "madn_fast.cuh"), os.path.join(CSRC, "madn_core.cuh")]
+    deps = [SRC, os.path.join(CSRC, "madn_fast.cuh"), os.path.join(CSRC, "madn_core.cuh"), os.path.join(CSRC, "madn_track.cuh")]
     if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
         os.makedirs(os.path.dirname(OUT), exist_ok=True)
         subprocess.run(["/usr/local/cuda/bin/nvcc", "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC",
@@ -98,6 +98,74 @@ def test_fast_core_playouts_match_oracle(hc, seed):
             stacked += int(((srt[:, :, 1:] == srt[:, :, :-1]) & (srt[:, :, 1:] >= 0)).any((1, 2))[live].sum())
         assert t > 50
     assert stacked > 0  # the stacked-own-pins quirk (proxied home exit) was exercised
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_track_rules_playouts_match_oracle(hc, seed):
+    """csrc/madn_track.cuh (track coordinates, training rule set — what the config-2 play kernel keeps in registers): mask by
+    mask and leaf by leaf against the oracle over whole games, through the absolute <-> track conversions, incl. the
+    team-proxy phase every game ends with and the stacked-own-pins quirk"""
+    rng = np.random.default_rng(300 + seed)
+    n = 768
+    cfg = O.MadnCfg(4, 0xF, 10, mask_of(TRAIN_RULES))
+    s = O.madn_reset(cfg, rng.integers(0, 1_000_000, n).astype(np.int32), int(rng.integers(0, 4)))
+    proxied = captured = finished = 0
+    for t in range(1200):
+        live = s.done == 0
+        if not live.any():
+            break
+        want = O.madn_det_valid_action(s).reshape(n, 24)
+        m = np.zeros(n, np.uint32)
+        cov = np.zeros(n, np.uint8)
+        assert hc.hostcore_track_valid_mask(C.c_int64(n), _p(s.board), _p(s.current_player), _p(s.pins), _p(s.reward), _p(s.done),
+                                            _p(s.action_set), _p(m), _p(cov)) == 0
+        cov = cov.astype(bool)
+        assert cov[live].all(), t                       # every live state the reference produces is covered
+        assert not cov[~live].any(), t                  # a finished game (a complete team) is not
+        assert np.array_equal(_bits(m)[live], want[live]), t
+        score = np.where(want, rng.random((n, 24)), -1.0)
+        a = score.argmax(1).astype(np.int32)
+        has = want.any(1)
+        f = s.copy()
+        stepped = np.zeros(n, np.uint8)
+        assert hc.hostcore_track_step(C.c_int64(n), _p(f.board), _p(f.current_player), _p(f.pins), _p(f.reward), _p(f.done),
+                                      _p(f.action_set), _p(a), _p(stepped)) == 0
+        assert np.array_equal(stepped.astype(bool), live)
+        o_step, o_skip = s.copy(), s.copy()
+        O.madn_det_step(o_step, np.stack([a // 6, a % 6 + 1], 1).astype(np.int8))
+        O.madn_det_no_step(o_skip)
+        cur = s.current_player.astype(np.int64)
+        own_goal = (np.take_along_axis(s.pins.astype(np.int64), cur[:, None, None].repeat(4, 2), 1)[:, 0] >= 40).all(1)
+        proxied += int((own_goal & live & has).sum())
+        before_home = (s.pins < 0).sum((1, 2))
+        for k in s.fields():
+            v = getattr(s, k)
+            sel = has.reshape((-1,) + (1,) * (v.ndim - 1))
+            lv = live.reshape((-1,) + (1,) * (v.ndim - 1))
+            v[...] = np.where(lv, np.where(sel, getattr(o_step, k), getattr(o_skip, k)), v)
+        captured += int(((s.pins < 0).sum((1, 2)) > before_home).sum())
+        finished += int(((s.done != 0) & live).sum())
+        for k in s.fields():
+            assert np.array_equal(getattr(s, k), getattr(f, k)), (t, k)
+    assert finished == n and proxied > 1000 and captured > 1000
+
+
+def test_track_rules_gate(hc):
+    """states outside the track rules' domain are refused (the kernel then runs the generic rules)"""
+    cfg = O.MadnCfg(4, 0xF, 10, mask_of(TRAIN_RULES))
+    s = O.madn_reset(cfg, np.arange(5, dtype=np.int32), 0)
+    s.action_set[1, 2, 3] = 9                       # a count that does not fit the packed row
+    s.action_set[2, 0, 0] = -1
+    s.pins[3, 0] = [40, 41, 42, 43]                 # team 0 / 2 already complete, done flag not set
+    s.pins[3, 2] = [48, 49, 50, 51]
+    s.pins[4, 1, 1] = 41                            # not canonical
+    for g in (3, 4):
+        s.board[g] = O.madn_set_pins_on_board(cfg, s.pins[g:g + 1])[0]
+    m = np.zeros(5, np.uint32)
+    cov = np.zeros(5, np.uint8)
+    assert hc.hostcore_track_valid_mask(C.c_int64(5), _p(s.board), _p(s.current_player), _p(s.pins), _p(s.reward), _p(s.done),
+                                        _p(s.action_set), _p(m), _p(cov)) == 0
+    assert cov.tolist() == [1, 0, 0, 0, 0]
 
 
 def test_non_canonical_states_are_detected(hc):
