@@ -650,7 +650,7 @@ struct PlayState {
   static constexpr int kWords = 20;
   MadnRegs s;
   __device__ bool from_regs(const MadnRegs& r) { s = r; return is_canonical4(r, r.occ); }
-  __device__ void to_regs(const MadnGeom&, MadnRegs& r) const { r = s; }
+  __device__ void store(const MadnGeom& g, const MadnPtrs& p, int64_t i) const { store_det_all(g, p, i, s); }
   __device__ bool done() const { return s.done != 0; }
   __device__ uint32_t mask(const RuleSet<CT> R, const MadnGeom& g, int& cp) const { return det_valid_mask4(R, g, s, cp); }
   __device__ void step(const RuleSet<CT> R, int cp, int a) { det_step4(R, s, cp, a); }
@@ -684,7 +684,36 @@ struct PlayState<kTrainRules> {
   static constexpr int kWords = 8;
   Track4 s;
   __device__ bool from_regs(const MadnRegs& r) { return track_from_regs(r, s); }
-  __device__ void to_regs(const MadnGeom& g, MadnRegs& r) const { track_to_regs(g, s, r); }
+  // every leaf straight from the track state: board = set_pins_on_board(pins) (deterministic_madn.py:259-271) is -1 everywhere,
+  // then one byte per pin (a thread's stores to one address keep their order; canonical: no cell is shared by two players)
+  __device__ void store(const MadnGeom&, const MadnPtrs& p, int64_t i) const {
+    int8_t* board = p.board + i * 56;
+    uint2* bw = reinterpret_cast<uint2*>(board);
+#pragma unroll
+    for (int w = 0; w < 7; ++w) bw[w] = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+    uint32_t pw[4];
+    uint64_t as[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint32_t w = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int pos = track_to_cell(q, byte_s(s.pins[q], k));
+        if (pos >= 0) board[pos] = (int8_t)q;
+        w |= (uint32_t)(pos & 0xFF) << (8 * k);
+      }
+      pw[q] = w;
+      as[q] = track_as_bytes(s.as[q]);
+    }
+    reinterpret_cast<uint4*>(p.pins)[i] = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+    uint64_t* aw = reinterpret_cast<uint64_t*>(p.aset) + i * 3;
+    aw[0] = as[0] | (as[1] << 48);
+    aw[1] = (as[1] >> 16) | (as[2] << 32);
+    aw[2] = (as[2] >> 32) | (as[3] << 16);
+    p.cur[i] = (int8_t)s.cur;
+    p.reward[i] = (int8_t)s.reward;
+    p.done[i] = (uint8_t)s.done;
+  }
   __device__ bool done() const { return s.done != 0; }
   __device__ uint32_t mask(const RuleSet<kTrainRules>, const MadnGeom&, int& cp) const { return track_valid_mask(s, cp); }
   __device__ void step(const RuleSet<kTrainRules>, int cp, int a) { track_step(s, cp, a); }
@@ -738,6 +767,8 @@ __global__ void __launch_bounds__(kPlayMaxThreads + 32) k_madn_det_play_cta(cons
   PlayState<CT> s;
   MadnRegs r0;  // as loaded (only live until the rule program is chosen)
   bool alive = false, canon = true, have = false;
+  bool pending = false;  // finished, not written back yet: the finished games of a warp are stored together at the next
+                         // compaction point (one lane at a time the store path was 3 % of all issued instructions)
   if (producer) {
     // The loop key chain rng_{t+1} = split(rng_t, N + 1)[0] (game_agent.py:60) is the same for every game: one warp per CTA
     // computes it, a round ahead, into a double-buffered ring (ring[i] = rng_{t0 + i}, i = 0..round_len + 1) instead of
@@ -776,6 +807,11 @@ __global__ void __launch_bounds__(kPlayMaxThreads + 32) k_madn_det_play_cta(cons
   bool pmode = false;  // CTA-uniform: draw-ahead mode (see below)
   while (true) {
     // ---- compaction point
+    if (pending) {
+      s.store(g, p, cta_base + gi);
+      if (game_len) game_len[cta_base + gi] = len;
+      pending = false;
+    }
     // (counts and ring are double-buffered by round parity: an empty warp can reach the next point while others still read)
     const uint32_t ab = __ballot_sync(FULL, alive);
     const int par = round & 1;
@@ -940,9 +976,7 @@ __global__ void __launch_bounds__(kPlayMaxThreads + 32) k_madn_det_play_cta(cons
 #endif
               if (s.done()) {
                 alive = false;
-                s.to_regs(g, r0);
-                store_det_all(g, p, cta_base + gi, r0);
-                if (game_len) game_len[cta_base + gi] = len;
+                pending = true;
               }
             }
             if (ii + 1 < kPChunk) {
@@ -1023,11 +1057,9 @@ __global__ void __launch_bounds__(kPlayMaxThreads + 32) k_madn_det_play_cta(cons
         }
         ++len;
         ++steps_done;
-        if (s.done()) {  // finished: write the game back now, the lane is free from here on
+        if (s.done()) {  // finished: the lane is free from the next compaction point on
           alive = false;
-          s.to_regs(g, r0);
-          store_det_all(g, p, cta_base + gi, r0);
-          if (game_len) game_len[cta_base + gi] = len;
+          pending = true;
         }
       }
       s_best[lane] = 0u;
@@ -1036,9 +1068,8 @@ __global__ void __launch_bounds__(kPlayMaxThreads + 32) k_madn_det_play_cta(cons
     }
     t = tend;
   }
-  if (alive) {  // max_steps reached with the game still running
-    s.to_regs(g, r0);
-    store_det_all(g, p, cta_base + gi, r0);
+  if (alive || pending) {  // max_steps reached with the game still running
+    s.store(g, p, cta_base + gi);
     if (game_len) game_len[cta_base + gi] = len;
   }
   if (total_steps) {

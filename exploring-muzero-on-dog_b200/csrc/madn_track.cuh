@@ -37,6 +37,23 @@ DS_FN uint32_t track_avail6(uint32_t v) {
   return (t | (t >> 6) | (t >> 12)) & 0x3Fu;
 }
 
+// track position of player p -> board cell (-1 = home)
+DS_FN int track_to_cell(int p, int u) {
+  int pos = u + start4(p);
+  pos = pos >= 40 ? pos - 40 : pos;
+  pos = u >= 40 ? u - 40 + goal4(p) : pos;
+  return u < 0 ? -1 : pos;
+}
+
+// nibble k -> byte k (one action-set row as the reference stores it)
+DS_FN uint64_t track_as_bytes(uint32_t v) {
+  uint32_t lo = v & 0xFFFFu, hi = (v >> 16) & 0xFFu;
+  lo = (lo | (lo << 8)) & 0x00FF00FFu;
+  lo = (lo | (lo << 4)) & 0x0F0F0F0Fu;
+  hi = (hi | (hi << 4)) & 0x0F0Fu;
+  return (uint64_t)lo | ((uint64_t)hi << 32);
+}
+
 // MadnRegs (absolute cells) -> track state; false if the state is outside what this file covers (the caller then keeps the
 // generic rules): not canonical, a count outside 0..7, or a team already complete (the reference would report that winner)
 DS_FN bool track_from_regs(const MadnRegs& r, Track4& s) {
@@ -74,20 +91,10 @@ DS_FN void track_to_regs(const MadnGeom& g, const Track4& s, MadnRegs& r) {
 #pragma unroll
   for (int p = 0; p < 4; ++p) {
     uint32_t w = 0;
-    uint64_t a = 0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int u = byte_s(s.pins[p], i);
-      int pos = u + start4(p);
-      pos = pos >= 40 ? pos - 40 : pos;
-      pos = u >= 40 ? u - 40 + goal4(p) : pos;
-      pos = u < 0 ? -1 : pos;
-      w |= (uint32_t)(pos & 0xFF) << (8 * i);
-    }
-#pragma unroll
-    for (int m = 0; m < 6; ++m) a |= (uint64_t)((s.as[p] >> (4 * m)) & 0xFu) << (8 * m);
+    for (int i = 0; i < 4; ++i) w |= (uint32_t)(track_to_cell(p, byte_s(s.pins[p], i)) & 0xFF) << (8 * i);
     r.pins[p] = w;
-    r.as[p] = a;
+    r.as[p] = track_as_bytes(s.as[p]);
   }
   r.cur = s.cur;
   r.reward = s.reward;
