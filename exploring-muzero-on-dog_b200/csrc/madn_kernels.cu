@@ -602,7 +602,7 @@ __global__ void __launch_bounds__(kThreads) k_madn_det_play_random(const __grid_
 __device__ unsigned long long g_play_trace[128];
 __device__ int g_play_trace_block;
 #endif
-constexpr int kPlayRound = 64;  // 24 / 32 / 48 / 64: 2.21 / 2.19 / 2.18 / 2.175 ms on config 2 (with key ring and tail mode)
+constexpr int kPlayRound = 48;  // 16 / 24 / 32 / 40 / 48 / 64: 1.81 / 1.78 / 1.77 / 1.76 / 1.75 / 1.76 ms on config 2 (finished games wait for the next compaction point)
 constexpr int kPlayMaxThreads = 512;  // game threads per CTA (+ 32: the producer warp)
 constexpr int kXWords = 23;  // cur|reward, len, game index + PlayState::kWords (at most 20: occ 8, pins 4, action set 8)
 
@@ -1414,7 +1414,10 @@ int dogstep_madn_det_play_random(const dogstep_madn_det_state* s, int64_t n, con
 #endif
     const size_t smem = play_smem_bytes(threads);
     const unsigned blocks = blocks_for(n, gpc);
-    const int round_len = kPlayRound;  // <= kRingMax
+    int round_len = kPlayRound;  // <= kRingMax
+#ifdef DOGSTEP_TRACE
+    if (const char* e = getenv("DOGSTEP_ROUND")) round_len = atoi(e);
+#endif
     if (g.rules == kTrainRules) {
       cudaFuncSetAttribute(k_madn_det_play_cta<kTrainRules>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       k_madn_det_play_cta<kTrainRules><<<blocks, threads + 32, smem, st>>>(g, p, n, rng, game_offset, max_steps, game_len, total_steps, round_len, gpc, p_enter);
