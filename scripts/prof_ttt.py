@@ -10,15 +10,22 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 from torch.profiler import ProfilerActivity, profile  # noqa: E402
 
-from exploring_muzero_on_dog_b200 import jaxrand  # noqa: E402
+from exploring_muzero_on_dog_b200 import jaxrand, _lib  # noqa: E402
+if os.environ.get("DOGSTEP_LIB"):
+    _lib.LIB_PATH = os.environ["DOGSTEP_LIB"]  # instrumented build (scripts/build_trace_lib.sh)
 from exploring_muzero_on_dog_b200.TicTacToe import mcts as tm  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 512
-tm.play_mcts_games(n, jaxrand.PRNGKey(0), num_simulations=50, limit=30, variant=1)
+kw = {"fused": {}} if len(sys.argv) > 2 and sys.argv[2] == "fused" else {}   # fused: one launch per move (k_ttt_search)
+tm.play_mcts_games(n, jaxrand.PRNGKey(0), num_simulations=50, limit=30, variant=1, **kw)
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
-    _, plies = tm.play_mcts_games(n, jaxrand.PRNGKey(1), num_simulations=50, limit=30, variant=1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _, plies = tm.play_mcts_games(n, jaxrand.PRNGKey(1), num_simulations=50, limit=30, variant=1, **kw)
+    e1.record()
     torch.cuda.synchronize()
+print(f"wall (events) {e0.elapsed_time(e1):.1f} ms")
 tot, cnt = collections.Counter(), collections.Counter()
 for e in prof.events():
     if e.device_type == torch.autograd.DeviceType.CUDA:
