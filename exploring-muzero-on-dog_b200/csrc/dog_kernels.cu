@@ -4,6 +4,8 @@
 #include <atomic>
 #include <cstdint>
 #include <mutex>
+#include <cstdio>
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include "../../include/dogstep.h"
 #include "common.cuh"
@@ -441,6 +443,9 @@ __device__ __forceinline__ int64_t dog_next_game(unsigned int* queue, int64_t fi
   return first + (int64_t)k;
 }
 
+#ifdef DOGSTEP_TRACE
+__device__ unsigned long long g_dog_trace[1024];  // CTA 0, every 64th turn: time, live warps
+#endif
 __global__ void __launch_bounds__(kSyncWarps * 32, 1) k_dog_play_random(const __grid_constant__ DogGeom g, DogPtrs p, int64_t n,
                                                                       Key2 rng0, int64_t game_offset, int max_steps,
                                                                       int32_t* __restrict__ game_len,
@@ -505,6 +510,17 @@ __global__ void __launch_bounds__(kSyncWarps * 32, 1) k_dog_play_random(const __
         }
       }
     }
+#ifdef DOGSTEP_TRACE
+    {
+      const int live = __syncthreads_count(have);
+      if (blockIdx.x == 0 && threadIdx.x == 0 && (turn & 63) == 0 && (turn >> 6) < 511) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+        g_dog_trace[2 * (turn >> 6)] = now;
+        g_dog_trace[2 * (turn >> 6) + 1] = (unsigned long long)(live / 32);
+      }
+    }
+#endif
     if (!__syncthreads_or(have)) break;
     if (threadIdx.x == 0) { int* qn = s_q + ((turn + 1) & 1) * 130; qn[0] = 0; qn[1] = 0; }  // next turn's queue (see parity note)
     if (have && !dealing) {
@@ -686,8 +702,24 @@ int dogstep_dog_play_random(const dogstep_dog_state* s, int64_t n, const dogstep
   }
   unsigned int* queue = pools[dev] + (ticket.fetch_add(1) & 63u);
   cudaMemsetAsync(queue, 0, sizeof(unsigned int), st);
+#ifdef DOGSTEP_TRACE
+  if (getenv("DOGSTEP_DOG_TRACE")) {
+    static unsigned long long z[1024];
+    cudaMemcpyToSymbol(g_dog_trace, z, sizeof(z));
+  }
+#endif
   k_dog_play_random<<<grid, kSyncWarps * 32, smem, st>>>(g, p, n, Key2{host_rng_key[0], host_rng_key[1]}, game_offset, max_steps,
                                                         game_len, total_steps, queue);
+#ifdef DOGSTEP_TRACE
+  if (getenv("DOGSTEP_DOG_TRACE")) {
+    cudaStreamSynchronize(st);
+    static unsigned long long h[1024];
+    cudaMemcpyFromSymbol(h, g_dog_trace, sizeof(h));
+    for (int r = 0; r < 511 && h[2 * r]; ++r)
+      fprintf(stderr, "turn %5d  +%9.1f us  live warps %2llu%s", 64 * r, (h[2 * r] - h[0]) / 1e3, h[2 * r + 1], (r % 4 == 3) ? "\n" : "   ");
+    fprintf(stderr, "\n");
+  }
+#endif
   return check_launch();
 }
 

@@ -2,7 +2,9 @@
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from exploring_muzero_on_dog_b200 import jaxrand
+from exploring_muzero_on_dog_b200 import jaxrand, _lib
+if os.environ.get('DOGSTEP_LIB'):
+    _lib.LIB_PATH = os.environ['DOGSTEP_LIB']  # instrumented build (scripts/build_trace_lib.sh)
 from exploring_muzero_on_dog_b200.DOG import dog
 R = dict(enable_teams=True, enable_initial_free_pin=False, enable_circular_board=True, enable_friendly_fire=True,
          enable_start_blocking=True, enable_jump_in_goal_area=False, must_traverse_start=True)
