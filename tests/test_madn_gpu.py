@@ -284,6 +284,57 @@ def test_det_play_random_non_canonical_games_take_the_generic_rules():
     assert np.array_equal(olen, glen.cpu().numpy())
 
 
+def test_det_play_random_states_outside_the_track_rules_take_the_generic_rules():
+    """the training-rule program keeps a game as track positions + nibble counts (csrc/madn_track.cuh); a CTA that loads a state
+    that representation cannot hold — a card count above 7, a negative count, a complete team whose done flag is not set — must
+    give the oracle's answer for every game it owns, and CTAs next to it are unaffected"""
+    dm = _dm()
+    from exploring_muzero_on_dog_b200 import jaxrand
+    n = 1500                                         # 11 games per CTA: games 5, 700, 1200 sit in different CTAs
+    key = jaxrand.split_host(jaxrand.PRNGKey(13))[1]
+    cfg = O.MadnCfg(4, 0xF, 10, mask_of(TRAIN_RULES))
+    s = O.madn_reset(cfg, np.arange(n, dtype=np.int32) + 50, 0)
+    O.madn_det_play_random(s, key, 40)
+    s.action_set[5, 2, 3] = 9
+    s.action_set[700, 0, 0] = -3
+    s.pins[1200, 0] = [40, 41, 42, 43]
+    s.pins[1200, 2] = [48, 49, 50, 51]
+    s.board[1200] = O.madn_set_pins_on_board(cfg, s.pins[1200:1201])[0]
+    s.done[1200] = 0
+    env = _upload_det(dm, s, TRAIN_RULES)
+    _, glen = dm.play_random(env, key, max_steps=2000)
+    olen, _, _ = O.madn_det_play_random(s, key, 2000)
+    assert_state_equal(s, env.numpy())
+    assert np.array_equal(olen, glen.cpu().numpy())
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_det_play_random_other_rule_sets_and_draw_ahead_sizes(seed):
+    """the persistent kernel under random rule dicts (the run-time-rules program: bitboard state) and at batch sizes whose CTAs
+    start below the draw-ahead threshold (<= 64 live games per CTA from the first iteration on), in chunks of 1 / 7 / 48 / 49
+    iterations per launch (round boundaries, a launch shorter than a draw chunk)"""
+    dm = _dm()
+    from exploring_muzero_on_dog_b200 import jaxrand
+    rng = np.random.default_rng(40 + seed)
+    for rules in all_rule_sets(rng, 2):
+        n = int(rng.integers(200, 9000))             # 2 .. 61 games per CTA
+        key = jaxrand.split_host(jaxrand.PRNGKey(seed))[1]
+        cfg = O.MadnCfg(4, 0xF, 10, mask_of(rules))
+        seeds = rng.integers(0, 1_000_000, n).astype(np.int32)
+        env = dm.env_reset(0, seed=seeds, **rules)
+        s = O.madn_reset(cfg, seeds, 0)
+        k = key
+        for chunk in (1, 7, 48, 49, 3, 2000):
+            k_next = dm.random_steps(env, k, chunk) if chunk < 2000 else None
+            if chunk == 2000:
+                dm.play_random(env, k, max_steps=chunk)
+            _, _, okey = O.madn_det_play_random(s, k, chunk)
+            assert_state_equal(s, env.numpy())
+            if k_next is not None:
+                assert np.asarray(k_next).tolist() == okey.tolist()
+                k = np.asarray(k_next, dtype=np.uint32)
+
+
 def test_entry_points_follow_the_device_of_their_tensors():
     """an env created with device='cuda:1' while cuda:0 is current must run on GPU 1, on GPU 1's current stream
     (needs two GPUs; the one-GPU test box skips it, `gpurun --gpus 2` runs it)"""
