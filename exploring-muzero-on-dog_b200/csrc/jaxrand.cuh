@@ -38,25 +38,64 @@ __host__ __device__ __forceinline__ uint32_t tf_add(uint32_t x0, uint32_t x1) {
 #endif
 }
 
+// a + k + c of a key injection (c = 1..5).  With both adds forced onto the fma pipe (DOGSTEP_TF_INJECT_IMAD) the config-2 play
+// kernel was 3 % SLOWER (1.80 against 1.75 ms): k + c is an integer add the compiler folds with its neighbours.
+__host__ __device__ __forceinline__ uint32_t tf_inject(uint32_t a, uint32_t k, uint32_t c) {
+#if defined(__CUDA_ARCH__) && defined(DOGSTEP_TF_INJECT_IMAD)
+  uint32_t t, r;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(t) : "r"(k), "r"(c_dogstep_one), "r"(c));
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(t), "r"(c_dogstep_one), "r"(a));
+  return r;
+#else
+  return tf_add(a, k + c);
+#endif
+}
+
+// x1 = rotl(x1, r) ^ x0 of a Threefry round.  DOGSTEP_TF_MULROT (an experiment switch, default 0) selects the rounds (bit j of the
+// mask = round j of a group of four) that rotate by a 32 x 32 -> 64 multiply with 2^r on the fma pipe followed by ONE three-input
+// xor (lo ^ hi ^ x0), instead of funnel shift + xor (two alu-pipe instructions); the multiplier is read from the constant bank so
+// that ptxas does not turn it back into a shift.  Measured in the config-2 play kernel (ALU pipe ~90 % busy, fma pipe half
+// idle): one round in four 1.75 -> 1.89 ms, two in four 2.01 ms, all 2.24 ms — the wide multiply costs more than it frees.
+#ifndef DOGSTEP_TF_MULROT
+#define DOGSTEP_TF_MULROT 0
+#endif
+#ifdef __CUDACC__
+static __constant__ uint32_t c_dogstep_pow2[8] = {1u << 13, 1u << 15, 1u << 26, 1u << 6, 1u << 17, 1u << 29, 1u << 16, 1u << 24};
+#endif
+template <int J, int R>
+__host__ __device__ __forceinline__ uint32_t tf_rotx(uint32_t x1, uint32_t x0) {
+#ifdef __CUDA_ARCH__
+  if ((DOGSTEP_TF_MULROT >> (J & 3)) & 1) {
+    uint32_t lo, hi;
+    asm("{ .reg .u64 t; mul.wide.u32 t, %2, %3; mov.b64 {%0, %1}, t; }" : "=r"(lo), "=r"(hi) : "r"(x1), "r"(c_dogstep_pow2[J]));
+    return lo ^ hi ^ x0;
+  }
+#endif
+  return rotl32(x1, R) ^ x0;
+}
+
 // Threefry-2x32, 20 rounds.  Fully unrolled: 20 x (IMAD, SHF, LOP) + 5 key injections.
 __host__ __device__ __forceinline__ Key2 threefry2x32(Key2 k, uint32_t c0, uint32_t c1) {
   const uint32_t ks0 = k.a, ks1 = k.b, ks2 = k.a ^ k.b ^ 0x1BD11BDAu;
   uint32_t x0 = c0 + ks0, x1 = c1 + ks1;
-#define DOGSTEP_TF_ROUND(r) \
-  x0 = tf_add(x0, x1);      \
-  x1 = rotl32(x1, r);       \
-  x1 ^= x0;
-  DOGSTEP_TF_ROUND(13) DOGSTEP_TF_ROUND(15) DOGSTEP_TF_ROUND(26) DOGSTEP_TF_ROUND(6)
-  x0 = tf_add(x0, ks1); x1 = tf_add(x1, ks2 + 1u);
-  DOGSTEP_TF_ROUND(17) DOGSTEP_TF_ROUND(29) DOGSTEP_TF_ROUND(16) DOGSTEP_TF_ROUND(24)
-  x0 = tf_add(x0, ks2); x1 = tf_add(x1, ks0 + 2u);
-  DOGSTEP_TF_ROUND(13) DOGSTEP_TF_ROUND(15) DOGSTEP_TF_ROUND(26) DOGSTEP_TF_ROUND(6)
-  x0 = tf_add(x0, ks0); x1 = tf_add(x1, ks1 + 3u);
-  DOGSTEP_TF_ROUND(17) DOGSTEP_TF_ROUND(29) DOGSTEP_TF_ROUND(16) DOGSTEP_TF_ROUND(24)
-  x0 = tf_add(x0, ks1); x1 = tf_add(x1, ks2 + 4u);
-  DOGSTEP_TF_ROUND(13) DOGSTEP_TF_ROUND(15) DOGSTEP_TF_ROUND(26) DOGSTEP_TF_ROUND(6)
-  x0 = tf_add(x0, ks2); x1 = tf_add(x1, ks0 + 5u);
+#define DOGSTEP_TF_ROUND(j, r) \
+  x0 = tf_add(x0, x1);         \
+  x1 = tf_rotx<j, r>(x1, x0);
+#define DOGSTEP_TF_GROUP_A DOGSTEP_TF_ROUND(0, 13) DOGSTEP_TF_ROUND(1, 15) DOGSTEP_TF_ROUND(2, 26) DOGSTEP_TF_ROUND(3, 6)
+#define DOGSTEP_TF_GROUP_B DOGSTEP_TF_ROUND(4, 17) DOGSTEP_TF_ROUND(5, 29) DOGSTEP_TF_ROUND(6, 16) DOGSTEP_TF_ROUND(7, 24)
+  DOGSTEP_TF_GROUP_A
+  x0 = tf_add(x0, ks1); x1 = tf_inject(x1, ks2, 1u);
+  DOGSTEP_TF_GROUP_B
+  x0 = tf_add(x0, ks2); x1 = tf_inject(x1, ks0, 2u);
+  DOGSTEP_TF_GROUP_A
+  x0 = tf_add(x0, ks0); x1 = tf_inject(x1, ks1, 3u);
+  DOGSTEP_TF_GROUP_B
+  x0 = tf_add(x0, ks1); x1 = tf_inject(x1, ks2, 4u);
+  DOGSTEP_TF_GROUP_A
+  x0 = tf_add(x0, ks2); x1 = tf_inject(x1, ks0, 5u);
 #undef DOGSTEP_TF_ROUND
+#undef DOGSTEP_TF_GROUP_A
+#undef DOGSTEP_TF_GROUP_B
   return Key2{x0, x1};
 }
 
