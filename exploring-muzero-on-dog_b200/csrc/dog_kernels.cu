@@ -445,6 +445,7 @@ __device__ __forceinline__ int64_t dog_next_game(unsigned int* queue, int64_t fi
 
 #ifdef DOGSTEP_TRACE
 __device__ unsigned long long g_dog_trace[1024];  // CTA 0, every 64th turn: time, live warps
+__device__ unsigned long long g_dog_solo[8];      // CTA 0 with ONE live game: cycles in flags / tasks / draw / transition / turn, turns
 #endif
 __global__ void __launch_bounds__(kSyncWarps * 32, 1) k_dog_play_random(const __grid_constant__ DogGeom g, DogPtrs p, int64_t n,
                                                                       Key2 rng0, int64_t game_offset, int max_steps,
@@ -489,6 +490,9 @@ __global__ void __launch_bounds__(kSyncWarps * 32, 1) k_dog_play_random(const __
     int* q = s_q + (turn & 1) * 130;
     int flags = 0;
     bool shared_mask = false;
+#ifdef DOGSTEP_TRACE
+    const long long tc0 = clock64();
+#endif
     if (have && dealing) {
       // The previous transition ended a round.  A deal is 120 Threefry draws plus a 24-step selection — 11 k cycles against
       // 5 k for a plain transition, and with 26 live games one of them deals in four turns out of five — so it is not done
@@ -511,8 +515,10 @@ __global__ void __launch_bounds__(kSyncWarps * 32, 1) k_dog_play_random(const __
       }
     }
 #ifdef DOGSTEP_TRACE
+    int live_tr = 0;
     {
       const int live = __syncthreads_count(have);
+      live_tr = live / 32;
       if (blockIdx.x == 0 && threadIdx.x == 0 && (turn & 63) == 0 && (turn >> 6) < 511) {
         unsigned long long now;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
@@ -523,6 +529,9 @@ __global__ void __launch_bounds__(kSyncWarps * 32, 1) k_dog_play_random(const __
 #endif
     if (!__syncthreads_or(have)) break;
     if (threadIdx.x == 0) { int* qn = s_q + ((turn + 1) & 1) * 130; qn[0] = 0; qn[1] = 0; }  // next turn's queue (see parity note)
+#ifdef DOGSTEP_TRACE
+    const long long tc1 = clock64();
+#endif
     if (have && !dealing) {
       if (shared_mask) {
         dog4_mask_task(R4, s, 4, lane);
@@ -543,11 +552,18 @@ __global__ void __launch_bounds__(kSyncWarps * 32, 1) k_dog_play_random(const __
     }
     ++turn;
     __syncthreads();
+#ifdef DOGSTEP_TRACE
+    const long long tc2 = clock64();
+    long long tc3 = tc2;
+#endif
     if (have && dealing) {                                          // the draws are in the record: select, deal, next round
       dog_deal_finish(g, s, lane);
       dealing = false;
     } else if (have) {
       const int a = dog_categorical_pipelined(g, s, lane, key, rng, (uint32_t)(game_offset + i + 1));  // phase B
+#ifdef DOGSTEP_TRACE
+      tc3 = clock64();
+#endif
       if (lane == 0) s.scratch[6] = 1;                              // phase C: transition, a deal that falls due is held back
       __syncwarp();
       if (a >= 0) {
@@ -576,6 +592,16 @@ __global__ void __launch_bounds__(kSyncWarps * 32, 1) k_dog_play_random(const __
         dealing = need_deal;
       }
     }
+#ifdef DOGSTEP_TRACE
+    if (blockIdx.x == 0 && live_tr == 1 && have && lane == 0) {
+      const long long tc4 = clock64();
+      atomicAdd(&g_dog_solo[0], (unsigned long long)(tc1 - tc0));
+      atomicAdd(&g_dog_solo[1], (unsigned long long)(tc2 - tc1));
+      atomicAdd(&g_dog_solo[2], (unsigned long long)(tc3 - tc2));
+      atomicAdd(&g_dog_solo[3], (unsigned long long)(tc4 - tc3));
+      atomicAdd(&g_dog_solo[4], 1ull);
+    }
+#endif
   }
   if (lane == 0 && total_steps && steps) atomicAdd(total_steps, steps);
 }
@@ -718,6 +744,12 @@ int dogstep_dog_play_random(const dogstep_dog_state* s, int64_t n, const dogstep
     for (int r = 0; r < 511 && h[2 * r]; ++r)
       fprintf(stderr, "turn %5d  +%9.1f us  live warps %2llu%s", 64 * r, (h[2 * r] - h[0]) / 1e3, h[2 * r + 1], (r % 4 == 3) ? "\n" : "   ");
     fprintf(stderr, "\n");
+    unsigned long long q[8], zz[8] = {0};
+    cudaMemcpyFromSymbol(q, g_dog_solo, sizeof(q));
+    cudaMemcpyToSymbol(g_dog_solo, zz, sizeof(zz));
+    if (q[4])
+      fprintf(stderr, "one live game (%llu turns): flags + barrier %.0f  mask tasks + barrier %.0f  draw %.0f  transition (or deal) %.0f cycles\n", q[4],
+              (double)q[0] / q[4], (double)q[1] / q[4], (double)q[2] / q[4], (double)q[3] / q[4]);
   }
 #endif
   return check_launch();

@@ -584,20 +584,24 @@ __global__ void __launch_bounds__(kThreads) k_madn_det_play_random(const __grid_
 }
 
 // Persistent lockstep loop for 4 players, distance 10 — every configuration of the reference (the generic kernel above
-// covers other geometries).  One CTA per SM (up to 512 games), one game per lane held in registers.  Per iteration:
-//   1. each lane takes its step key and derives the 24-bit legal mask (madn_fast.cuh: branch-free bit rows);
+// covers other geometries).  One CTA per SM (up to 512 games), one game per lane held in registers (PlayState: the track
+// state of madn_track.cuh for the training rule dict, the bitboard registers of madn_fast.cuh for a run-time rule mask).
+// Per iteration:
+//   1. each lane takes its step key and derives the 24-bit legal mask (branch-free bit rows);
 //   2. the (game, action) pairs of the warp are compacted into a shared list and dealt out evenly to the 32 lanes,
 //      two per lane and pass, so the Threefry calls — one per LEGAL action, half of all instructions — are
 //      load-balanced; the first pass also derives the NEXT iteration's step key (a third independent chain);
 //   3. the argmax of the categorical draw is a shared-memory atomicMax per game on (mantissa << 5 | 23 - action):
 //      largest 23-bit mantissa first, lowest action index on ties — jax.random.categorical's choice;
-//   4. each lane applies its game's move (incremental bitboard update); a finished game is written back at once.
-// Games end at different plies (mean 403, max ~850 in config 2), so a warp that kept its 32 games to the end would idle
-// 30 % of its lane-iterations: every kPlayRound iterations the live games of the CTA are packed into the lowest warps
-// through shared memory (23 words per game) and the emptied warps only wait at the barriers.  The loop key chain
+//   4. each lane applies its game's move; a finished game waits in its lane for the next compaction point, where the finished
+//      games of a warp are written back together.
+// Games end at different plies (mean 403, max ~850 in config 2): every kPlayRound iterations the live games of the CTA are
+// packed through shared memory (PlayState::kWords + 3 words per game) into the fewest warps that give all four warp schedulers
+// the same number of games (PlayShare), and the emptied warps only wait at the barriers.  The loop key chain
 // (rng <- split(rng, N + 1)[0], the same for every game) is produced a round ahead by one extra warp per CTA into a
-// double-buffered shared ring, so a warp that ran empty and is refilled finds the current value there.
-// A CTA that loaded a non-canonical game (see madn_fast.cuh) runs the generic rules of madn_core.cuh instead.
+// double-buffered shared ring.  Once a CTA is down to kPEnter games it switches to the draw-ahead mode (see the kernel).
+// A CTA that loaded a game outside the specialised rules' domain (madn_fast.cuh / madn_track.cuh) plays all its games with the
+// generic rules of madn_core.cuh (play_random_warp).
 #ifdef DOGSTEP_TRACE
 __device__ unsigned long long g_play_trace[128];
 __device__ int g_play_trace_block;
