@@ -335,6 +335,30 @@ def test_det_play_random_other_rule_sets_and_draw_ahead_sizes(seed):
                 k = np.asarray(k_next, dtype=np.uint32)
 
 
+@pytest.mark.parametrize("n", [65536, 5000])
+def test_det_play_random_repeated_runs_are_bit_identical(n):
+    """the persistent kernel hands games between warps through shared memory (compaction rounds, the draw-ahead tables behind
+    named barriers, the key ring): a missing barrier or fence would show as run-to-run differences.  30 runs of the same
+    batch must give the same bytes in every leaf and the same game lengths (the first run is checked against the oracle by
+    the tests above / by bench.py at full size)"""
+    dm = _dm()
+    from exploring_muzero_on_dog_b200 import jaxrand
+    key = jaxrand.split_host(jaxrand.PRNGKey(21))[1]
+    seeds = jaxrand.randint(key, n, 0, 1_000_000)
+    env0 = dm.env_reset(0, seed=seeds, **TRAIN_RULES)
+    ref = None
+    for rep in range(30):
+        env = env0.clone()
+        _, glen = dm.play_random(env, key, max_steps=2000)
+        got = {k: v.clone() for k, v in env.leaves().items()} if hasattr(env, "leaves") else {k: torch.as_tensor(v) for k, v in env.numpy().items()}
+        got["game_len"] = glen.clone()
+        if ref is None:
+            ref = got
+            continue
+        for k, v in ref.items():
+            assert torch.equal(torch.as_tensor(v).cpu(), torch.as_tensor(got[k]).cpu()), (rep, k)
+
+
 def test_entry_points_follow_the_device_of_their_tensors():
     """an env created with device='cuda:1' while cuda:0 is current must run on GPU 1, on GPU 1's current stream
     (needs two GPUs; the one-GPU test box skips it, `gpurun --gpus 2` runs it)"""
