@@ -780,7 +780,8 @@ __global__ void __launch_bounds__(kPlayMaxThreads + 32) k_madn_det_play_cta(cons
     // of the next step key).
     Key2 r = rng0;
     if (lane == 0) s_ring[0] = make_uint2(r.a, r.b);
-    for (int i = 1; i <= round_len + 1; ++i) {
+    const int need = min(round_len, max_steps);  // a launch of a few iterations (random_steps) does not pay for a whole round
+    for (int i = 1; i <= need; ++i) {
       r = split_i(r, 0u);
       if (lane == 0) s_ring[i] = make_uint2(r.a, r.b);
     }
@@ -881,14 +882,17 @@ __global__ void __launch_bounds__(kPlayMaxThreads + 32) k_madn_det_play_cta(cons
     // ---- kPlayRound lockstep iterations
     const int tend = min(t + round_len, max_steps);
     const uint2* rk = s_ring + par * (kRingMax + 2);  // rk[i] = the loop key of iteration t + i
-    if (producer) {  // next round's keys
-      uint2* nk = s_ring + (par ^ 1) * (kRingMax + 2);
-      const uint2 r0 = rk[round_len];
-      Key2 r{r0.x, r0.y};
-      if (lane == 0) nk[0] = r0;
-      for (int i = 1; i <= round_len + 1; ++i) {
-        r = split_i(r, 0u);
-        if (lane == 0) nk[i] = make_uint2(r.a, r.b);
+    if (producer) {  // next round's keys (none after the last round)
+      const int need = min(round_len, max_steps - tend);
+      if (need > 0) {
+        uint2* nk = s_ring + (par ^ 1) * (kRingMax + 2);
+        const uint2 r0 = rk[round_len];
+        Key2 r{r0.x, r0.y};
+        if (lane == 0) nk[0] = r0;
+        for (int i = 1; i <= need; ++i) {
+          r = split_i(r, 0u);
+          if (lane == 0) nk[i] = make_uint2(r.a, r.b);
+        }
       }
       t = tend;
       continue;
