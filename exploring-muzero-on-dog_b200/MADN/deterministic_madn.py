@@ -216,3 +216,74 @@ def play_random(env, rng_key, max_steps=2000, game_offset=0, game_len=None, tota
                                                       C.c_int64(game_offset), C.c_int32(max_steps), _lib.ptr(game_len),
                                                       _lib.ptr(total_steps), _lib.stream()), "madn_det_play_random")
     return env, game_len
+
+
+# ---- true-env mctx callbacks (:480-590) and the search that uses them (MADN/simulate_deterministicMADN.py:12-35) ---------------
+def embed_dim(env):
+    """floats of the env embedding: board, current_player, pins, reward, done, action_set"""
+    return int(_lib.lib().dogstep_madn_det_embed_dim(C.byref(env.cfg())))
+
+
+def policy_function(env):
+    """policy_function (:495-507) -> f32 [n, 24]: 100 * valid_action + 200 * winning_action (:480-493)"""
+    lg = torch.empty((env.n, 24), dtype=torch.float32, device=env.device)
+    cfg, st = env.cfg(), env.cstate()
+    _lib.check(_lib.lib().dogstep_madn_det_policy_function(C.byref(st), C.c_int64(env.n), C.byref(cfg), _lib.ptr(lg), _lib.stream()),
+               "madn_det_policy_function")
+    return _out(env, lg)
+
+
+def root_fn(env, rng_key):
+    """root_fn (:551-566); rng_key uint32 [n, 2].  value = rollout(env, key) (:509-541) as a scalar per game: the reference's
+    float32[4] holds four equal entries (see include/dogstep.h)."""
+    from .. import mcts
+    n, dev = env.n, env.device
+    prior = torch.empty((n, 24), dtype=torch.float32, device=dev)
+    value = torch.empty(n, dtype=torch.float32, device=dev)
+    emb = torch.empty((n, embed_dim(env)), dtype=torch.float32, device=dev)
+    cfg, st = env.cfg(), env.cstate()
+    _lib.check(_lib.lib().dogstep_madn_det_root_fn(C.byref(st), C.c_int64(n), C.byref(cfg), _lib.ptr(rng_key.contiguous()), _lib.ptr(prior),
+                                                  _lib.ptr(value), _lib.ptr(emb), _lib.stream()), "madn_det_root_fn")
+    return mcts.RootFnOutput(prior, value, emb)
+
+
+def value_function(env, rng_key):
+    """value_function (:543-549) = rollout(env, rng_key)"""
+    return root_fn(env, rng_key).value
+
+
+rollout = value_function
+
+
+def make_recurrent_fn(env):
+    """recurrent_fn (:568-590) for games with `env`'s static fields (players, layout, distance, rule dict), on the env embedding"""
+    from .. import mcts
+    cfg = env.cfg()
+
+    def recurrent_fn(params, rng_key, action, embedding):
+        n, dev = embedding.shape[0], embedding.device
+        prior = torch.empty((n, 24), dtype=torch.float32, device=dev)
+        value, reward, discount = (torch.empty(n, dtype=torch.float32, device=dev) for _ in range(3))
+        nxt = torch.empty_like(embedding)
+        _lib.check(_lib.lib().dogstep_madn_det_recurrent_fn(C.c_int64(n), C.byref(cfg), _lib.ptr(rng_key.contiguous()),
+                                                           _lib.ptr(action.to(torch.int32).contiguous()), _lib.ptr(embedding.contiguous()),
+                                                           _lib.ptr(prior), _lib.ptr(value), _lib.ptr(reward), _lib.ptr(discount),
+                                                           _lib.ptr(nxt), _lib.stream()), "madn_det_recurrent_fn")
+        return mcts.RecurrentFnOutput(reward, discount, prior, value), nxt
+    return recurrent_fn
+
+
+def run_gumbel(rng_key, env, num_simulations, graph_cache=None):
+    """run_gumbel (MADN/simulate_deterministicMADN.py:12-35): mctx.gumbel_muzero_policy on the true env with rollout values,
+    invalid_actions = ~valid_action, max_depth 350, qtransform_by_min_max(-1, 1) — batched over games (the reference runs
+    batch_size = 1); rng_key uint32 [n, 2]"""
+    import functools
+    from .. import mcts
+    from ..TicTacToe.mcts import _split_each
+    key1, key2 = _split_each(rng_key, 0), _split_each(rng_key, 1)    # key1, key2 = split(rng_key)
+    root = root_fn(env, _split_each(key2, 0))                         # root_fn(env, split(key2, batch_size = 1)[0])
+    invalid = ~valid_action(env).reshape(env.n, 24)
+    return mcts.gumbel_muzero_policy(None, key1, root, make_recurrent_fn(env), num_simulations, invalid_actions=invalid, max_depth=350,
+                                     qtransform=functools.partial(mcts.qtransform_by_min_max, min_value=-1, max_value=1),
+                                     graph_cache=graph_cache)
+

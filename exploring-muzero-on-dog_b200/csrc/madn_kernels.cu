@@ -1123,6 +1123,154 @@ __global__ void __launch_bounds__(kThreads) k_madn_cls_throw_die(const __grid_co
   }
 }
 
+// ---- true-env mctx callbacks of the deterministic game (MADN/deterministic_madn.py:480-590) -------------------------------
+// winning_action / policy_function / rollout / value_function / root_fn / recurrent_fn, the callbacks MADN/simulate_deterministicMADN.py
+// hands to mctx.gumbel_muzero_policy.  One warp per game; every lane holds the game in registers (generic rules: any geometry,
+// any rule set), lane a < 24 owns action a = pin * 6 + move - 1: its legality, the hypothetical env_step that tells whether it
+// wins (reward == 1), its Gumbel draw.  The env embedding is the state as floats: board[total], current_player, pins[4 n],
+// reward, done, action_set[6 n].  The reference's rollout value is a float32[4] of four equal entries (its `winner == -1` test
+// compares a bool array): +1 if the root player('s team) has won when the rollout stops, -1 otherwise, also at the 300-step cap;
+// the scalar is returned.
+constexpr int kTrueEnvWarps = 4;
+
+__device__ __forceinline__ float madn_policy_lane(const MadnGeom& g, const MadnRegs& s, uint32_t m, int a) {
+  MadnRegs t = s;
+  madn_det_step(g, t, a / 6, a % 6 + 1, m);  // winning_action (:480-493): env_step on a copy
+  return __fadd_rn(((m >> a) & 1u) ? 100.0f : 0.0f, t.reward == 1 ? 200.0f : 0.0f);
+}
+
+__device__ float madn_rollout_warp(const MadnGeom& g, const MadnRegs& s0, Key2 key, int lane) {
+  const uint32_t FULL = 0xFFFFFFFFu;
+  MadnRegs e = s0;
+  const int a = min(lane, 23);
+  for (int steps = 0; !e.done && steps < 300; ++steps) {
+    const Key2 nk = split_i(key, 0u), sub = split_i(key, 1u);  // key, subkey = split(key)
+    key = nk;
+    const uint32_t m = madn_det_valid_mask(g, e);
+    if (m == 0u) {
+      madn_det_no_step(g, e);
+      continue;
+    }
+    const float lg = madn_policy_lane(g, e, m, a);
+    const float u = uniform_i(sub, (uint32_t)a, 1.17549435e-38f, 1.0f);
+    const float v = __fadd_rn(-eval_log_f(-eval_log_f(u)), lg);  // jax.random.categorical: first maximum of gumbel + logits
+    uint32_t ord = __float_as_uint(__fadd_rn(v, 0.0f));
+    ord = (ord & 0x80000000u) ? ~ord : (ord | 0x80000000u);
+    ord = lane < 24 ? ord : 0u;
+    const uint32_t best = __reduce_max_sync(FULL, ord);
+    const int act = __ffs(__ballot_sync(FULL, ord == best && lane < 24)) - 1;
+    madn_det_step(g, e, act / 6, act % 6 + 1, m);  // map_action (:469-479)
+  }
+  return ((madn_winner_mask(g, e) >> gidx(s0.cur, 4)) & 1u) ? 1.0f : -1.0f;
+}
+
+__device__ void madn_from_emb(const MadnGeom& g, const float* __restrict__ f, MadnRegs& s) {
+#pragma unroll
+  for (int p = 0; p < 4; ++p) { s.occ[p] = 0ull; s.pins[p] = 0xFFFFFFFFu; s.as[p] = 0ull; }
+  for (int c = 0; c < g.total; ++c) {
+    const int v = (int)(int8_t)f[c];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) s.occ[p] |= (v == p) ? (1ull << c) : 0ull;
+  }
+  const float* q = f + g.total;
+  s.cur = (int)(int8_t)q[0];
+  for (int p = 0; p < g.n; ++p) {
+    uint32_t w = 0;
+    for (int k = 0; k < 4; ++k) w |= (uint32_t)((int)(int8_t)q[1 + 4 * p + k] & 0xFF) << (8 * k);
+    s.pins[p] = w;
+  }
+  q += 1 + 4 * g.n;
+  s.reward = (int)(int8_t)q[0];
+  s.done = ((int)q[1] & 0xFF) != 0;
+  for (int p = 0; p < g.n; ++p) {
+    uint64_t w = 0;
+    for (int k = 0; k < 6; ++k) w |= (uint64_t)((int)(int8_t)q[2 + 6 * p + k] & 0xFF) << (8 * k);
+    s.as[p] = w;
+  }
+  s.die = 0;
+}
+
+// every lane holds the same state; the lanes write the row together
+__device__ void madn_to_emb(const MadnGeom& g, const MadnRegs& s, float* __restrict__ f, int lane) {
+  const int E = g.total + 10 * g.n + 3;
+  for (int k = lane; k < E; k += 32) {
+    int v;
+    if (k < g.total) {
+      v = -1;
+#pragma unroll
+      for (int p = 0; p < 4; ++p) v = ((s.occ[p] >> k) & 1ull) ? p : v;  // later players win, as set_pins_on_board writes them
+    } else if (k == g.total) {
+      v = s.cur;
+    } else if (k < g.total + 1 + 4 * g.n) {
+      const int j = k - g.total - 1;
+      v = byte_s(pick4(s.pins, j >> 2), j & 3);
+    } else if (k == g.total + 1 + 4 * g.n) {
+      v = s.reward;
+    } else if (k == g.total + 2 + 4 * g.n) {
+      v = s.done;
+    } else {
+      const int j = k - (g.total + 3 + 4 * g.n);
+      v = byte_s64(pick4(s.as, j / 6), j % 6);
+    }
+    f[k] = (float)v;
+  }
+}
+
+__global__ void __launch_bounds__(kTrueEnvWarps * 32) k_madn_det_policy_function(const __grid_constant__ MadnGeom g, MadnPtrs p, int64_t n,
+                                                                                float* __restrict__ logits) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * kTrueEnvWarps + (threadIdx.x >> 5);
+  if (i >= n) return;
+  MadnRegs s;
+  load_state<true>(g, p, i, s);
+  const uint32_t m = madn_det_valid_mask(g, s);
+  const float lg = madn_policy_lane(g, s, m, min(lane, 23));
+  if (lane < 24) logits[i * 24 + lane] = lg;
+}
+
+__global__ void __launch_bounds__(kTrueEnvWarps * 32) k_madn_det_root_fn(const __grid_constant__ MadnGeom g, MadnPtrs p, int64_t n,
+                                                                        const uint32_t* __restrict__ keys, float* __restrict__ prior,
+                                                                        float* __restrict__ value, float* __restrict__ emb) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * kTrueEnvWarps + (threadIdx.x >> 5);
+  if (i >= n) return;
+  MadnRegs s;
+  load_state<true>(g, p, i, s);
+  const uint32_t m = madn_det_valid_mask(g, s);
+  const float lg = madn_policy_lane(g, s, m, min(lane, 23));
+  if (lane < 24) prior[i * 24 + lane] = lg;
+  const float v = madn_rollout_warp(g, s, Key2{keys[2 * i], keys[2 * i + 1]}, lane);
+  if (lane == 0) value[i] = v;
+  madn_to_emb(g, s, emb + i * (g.total + 10 * g.n + 3), lane);
+}
+
+__global__ void __launch_bounds__(kTrueEnvWarps * 32) k_madn_det_recurrent_fn(const __grid_constant__ MadnGeom g, int64_t n,
+                                                                             const uint32_t* __restrict__ keys,
+                                                                             const int32_t* __restrict__ action,
+                                                                             const float* __restrict__ emb_in, float* __restrict__ prior,
+                                                                             float* __restrict__ value, float* __restrict__ reward,
+                                                                             float* __restrict__ discount, float* __restrict__ emb_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * kTrueEnvWarps + (threadIdx.x >> 5);
+  if (i >= n) return;
+  const int E = g.total + 10 * g.n + 3;
+  MadnRegs s;
+  madn_from_emb(g, emb_in + i * E, s);
+  const int a = action[i];
+  madn_det_step(g, s, (int)(int8_t)floordiv(a, 6), (int)(int8_t)(floormod(a, 6) + 1), madn_det_valid_mask(g, s));  // map_action: both int8
+  const uint32_t m = madn_det_valid_mask(g, s);
+  const float lg = madn_policy_lane(g, s, m, min(lane, 23));
+  if (lane < 24) prior[i * 24 + lane] = lg;
+  const float v = s.done ? 0.0f : madn_rollout_warp(g, s, Key2{keys[2 * i], keys[2 * i + 1]}, lane);
+  if (lane == 0) {
+    value[i] = v;
+    reward[i] = (float)s.reward;
+    discount[i] = s.done ? 0.0f : -1.0f;
+  }
+  __syncwarp();
+  madn_to_emb(g, s, emb_out + i * E, lane);  // emb_out may alias emb_in: every lane has read its input above
+}
+
 // ---- self-play bookkeeping: one lockstep iteration of play_batch_of_games_jitted after the search ---------------------
 // MuZero_det_MADN/game_agent.py:64-148 (do_active_step) and MuZero_Classic_MADN/game_agent_stochastic.py:86-204.
 // CTAs of 256 threads take 32 games: warp 0 steps them thread per game (coalesced leaf loads, env_step / no_step, targets,
@@ -1378,6 +1526,41 @@ int dogstep_madn_cls_encode_board(const dogstep_madn_cls_state* s, int64_t n, co
   if (!obs) return DOGSTEP_ERR_INVALID_ARG;
   int64_t words = n * (2 * g.n + 3) * (g.total >> 2);
   k_madn_encode_board<false><<<blocks_for(words, 256), 256, 0, st>>>(g, p, n, obs);
+  return check_launch();
+}
+
+int dogstep_madn_det_embed_dim(const dogstep_madn_cfg* cfg) {
+  MadnGeom g;
+  if (madn_make_geom(cfg, &g)) return -1;
+  return g.total + 10 * g.n + 3;
+}
+
+int dogstep_madn_det_policy_function(const dogstep_madn_det_state* s, int64_t n, const dogstep_madn_cfg* cfg, float* logits,
+                                     void* stream) {
+  DS_PROLOGUE(det_ptrs)
+  if (!logits) return DOGSTEP_ERR_INVALID_ARG;
+  k_madn_det_policy_function<<<blocks_for(n, kTrueEnvWarps), kTrueEnvWarps * 32, 0, st>>>(g, p, n, logits);
+  return check_launch();
+}
+
+int dogstep_madn_det_root_fn(const dogstep_madn_det_state* s, int64_t n, const dogstep_madn_cfg* cfg, const uint32_t* keys,
+                             float* prior_logits, float* value, float* embedding, void* stream) {
+  DS_PROLOGUE(det_ptrs)
+  if (!keys || !prior_logits || !value || !embedding) return DOGSTEP_ERR_INVALID_ARG;
+  k_madn_det_root_fn<<<blocks_for(n, kTrueEnvWarps), kTrueEnvWarps * 32, 0, st>>>(g, p, n, keys, prior_logits, value, embedding);
+  return check_launch();
+}
+
+int dogstep_madn_det_recurrent_fn(int64_t n, const dogstep_madn_cfg* cfg, const uint32_t* keys, const int32_t* action,
+                                  const float* embedding_in, float* prior_logits, float* value, float* reward, float* discount,
+                                  float* embedding_out, void* stream) {
+  MadnGeom g;
+  if (n < 0) return DOGSTEP_ERR_INVALID_ARG;
+  if (int rc = madn_make_geom(cfg, &g)) return rc;
+  if (!keys || !action || !embedding_in || !prior_logits || !value || !reward || !discount || !embedding_out) return DOGSTEP_ERR_INVALID_ARG;
+  if (n == 0) return DOGSTEP_OK;
+  k_madn_det_recurrent_fn<<<blocks_for(n, kTrueEnvWarps), kTrueEnvWarps * 32, 0, (cudaStream_t)stream>>>(
+      g, n, keys, action, embedding_in, prior_logits, value, reward, discount, embedding_out);
   return check_launch();
 }
 

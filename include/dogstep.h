@@ -75,6 +75,28 @@ int dogstep_madn_det_no_step(const dogstep_madn_det_state* s, int64_t n, const d
 int dogstep_madn_set_pins_on_board(const int8_t* pins, int8_t* board, int64_t n, const dogstep_madn_cfg* cfg,
                                    void* stream);
 
+/* True-env mctx callbacks of the deterministic game — MADN/deterministic_madn.py:480-590, the functions
+ * MADN/simulate_deterministicMADN.py:12-35 hands to mctx.gumbel_muzero_policy.  The env embedding is the state as floats,
+ * E = total + 10 * num_players + 3: board[total], current_player, pins[4 P], reward, done, action_set[6 P]
+ * (dogstep_madn_det_embed_dim).  Actions are indices 0..23 (map_action :469-479: pin = a // 6, move = a % 6 + 1, both int8).
+ *   policy_function (:495-507): logits f32 [n,24] = 100 * valid_action + 200 * winning_action, winning_action (:480-493) =
+ *     "env_step on a copy returns reward 1";
+ *   root_fn (:551-566): prior = policy_function(env), value = rollout(env, key) (:509-541: at most 300 steps of
+ *     key, subkey = split(key); no_step if nothing is legal, else categorical(subkey, policy_function) -> env_step), embedding = env.
+ *     The reference's value is a float32[4] of four equal entries (its `winner == -1` test compares a bool array): +1 if the
+ *     root player('s team) has won when the rollout stops, -1 otherwise — also when the cap ends it; the scalar is written;
+ *   recurrent_fn (:568-590): env_step(embedding, map_action(action)); reward, discount = done ? 0 : -1, prior of the successor,
+ *     value = done ? 0 : rollout.  embedding_out may alias embedding_in.
+ * keys u32 [n,2].  One warp per game, generic rules (any geometry / rule set). */
+int dogstep_madn_det_embed_dim(const dogstep_madn_cfg* cfg);
+int dogstep_madn_det_policy_function(const dogstep_madn_det_state* s, int64_t n, const dogstep_madn_cfg* cfg, float* logits,
+                                     void* stream);
+int dogstep_madn_det_root_fn(const dogstep_madn_det_state* s, int64_t n, const dogstep_madn_cfg* cfg, const uint32_t* keys,
+                             float* prior_logits, float* value, float* embedding, void* stream);
+int dogstep_madn_det_recurrent_fn(int64_t n, const dogstep_madn_cfg* cfg, const uint32_t* keys, const int32_t* action,
+                                  const float* embedding_in, float* prior_logits, float* value, float* reward, float* discount,
+                                  float* embedding_out, void* stream);
+
 /* encode_board — MADN/deterministic_madn.py:395-438.  obs: int8 [n, 8*P+2, total]. */
 int dogstep_madn_det_encode_board(const dogstep_madn_det_state* s, int64_t n, const dogstep_madn_cfg* cfg,
                                   int8_t* obs, void* stream);

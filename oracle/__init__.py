@@ -181,6 +181,48 @@ def madn_det_valid_action(s):
     return mask.astype(bool)
 
 
+def _det_args(s):
+    return (C.c_int64(s.n), _p(s.board), _p(s.current_player), _p(s.pins), _p(s.reward), _p(s.done), _p(s.action_set))
+
+
+def madn_det_embed_dim(cfg):
+    return int(lib().orc_madn_det_embed_dim(*cfg.args))
+
+
+def madn_det_policy_function(s):
+    """policy_function of the true-env search (deterministic_madn.py:495-507) -> f32 [n, 24]"""
+    out = np.empty((s.n, 24), np.float32)
+    assert lib().orc_madn_det_policy_function(*s.cfg.args, *_det_args(s), _p(out)) == 0
+    return out
+
+
+def madn_det_root_fn(s, keys):
+    """root_fn (:551-566) -> (prior f32 [n, 24], value f32 [n], embedding f32 [n, E])"""
+    keys = _c(keys, np.uint32)
+    prior, value = np.empty((s.n, 24), np.float32), np.empty(s.n, np.float32)
+    emb = np.empty((s.n, madn_det_embed_dim(s.cfg)), np.float32)
+    assert lib().orc_madn_det_root_fn(*s.cfg.args, *_det_args(s), _p(keys), _p(prior), _p(value), _p(emb)) == 0
+    return prior, value, emb
+
+
+def madn_det_recurrent_fn(cfg, keys, action, emb):
+    """recurrent_fn (:568-590) on the env embedding -> (prior, value, reward, discount, embedding_out)"""
+    keys, action, emb = _c(keys, np.uint32), _c(action, np.int32), _c(emb, np.float32)
+    n = action.size
+    prior, value, reward, discount = np.empty((n, 24), np.float32), np.empty(n, np.float32), np.empty(n, np.float32), np.empty(n, np.float32)
+    emb_out = np.empty_like(emb)
+    assert lib().orc_madn_det_recurrent_fn(*cfg.args, C.c_int64(n), _p(keys), _p(action), _p(emb), _p(prior), _p(value), _p(reward),
+                                           _p(discount), _p(emb_out)) == 0
+    return prior, value, reward, discount, emb_out
+
+
+def madn_det_embedding(s):
+    """the env as floats: board, current_player, pins, reward, done, action_set"""
+    n = s.n
+    return np.concatenate([s.board.reshape(n, -1), s.current_player.reshape(n, 1), s.pins.reshape(n, -1), s.reward.reshape(n, 1),
+                           s.done.reshape(n, 1), s.action_set.reshape(n, -1)], axis=1).astype(np.float32)
+
+
 def madn_det_step(s, action):
     """in place; returns (reward, done)"""
     action = _c(action, np.int8).reshape(s.n, 2)

@@ -19,6 +19,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <pthread.h>
+#include <math.h>
 #include "../include/dogstep_rules.h"
 #include "jaxrand_oracle.h"
 
@@ -672,4 +673,138 @@ void orc_gumbel(const uint32_t *key, int64_t n, float *out) {
 int orc_choice6_v(const uint32_t *key, const float *p) { return orc_choice6(key, p); }
 int orc_categorical(const uint32_t *key, const uint8_t *mask, int na, int float_gumbel) {
   return categorical_valid(key, mask, na, float_gumbel);
+}
+
+
+/* ------------------------------------------------------------------------------------------
+ * True-env mctx callbacks of the deterministic game — MADN/deterministic_madn.py:480-590
+ * (winning_action, policy_function, rollout, value_function, root_fn, recurrent_fn).
+ * A state here is the six leaves of one game; `emb` is the same state as floats:
+ * board[total], current_player, pins[4 n], reward, done, action_set[6 n].
+ * The reference's rollout returns jnp.where(winner == -1, 0.0, jnp.where(winner[root_player], 1.0, -1.0)) with `winner`
+ * the BOOL array of get_winner: `winner == -1` is never true, so the value is a float32[4] of four equal entries,
+ * +1 if the root player('s team) has won when the rollout stops, else -1 (also when the 300-step cap ends it).  The scalar
+ * is returned.  Pinned by tests/golden/madn_det_reference_trueenv.npz (the reference's own functions on the shim).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int8_t board[64];
+  int8_t cur, reward;
+  uint8_t done;
+  int8_t pins[16];
+  int8_t aset[24];
+} det_env;
+
+static float f_log_d(float x) { return (float)log((double)x); } /* float contract of DESIGN 5 */
+
+static void det_policy_one(const madn_cfg *c, const det_env *e, float logits[24]) {
+  uint8_t mask[24];
+  orc_madn_det_valid_action_one(c, e->board, e->cur, e->pins, e->aset, mask);
+  for (int a = 0; a < 24; ++a) {  /* winning_action (:480-493): env_step on a copy, reward == 1 */
+    det_env t = *e;
+    orc_madn_det_step_one(c, t.board, &t.cur, t.pins, &t.reward, &t.done, t.aset, a / 6, a % 6 + 1);
+    logits[a] = (mask[a] ? 100.0f : 0.0f) + (t.reward == 1 ? 200.0f : 0.0f);
+  }
+}
+
+static float det_rollout_one(const madn_cfg *c, const det_env *e0, const uint32_t key_in[2]) {
+  det_env e = *e0;
+  uint32_t key[2] = {key_in[0], key_in[1]};
+  for (int steps = 0; !e.done && steps < 300; ++steps) {
+    uint32_t nk[2], sub[2];
+    orc_split_i(key, 0, nk); orc_split_i(key, 1, sub);
+    key[0] = nk[0]; key[1] = nk[1];
+    uint8_t mask[24];
+    orc_madn_det_valid_action_one(c, e.board, e.cur, e.pins, e.aset, mask);
+    int any = 0;
+    for (int a = 0; a < 24; ++a) any |= mask[a];
+    if (!any) { orc_madn_det_no_step_one(c, &e.cur, e.aset); continue; }
+    float lg[24];
+    det_policy_one(c, &e, lg);
+    int best = 0; float bv = 0.f;
+    for (int a = 0; a < 24; ++a) {  /* jax.random.categorical: first maximum of gumbel + logits */
+      float u = orc_uniform_i(sub, (uint32_t)a, 1.17549435e-38f, 1.0f);
+      float v = -f_log_d(-f_log_d(u)) + lg[a];
+      if (a == 0 || v > bv) { bv = v; best = a; }
+    }
+    orc_madn_det_step_one(c, e.board, &e.cur, e.pins, &e.reward, &e.done, e.aset, best / 6, best % 6 + 1);
+  }
+  int winner[4];
+  get_winner(c, e.board, winner);
+  return winner[gidx(e0->cur, 4)] ? 1.0f : -1.0f;
+}
+
+static void det_ld(const madn_cfg *c, det_env *e, int64_t g, const int8_t *board, const int8_t *cur, const int8_t *pins,
+                   const int8_t *reward, const uint8_t *done, const int8_t *aset) {
+  memset(e, 0, sizeof(*e));
+  memcpy(e->board, board + g * c->total, c->total);
+  e->cur = cur[g]; e->reward = reward[g]; e->done = done[g];
+  memcpy(e->pins, pins + g * c->n * 4, c->n * 4);
+  memcpy(e->aset, aset + g * c->n * 6, c->n * 6);
+}
+static void det_to_emb(const madn_cfg *c, const det_env *e, float *f) {
+  int k = 0;
+  for (int i = 0; i < c->total; ++i) f[k++] = e->board[i];
+  f[k++] = e->cur;
+  for (int i = 0; i < c->n * 4; ++i) f[k++] = e->pins[i];
+  f[k++] = e->reward; f[k++] = e->done;
+  for (int i = 0; i < c->n * 6; ++i) f[k++] = e->aset[i];
+}
+static void det_from_emb(const madn_cfg *c, det_env *e, const float *f) {
+  int k = 0;
+  memset(e, 0, sizeof(*e));
+  for (int i = 0; i < c->total; ++i) e->board[i] = (int8_t)f[k++];
+  e->cur = (int8_t)f[k++];
+  for (int i = 0; i < c->n * 4; ++i) e->pins[i] = (int8_t)f[k++];
+  e->reward = (int8_t)f[k++]; e->done = (uint8_t)f[k++];
+  for (int i = 0; i < c->n * 6; ++i) e->aset[i] = (int8_t)f[k++];
+}
+
+int orc_madn_det_embed_dim(CFG_ARGS) { MAKE_CFG; return cfg.total > 64 ? -1 : cfg.total + 10 * cfg.n + 3; }
+
+/* policy_function (:495-507) -> f32 [n, 24] */
+int orc_madn_det_policy_function(CFG_ARGS, int64_t n, const int8_t *board, const int8_t *current_player, const int8_t *pins,
+                                 const int8_t *reward, const uint8_t *done, const int8_t *action_set, float *logits) {
+  MAKE_CFG;
+  if (cfg.total > 64) return -1;
+  for (int64_t g = 0; g < n; ++g) {
+    det_env e; det_ld(&cfg, &e, g, board, current_player, pins, reward, done, action_set);
+    det_policy_one(&cfg, &e, logits + 24 * g);
+  }
+  return 0;
+}
+
+/* root_fn (:551-566): prior = policy_function(env), value = rollout(env, key), embedding = env.  keys u32 [n, 2] */
+int orc_madn_det_root_fn(CFG_ARGS, int64_t n, const int8_t *board, const int8_t *current_player, const int8_t *pins,
+                         const int8_t *reward, const uint8_t *done, const int8_t *action_set, const uint32_t *keys,
+                         float *prior, float *value, float *emb) {
+  MAKE_CFG;
+  if (cfg.total > 64) return -1;
+  const int E = cfg.total + 10 * cfg.n + 3;
+  for (int64_t g = 0; g < n; ++g) {
+    det_env e; det_ld(&cfg, &e, g, board, current_player, pins, reward, done, action_set);
+    det_policy_one(&cfg, &e, prior + 24 * g);
+    value[g] = det_rollout_one(&cfg, &e, keys + 2 * g);
+    det_to_emb(&cfg, &e, emb + (int64_t)E * g);
+  }
+  return 0;
+}
+
+/* recurrent_fn (:568-590): env_step(embedding, map_action(action)); reward, discount = done ? 0 : -1, prior = policy_function,
+ * value = done ? 0 : rollout */
+int orc_madn_det_recurrent_fn(CFG_ARGS, int64_t n, const uint32_t *keys, const int32_t *action, const float *emb_in,
+                              float *prior, float *value, float *reward, float *discount, float *emb_out) {
+  MAKE_CFG;
+  if (cfg.total > 64) return -1;
+  const int E = cfg.total + 10 * cfg.n + 3;
+  for (int64_t g = 0; g < n; ++g) {
+    det_env e; det_from_emb(&cfg, &e, emb_in + (int64_t)E * g);
+    const int a = action[g];
+    orc_madn_det_step_one(&cfg, e.board, &e.cur, e.pins, &e.reward, &e.done, e.aset, (int8_t)fdiv(a, 6), (int8_t)(fmod_(a, 6) + 1)); /* map_action (:469-479): both int8 */
+    reward[g] = (float)e.reward;
+    discount[g] = e.done ? 0.0f : -1.0f;
+    det_policy_one(&cfg, &e, prior + 24 * g);
+    value[g] = e.done ? 0.0f : det_rollout_one(&cfg, &e, keys + 2 * g);
+    det_to_emb(&cfg, &e, emb_out + (int64_t)E * g);
+  }
+  return 0;
 }
