@@ -143,3 +143,97 @@ def encode_board(env, dtype=torch.int8):
     _lib.check(_lib.lib().dogstep_madn_cls_encode_board(C.byref(st), C.c_int64(env.n), C.byref(cfg), _lib.ptr(obs),
                                                        _lib.stream()), "madn_cls_encode_board")
     return _out(env, obs if dtype == torch.int8 else obs.to(dtype))
+
+
+# ---- true-env mctx callbacks (:541-714) and the search that uses them (MADN/simulate_classicMADN.py:51-76) ------
+# The reference as it stands raises before any of these returns (winning_action builds its scratch copy without the `key`
+# field, :551-565); see include/dogstep.h and tests/golden/gen_madn_cls_trueenv_goldens.py for what is computed and how it is pinned.
+def embed_dim(env):
+    """floats of the env embedding: board, current_player, pins, reward, done, die, key as four 16-bit halves"""
+    return int(_lib.lib().dogstep_madn_cls_embed_dim(C.byref(env.cfg())))
+
+
+def policy_function(env):
+    """policy_function (:571-583) -> f32 [n, 4]: 100 * valid_action + 200 * winning_action (:543-569)"""
+    lg = torch.empty((env.n, 4), dtype=torch.float32, device=env.device)
+    cfg, st = env.cfg(), env.cstate()
+    _lib.check(_lib.lib().dogstep_madn_cls_policy_function(C.byref(st), C.c_int64(env.n), C.byref(cfg), _lib.ptr(lg), _lib.stream()),
+               "madn_cls_policy_function")
+    return _out(env, lg)
+
+
+def root_fn(env, rng_key):
+    """root_fn (:690-714); rng_key uint32 [n, 2]; value = rollout(env, key) (:585-616) as a scalar per game"""
+    from .. import mcts
+    n, dev = env.n, env.device
+    prior = torch.empty((n, 4), dtype=torch.float32, device=dev)
+    value = torch.empty(n, dtype=torch.float32, device=dev)
+    emb = torch.empty((n, embed_dim(env)), dtype=torch.float32, device=dev)
+    cfg, st = env.cfg(), env.cstate()
+    _lib.check(_lib.lib().dogstep_madn_cls_root_fn(C.byref(st), C.c_int64(n), C.byref(cfg), _lib.ptr(rng_key.contiguous()), _lib.ptr(prior),
+                                                  _lib.ptr(value), _lib.ptr(emb), _lib.stream()), "madn_cls_root_fn")
+    return mcts.RootFnOutput(prior, value, emb)
+
+
+def value_function(env, rng_key):
+    """value_function (:618-622) = rollout(env, rng_key)"""
+    return root_fn(env, rng_key).value
+
+
+rollout = value_function
+
+
+def _keys_or_zeros(rng_key, n, dev):  # mcts.stochastic_muzero_policy probes the callbacks' shapes with rng_key = None
+    return torch.zeros((n, 2), dtype=torch.uint32, device=dev) if rng_key is None else rng_key.contiguous()
+
+
+def make_recurrent_fn(env):
+    """recurrent_fn (:657-688), the decision node: (chance_logits = log(1/6) x 6, afterstate_value), afterstate embedding"""
+    from .. import mcts
+    cfg = env.cfg()
+
+    def recurrent_fn(params, rng_key, action, embedding):
+        n, dev = embedding.shape[0], embedding.device
+        chance = torch.empty((n, 6), dtype=torch.float32, device=dev)
+        value = torch.empty(n, dtype=torch.float32, device=dev)
+        nxt = torch.empty_like(embedding)
+        _lib.check(_lib.lib().dogstep_madn_cls_decision_recurrent_fn(
+            C.c_int64(n), C.byref(cfg), _lib.ptr(_keys_or_zeros(rng_key, n, dev)), _lib.ptr(action.to(torch.int32).contiguous()),
+            _lib.ptr(embedding.contiguous()), _lib.ptr(chance), _lib.ptr(value), _lib.ptr(nxt), _lib.stream()), "madn_cls_decision_recurrent_fn")
+        return mcts.DecisionRecurrentFnOutput(chance, value), nxt
+    return recurrent_fn
+
+
+def make_recurrent_chance_fn(env):
+    """recurrent_chance_fn (:624-655): (action_logits = valid_action as 0 / 1, value, reward, discount), state embedding"""
+    from .. import mcts
+    cfg = env.cfg()
+
+    def recurrent_chance_fn(params, rng_key, chance_outcome, afterstate):
+        n, dev = afterstate.shape[0], afterstate.device
+        logits = torch.empty((n, 4), dtype=torch.float32, device=dev)
+        value, reward, discount = (torch.empty(n, dtype=torch.float32, device=dev) for _ in range(3))
+        nxt = torch.empty_like(afterstate)
+        _lib.check(_lib.lib().dogstep_madn_cls_chance_recurrent_fn(
+            C.c_int64(n), C.byref(cfg), _lib.ptr(_keys_or_zeros(rng_key, n, dev)), _lib.ptr(chance_outcome.to(torch.int32).contiguous()),
+            _lib.ptr(afterstate.contiguous()), _lib.ptr(logits), _lib.ptr(value), _lib.ptr(reward), _lib.ptr(discount), _lib.ptr(nxt),
+            _lib.stream()), "madn_cls_chance_recurrent_fn")
+        return mcts.ChanceRecurrentFnOutput(logits, value, reward, discount), nxt
+    return recurrent_chance_fn
+
+
+def run_mcts_search(env, rng_key, num_simulations=100, dirichlet_noise=None, graph_cache=None):
+    """run_mcts_search (MADN/simulate_classicMADN.py:51-76): mctx.stochastic_muzero_policy on the true env with rollout values,
+    invalid_actions = ~valid_action, max_depth 500, qtransform_by_min_max(-1, 1) — batched over games; rng_key uint32 [n, 2].
+    dirichlet_noise: the root noise sample (mcts.stochastic_muzero_policy; jax's gamma sampler is not reproduced)"""
+    import functools
+    from .. import mcts
+    from ..TicTacToe.mcts import _split_each
+    key1, key2 = _split_each(rng_key, 0), _split_each(rng_key, 1)    # key1, key2 = split(rng_key)
+    root = root_fn(env, _split_each(key2, 0))                         # root_fn(env, split(key2, batch_size = 1)[0])
+    invalid = ~valid_action(env).reshape(env.n, 4)
+    return mcts.stochastic_muzero_policy(None, key1, root, make_recurrent_fn(env), make_recurrent_chance_fn(env), num_simulations,
+                                         invalid_actions=invalid, max_depth=500, dirichlet_noise=dirichlet_noise,
+                                         qtransform=functools.partial(mcts.qtransform_by_min_max, min_value=-1, max_value=1),
+                                         graph_cache=graph_cache)
+

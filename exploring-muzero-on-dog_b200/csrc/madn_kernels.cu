@@ -1090,15 +1090,8 @@ __global__ void __launch_bounds__(kPlayMaxThreads + 32) k_madn_det_play_cta(cons
 
 // MuZero_det_MADN/game_agent.py:12-22 — the rule dict of every training / benchmark configuration gets its own program
 
-__global__ void __launch_bounds__(kThreads) k_madn_cls_throw_die(const __grid_constant__ MadnGeom g, MadnPtrs p, int64_t n,
-                                                                 float* __restrict__ probs, int write_die, int only_active) {
-  int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-  if (i >= n) return;
-  if (only_active && p.done[i] != 0) return;
-  MadnRegs s;
-  load_state<false>(g, p, i, s);
-  // dice_probabilities (classic_madn.py:14-18,208-228): float32 literals rounded from doubles
-  float pr[6];
+// dice_probabilities (classic_madn.py:14-18,208-228): float32 literals rounded from doubles
+__device__ __forceinline__ void madn_dice_probabilities(const MadnGeom& g, const MadnRegs& s, float pr[6]) {
   const int locked = madn_soft_locked(g, s) && DS_RULE(g, DOGSTEP_RULE_DICE_RETHROW);
   if (locked && DS_RULE(g, DOGSTEP_RULE_START_ON_1)) {
     pr[0] = pr[5] = (float)(76.0 / 216);
@@ -1110,16 +1103,36 @@ __global__ void __launch_bounds__(kThreads) k_madn_cls_throw_die(const __grid_co
 #pragma unroll
     for (int k = 0; k < 6; ++k) pr[k] = (float)(1.0 / 6);
   }
+}
+
+// throw_die (:230-242): key, rng_key = split(env.key); die = choice(rng_key, 1..6, p = dice_probabilities(env))
+__device__ __forceinline__ void madn_throw_die(const MadnGeom& g, MadnRegs& s, Key2& key) {
+  float pr[6];
+  madn_dice_probabilities(g, s, pr);
+  const Key2 knew = split_i(key, 0), sub = split_i(key, 1);
+  s.die = choice6(sub, pr) + 1;
+  key = knew;
+}
+
+__global__ void __launch_bounds__(kThreads) k_madn_cls_throw_die(const __grid_constant__ MadnGeom g, MadnPtrs p, int64_t n,
+                                                                 float* __restrict__ probs, int write_die, int only_active) {
+  int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n) return;
+  if (only_active && p.done[i] != 0) return;
+  MadnRegs s;
+  load_state<false>(g, p, i, s);
   if (probs) {
+    float pr[6];
+    madn_dice_probabilities(g, s, pr);
 #pragma unroll
     for (int k = 0; k < 6; ++k) probs[i * 6 + k] = pr[k];
   }
   if (write_die) {
     Key2 key{p.key[2 * i], p.key[2 * i + 1]};
-    Key2 knew = split_i(key, 0), sub = split_i(key, 1);
-    p.die[i] = (int8_t)(choice6(sub, pr) + 1);
-    p.key[2 * i] = knew.a;
-    p.key[2 * i + 1] = knew.b;
+    madn_throw_die(g, s, key);
+    p.die[i] = (int8_t)s.die;
+    p.key[2 * i] = key.a;
+    p.key[2 * i + 1] = key.b;
   }
 }
 
@@ -1269,6 +1282,162 @@ __global__ void __launch_bounds__(kTrueEnvWarps * 32) k_madn_det_recurrent_fn(co
   }
   __syncwarp();
   madn_to_emb(g, s, emb_out + i * E, lane);  // emb_out may alias emb_in: every lane has read its input above
+}
+
+// ---- true-env mctx callbacks of the dice game (MADN/classic_madn.py:541-714) ------------------------------------
+// winning_action / policy_function / rollout / root_fn / recurrent_fn (decision node -> afterstate) / recurrent_chance_fn
+// (afterstate + die -> state), for mctx.stochastic_muzero_policy on the true env.  The reference as it stands raises before any
+// of them returns (winning_action builds its scratch copy without the dataclass's `key` field, :551-565); what is restated is
+// what its function bodies compute once that constructor call goes through (pinned by tests/golden/madn_cls_reference_trueenv.npz).
+// One warp per game, every lane holds the game, lane a < 4 owns pin a.  Embedding: board[total], current_player, pins[4 n],
+// reward, done, die, key as four 16-bit halves (a float32 cannot hold a uint32).  The rollout throws the die with the ENV's key
+// chain (throw_die, :230-242) and draws the move with the rollout's.
+__device__ __forceinline__ float madn_cls_policy_lane(const MadnGeom& g, const MadnRegs& s, uint32_t m, int a) {
+  MadnRegs t = s;
+  madn_cls_step(g, t, a, m);  // winning_action (:543-569)
+  return __fadd_rn(((m >> a) & 1u) ? 100.0f : 0.0f, t.reward == 1 ? 200.0f : 0.0f);
+}
+
+__device__ float madn_cls_rollout_warp(const MadnGeom& g, const MadnRegs& s0, Key2 env_key, Key2 key, int lane) {
+  const uint32_t FULL = 0xFFFFFFFFu;
+  MadnRegs e = s0;
+  const int a = min(lane, 3);
+  for (int steps = 0; !e.done && steps < 300; ++steps) {
+    const Key2 nk = split_i(key, 0u), sub = split_i(key, 1u);
+    key = nk;
+    madn_throw_die(g, e, env_key);
+    const uint32_t m = madn_cls_valid_mask(g, e);
+    if (m == 0u) {
+      e.cur = (int)(int8_t)floormod(e.cur + 1, g.n);  // no_step (:353-365)
+      continue;
+    }
+    const float lg = madn_cls_policy_lane(g, e, m, a);
+    const float u = uniform_i(sub, (uint32_t)a, 1.17549435e-38f, 1.0f);
+    const float v = __fadd_rn(-eval_log_f(-eval_log_f(u)), lg);
+    uint32_t ord = __float_as_uint(__fadd_rn(v, 0.0f));
+    ord = (ord & 0x80000000u) ? ~ord : (ord | 0x80000000u);
+    ord = lane < 4 ? ord : 0u;
+    const uint32_t best = __reduce_max_sync(FULL, ord);
+    const int act = __ffs(__ballot_sync(FULL, ord == best && lane < 4)) - 1;
+    madn_cls_step(g, e, act, m);
+  }
+  return ((madn_winner_mask(g, e) >> gidx(s0.cur, 4)) & 1u) ? 1.0f : -1.0f;
+}
+
+__device__ void madn_cls_from_emb(const MadnGeom& g, const float* __restrict__ f, MadnRegs& s, Key2& key) {
+#pragma unroll
+  for (int p = 0; p < 4; ++p) { s.occ[p] = 0ull; s.pins[p] = 0xFFFFFFFFu; s.as[p] = 0ull; }
+  for (int c = 0; c < g.total; ++c) {
+    const int v = (int)(int8_t)f[c];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) s.occ[p] |= (v == p) ? (1ull << c) : 0ull;
+  }
+  const float* q = f + g.total;
+  s.cur = (int)(int8_t)q[0];
+  for (int p = 0; p < g.n; ++p) {
+    uint32_t w = 0;
+    for (int k = 0; k < 4; ++k) w |= (uint32_t)((int)(int8_t)q[1 + 4 * p + k] & 0xFF) << (8 * k);
+    s.pins[p] = w;
+  }
+  q += 1 + 4 * g.n;
+  s.reward = (int)(int8_t)q[0];
+  s.done = ((int)q[1] & 0xFF) != 0;
+  s.die = (int)(int8_t)q[2];
+  key = Key2{(uint32_t)q[3] | ((uint32_t)q[4] << 16), (uint32_t)q[5] | ((uint32_t)q[6] << 16)};
+}
+
+__device__ void madn_cls_to_emb(const MadnGeom& g, const MadnRegs& s, Key2 key, float* __restrict__ f, int lane) {
+  const int E = g.total + 4 * g.n + 8, tail = g.total + 1 + 4 * g.n;
+  for (int k = lane; k < E; k += 32) {
+    float v;
+    if (k < g.total) {
+      int b = -1;
+#pragma unroll
+      for (int p = 0; p < 4; ++p) b = ((s.occ[p] >> k) & 1ull) ? p : b;
+      v = (float)b;
+    } else if (k == g.total) {
+      v = (float)s.cur;
+    } else if (k < tail) {
+      const int j = k - g.total - 1;
+      v = (float)byte_s(pick4(s.pins, j >> 2), j & 3);
+    } else {
+      const int j = k - tail;
+      v = j == 0 ? (float)s.reward : j == 1 ? (float)s.done : j == 2 ? (float)s.die
+          : j == 3 ? (float)(key.a & 0xFFFFu) : j == 4 ? (float)(key.a >> 16) : j == 5 ? (float)(key.b & 0xFFFFu) : (float)(key.b >> 16);
+    }
+    f[k] = v;
+  }
+}
+
+// mode 0: policy_function only (logits), 1: root_fn
+__global__ void __launch_bounds__(kTrueEnvWarps * 32) k_madn_cls_root_fn(const __grid_constant__ MadnGeom g, MadnPtrs p, int64_t n,
+                                                                        const uint32_t* __restrict__ keys, float* __restrict__ prior,
+                                                                        float* __restrict__ value, float* __restrict__ emb, int mode) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * kTrueEnvWarps + (threadIdx.x >> 5);
+  if (i >= n) return;
+  MadnRegs s;
+  load_state<false>(g, p, i, s);
+  const uint32_t m = madn_cls_valid_mask(g, s);
+  const float lg = madn_cls_policy_lane(g, s, m, min(lane, 3));
+  if (lane < 4) prior[i * 4 + lane] = lg;
+  if (mode == 0) return;
+  const Key2 ek{p.key[2 * i], p.key[2 * i + 1]};
+  const float v = madn_cls_rollout_warp(g, s, ek, Key2{keys[2 * i], keys[2 * i + 1]}, lane);
+  if (lane == 0) value[i] = v;
+  madn_cls_to_emb(g, s, ek, emb + i * (g.total + 4 * g.n + 8), lane);
+}
+
+// recurrent_fn (:657-688), the decision node
+__global__ void __launch_bounds__(kTrueEnvWarps * 32) k_madn_cls_decision_fn(const __grid_constant__ MadnGeom g, int64_t n,
+                                                                            const uint32_t* __restrict__ keys,
+                                                                            const int32_t* __restrict__ action,
+                                                                            const float* __restrict__ emb_in,
+                                                                            float* __restrict__ chance_logits,
+                                                                            float* __restrict__ afterstate_value,
+                                                                            float* __restrict__ emb_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * kTrueEnvWarps + (threadIdx.x >> 5);
+  if (i >= n) return;
+  const int E = g.total + 4 * g.n + 8;
+  MadnRegs s;
+  Key2 ek;
+  madn_cls_from_emb(g, emb_in + i * E, s, ek);
+  const uint32_t m = madn_cls_valid_mask(g, s);
+  if (m == 0u) s.cur = (int)(int8_t)floormod(s.cur + 1, g.n);  // no_step
+  else madn_cls_step(g, s, action[i], m);
+  if (lane < 6) chance_logits[i * 6 + lane] = eval_log_f((float)(1.0 / 6.0));  // jnp.ones(6) * jnp.log(1.0 / 6.0)
+  const float v = madn_cls_rollout_warp(g, s, ek, Key2{keys[2 * i], keys[2 * i + 1]}, lane);
+  if (lane == 0) afterstate_value[i] = v;
+  __syncwarp();
+  madn_cls_to_emb(g, s, ek, emb_out + i * E, lane);
+}
+
+// recurrent_chance_fn (:624-655)
+__global__ void __launch_bounds__(kTrueEnvWarps * 32) k_madn_cls_chance_fn(const __grid_constant__ MadnGeom g, int64_t n,
+                                                                          const uint32_t* __restrict__ keys,
+                                                                          const int32_t* __restrict__ outcome,
+                                                                          const float* __restrict__ emb_in, float* __restrict__ action_logits,
+                                                                          float* __restrict__ value, float* __restrict__ reward,
+                                                                          float* __restrict__ discount, float* __restrict__ emb_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * kTrueEnvWarps + (threadIdx.x >> 5);
+  if (i >= n) return;
+  const int E = g.total + 4 * g.n + 8;
+  MadnRegs s;
+  Key2 ek;
+  madn_cls_from_emb(g, emb_in + i * E, s, ek);
+  s.die = (int)(int8_t)(outcome[i] + 1);  // set_die(afterstate, chance_outcome + 1)
+  const uint32_t m = madn_cls_valid_mask(g, s);
+  if (lane < 4) action_logits[i * 4 + lane] = ((m >> lane) & 1u) ? 1.0f : 0.0f;
+  const float v = madn_cls_rollout_warp(g, s, ek, Key2{keys[2 * i], keys[2 * i + 1]}, lane);
+  if (lane == 0) {
+    value[i] = v;
+    reward[i] = (float)s.reward;
+    discount[i] = s.done ? 0.0f : 1.0f;
+  }
+  __syncwarp();
+  madn_cls_to_emb(g, s, ek, emb_out + i * E, lane);
 }
 
 // ---- self-play bookkeeping: one lockstep iteration of play_batch_of_games_jitted after the search ---------------------
@@ -1561,6 +1730,55 @@ int dogstep_madn_det_recurrent_fn(int64_t n, const dogstep_madn_cfg* cfg, const 
   if (n == 0) return DOGSTEP_OK;
   k_madn_det_recurrent_fn<<<blocks_for(n, kTrueEnvWarps), kTrueEnvWarps * 32, 0, (cudaStream_t)stream>>>(
       g, n, keys, action, embedding_in, prior_logits, value, reward, discount, embedding_out);
+  return check_launch();
+}
+
+int dogstep_madn_cls_embed_dim(const dogstep_madn_cfg* cfg) {
+  MadnGeom g;
+  if (madn_make_geom(cfg, &g)) return -1;
+  return g.total + 4 * g.n + 8;
+}
+
+int dogstep_madn_cls_policy_function(const dogstep_madn_cls_state* s, int64_t n, const dogstep_madn_cfg* cfg, float* logits,
+                                     void* stream) {
+  DS_PROLOGUE(cls_ptrs)
+  if (!logits) return DOGSTEP_ERR_INVALID_ARG;
+  k_madn_cls_root_fn<<<blocks_for(n, kTrueEnvWarps), kTrueEnvWarps * 32, 0, st>>>(g, p, n, nullptr, logits, nullptr, nullptr, 0);
+  return check_launch();
+}
+
+int dogstep_madn_cls_root_fn(const dogstep_madn_cls_state* s, int64_t n, const dogstep_madn_cfg* cfg, const uint32_t* keys,
+                             float* prior_logits, float* value, float* embedding, void* stream) {
+  DS_PROLOGUE(cls_ptrs)
+  if (!keys || !prior_logits || !value || !embedding || !p.key) return DOGSTEP_ERR_INVALID_ARG;
+  k_madn_cls_root_fn<<<blocks_for(n, kTrueEnvWarps), kTrueEnvWarps * 32, 0, st>>>(g, p, n, keys, prior_logits, value, embedding, 1);
+  return check_launch();
+}
+
+int dogstep_madn_cls_decision_recurrent_fn(int64_t n, const dogstep_madn_cfg* cfg, const uint32_t* keys, const int32_t* action,
+                                           const float* embedding_in, float* chance_logits, float* afterstate_value,
+                                           float* embedding_out, void* stream) {
+  MadnGeom g;
+  if (n < 0) return DOGSTEP_ERR_INVALID_ARG;
+  if (int rc = madn_make_geom(cfg, &g)) return rc;
+  if (!keys || !action || !embedding_in || !chance_logits || !afterstate_value || !embedding_out) return DOGSTEP_ERR_INVALID_ARG;
+  if (n == 0) return DOGSTEP_OK;
+  k_madn_cls_decision_fn<<<blocks_for(n, kTrueEnvWarps), kTrueEnvWarps * 32, 0, (cudaStream_t)stream>>>(
+      g, n, keys, action, embedding_in, chance_logits, afterstate_value, embedding_out);
+  return check_launch();
+}
+
+int dogstep_madn_cls_chance_recurrent_fn(int64_t n, const dogstep_madn_cfg* cfg, const uint32_t* keys, const int32_t* chance_outcome,
+                                         const float* embedding_in, float* action_logits, float* value, float* reward,
+                                         float* discount, float* embedding_out, void* stream) {
+  MadnGeom g;
+  if (n < 0) return DOGSTEP_ERR_INVALID_ARG;
+  if (int rc = madn_make_geom(cfg, &g)) return rc;
+  if (!keys || !chance_outcome || !embedding_in || !action_logits || !value || !reward || !discount || !embedding_out)
+    return DOGSTEP_ERR_INVALID_ARG;
+  if (n == 0) return DOGSTEP_OK;
+  k_madn_cls_chance_fn<<<blocks_for(n, kTrueEnvWarps), kTrueEnvWarps * 32, 0, (cudaStream_t)stream>>>(
+      g, n, keys, chance_outcome, embedding_in, action_logits, value, reward, discount, embedding_out);
   return check_launch();
 }
 

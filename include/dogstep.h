@@ -153,6 +153,34 @@ int dogstep_madn_cls_no_step(const dogstep_madn_cls_state* s, int64_t n, const d
 int dogstep_madn_cls_encode_board(const dogstep_madn_cls_state* s, int64_t n, const dogstep_madn_cfg* cfg,
                                   int8_t* obs, void* stream);
 
+/* True-env mctx callbacks of the dice game — MADN/classic_madn.py:541-714, for mctx.stochastic_muzero_policy
+ * on the true env.  The reference as it stands raises before any of them returns: winning_action (:551-565) builds its scratch
+ * copy without the dataclass's `key` field; these entry points compute what the reference's function bodies compute once that
+ * constructor call goes through (pinned by tests/golden/madn_cls_reference_trueenv.npz, see its generator).
+ * Embedding E = total + 4 * num_players + 8: board[total], current_player, pins[4 P], reward, done, die, env.key as four 16-bit
+ * halves (k0 lo, k0 hi, k1 lo, k1 hi).  Actions are pins 0..3, chance outcomes 0..5 (die - 1).  keys u32 [n,2].
+ *   policy_function (:571-583): logits f32 [n,4] = 100 * valid_action + 200 * winning_action;
+ *   root_fn (:690-714): prior = policy_function(env), value = rollout(env, key) (:585-616: at most 300 steps of key, subkey =
+ *     split(key); env = throw_die(env) on the ENV's key chain; no_step if nothing is legal, else categorical(subkey,
+ *     policy_function) -> env_step; value +-1 as in the deterministic game), embedding = env;
+ *   recurrent_fn (:657-688, decision node): afterstate = no_step(env) if nothing is legal else env_step(env, action);
+ *     chance_logits f32 [n,6] = log(1/6), afterstate_value = rollout(afterstate, key);
+ *   recurrent_chance_fn (:624-655): env = set_die(afterstate, outcome + 1); action_logits f32 [n,4] = valid_action as 0 / 1,
+ *     value = rollout(env, key), reward = env.reward, discount = done ? 0 : 1.
+ * embedding_out may alias embedding_in. */
+int dogstep_madn_cls_embed_dim(const dogstep_madn_cfg* cfg);
+int dogstep_madn_cls_policy_function(const dogstep_madn_cls_state* s, int64_t n, const dogstep_madn_cfg* cfg, float* logits,
+                                     void* stream);
+int dogstep_madn_cls_root_fn(const dogstep_madn_cls_state* s, int64_t n, const dogstep_madn_cfg* cfg, const uint32_t* keys,
+                             float* prior_logits, float* value, float* embedding, void* stream);
+int dogstep_madn_cls_decision_recurrent_fn(int64_t n, const dogstep_madn_cfg* cfg, const uint32_t* keys, const int32_t* action,
+                                           const float* embedding_in, float* chance_logits, float* afterstate_value,
+                                           float* embedding_out, void* stream);
+int dogstep_madn_cls_chance_recurrent_fn(int64_t n, const dogstep_madn_cfg* cfg, const uint32_t* keys, const int32_t* chance_outcome,
+                                         const float* embedding_in, float* action_logits, float* value, float* reward,
+                                         float* discount, float* embedding_out, void* stream);
+
+
 /* ---------------------------------------------------------------- DOG (2v2 card game)
  * Batched leaves of the `DOG` dataclass (DOG/dog.py:31-56).  num_cards is 14: the disable_* rule bits
  * are rejected with DOGSTEP_ERR_UNSUPPORTED (the reference itself is only self-consistent with all cards).

@@ -223,6 +223,57 @@ def madn_det_embedding(s):
                            s.done.reshape(n, 1), s.action_set.reshape(n, -1)], axis=1).astype(np.float32)
 
 
+def _cls_args(s):
+    return (C.c_int64(s.n), _p(s.board), _p(s.current_player), _p(s.pins), _p(s.reward), _p(s.done), _p(s.die), _p(s.key))
+
+
+def madn_cls_embed_dim(cfg):
+    return int(lib().orc_madn_cls_embed_dim(*cfg.args))
+
+
+def madn_cls_embedding(s):
+    """the dice env as floats: board, current_player, pins, reward, done, die, key as four 16-bit halves"""
+    n = s.n
+    k = s.key.astype(np.uint32)
+    halves = np.stack([k[:, 0] & 0xFFFF, k[:, 0] >> 16, k[:, 1] & 0xFFFF, k[:, 1] >> 16], 1)
+    return np.concatenate([s.board.reshape(n, -1), s.current_player.reshape(n, 1), s.pins.reshape(n, -1), s.reward.reshape(n, 1),
+                           s.done.reshape(n, 1), s.die.reshape(n, 1), halves], axis=1).astype(np.float32)
+
+
+def madn_cls_policy_function(s):
+    """policy_function of the dice game's true-env search (classic_madn.py:571-583) -> f32 [n, 4]"""
+    out = np.empty((s.n, 4), np.float32)
+    assert lib().orc_madn_cls_policy_function(*s.cfg.args, *_cls_args(s), _p(out)) == 0
+    return out
+
+
+def madn_cls_root_fn(s, keys):
+    keys = _c(keys, np.uint32)
+    prior, value = np.empty((s.n, 4), np.float32), np.empty(s.n, np.float32)
+    emb = np.empty((s.n, madn_cls_embed_dim(s.cfg)), np.float32)
+    assert lib().orc_madn_cls_root_fn(*s.cfg.args, *_cls_args(s), _p(keys), _p(prior), _p(value), _p(emb)) == 0
+    return prior, value, emb
+
+
+def madn_cls_decision_recurrent_fn(cfg, keys, action, emb):
+    """recurrent_fn (:657-688) -> (chance_logits f32 [n, 6], afterstate_value, afterstate embedding)"""
+    keys, action, emb = _c(keys, np.uint32), _c(action, np.int32), _c(emb, np.float32)
+    n = action.size
+    cl, av, out = np.empty((n, 6), np.float32), np.empty(n, np.float32), np.empty_like(emb)
+    assert lib().orc_madn_cls_decision_recurrent_fn(*cfg.args, C.c_int64(n), _p(keys), _p(action), _p(emb), _p(cl), _p(av), _p(out)) == 0
+    return cl, av, out
+
+
+def madn_cls_chance_recurrent_fn(cfg, keys, outcome, emb):
+    """recurrent_chance_fn (:624-655) -> (action_logits f32 [n, 4], value, reward, discount, embedding)"""
+    keys, outcome, emb = _c(keys, np.uint32), _c(outcome, np.int32), _c(emb, np.float32)
+    n = outcome.size
+    al, v, r, d, out = np.empty((n, 4), np.float32), np.empty(n, np.float32), np.empty(n, np.float32), np.empty(n, np.float32), np.empty_like(emb)
+    assert lib().orc_madn_cls_chance_recurrent_fn(*cfg.args, C.c_int64(n), _p(keys), _p(outcome), _p(emb), _p(al), _p(v), _p(r), _p(d),
+                                                  _p(out)) == 0
+    return al, v, r, d, out
+
+
 def madn_det_step(s, action):
     """in place; returns (reward, done)"""
     action = _c(action, np.int8).reshape(s.n, 2)

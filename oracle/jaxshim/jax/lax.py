@@ -4,8 +4,11 @@ import numpy as _np
 from ._core import wrap
 
 
-def cond(pred, true_fun, false_fun, *operands, operand=None, **kw):
-    if operand is not None and not operands:
+_NO_OPERAND = object()
+
+
+def cond(pred, true_fun, false_fun, *operands, operand=_NO_OPERAND, **kw):
+    if operand is not _NO_OPERAND and not operands:  # jax's legacy keyword: `operand=None` passes None as the one operand
         operands = (operand,)
     return true_fun(*operands) if bool(_np.asarray(pred)) else false_fun(*operands)
 

@@ -808,3 +808,158 @@ int orc_madn_det_recurrent_fn(CFG_ARGS, int64_t n, const uint32_t *keys, const i
   }
   return 0;
 }
+
+
+/* ------------------------------------------------------------------------------------------
+ * True-env mctx callbacks of the dice game — MADN/classic_madn.py:541-714 (winning_action, policy_function, rollout,
+ * root_fn, recurrent_fn = decision node -> afterstate, recurrent_chance_fn = afterstate + die -> state).  SURVEY 8 row b4.
+ * The reference as it stands raises before any of them returns: winning_action (:551-565) builds its scratch copy without the
+ * dataclass's `key` field.  env_step never reads that field; tests/golden/gen_madn_cls_trueenv_goldens.py runs the
+ * reference's own function bodies with that one constructor call made to go through, and this restatement is pinned to
+ * its outputs (tests/golden/madn_cls_reference_trueenv.npz).
+ * emb: board[total], current_player, pins[4 n], reward, done, die, key as four 16-bit halves (k0 lo, k0 hi, k1 lo, k1 hi —
+ * a float32 cannot hold a uint32).  The rollout value is +-1 exactly as in the deterministic game (see above).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int8_t board[64];
+  int8_t cur, reward, die;
+  uint8_t done;
+  int8_t pins[16];
+  uint32_t key[2];
+} cls_env;
+
+static void cls_policy_one(const madn_cfg *c, const cls_env *e, float logits[4]) {
+  uint8_t mask[4];
+  orc_madn_cls_valid_action_one(c, e->board, e->cur, e->pins, e->die, mask);
+  for (int a = 0; a < 4; ++a) {  /* winning_action (:543-569) */
+    cls_env t = *e;
+    orc_madn_cls_step_one(c, t.board, &t.cur, t.pins, &t.reward, &t.done, t.die, a);
+    logits[a] = (mask[a] ? 100.0f : 0.0f) + (t.reward == 1 ? 200.0f : 0.0f);
+  }
+}
+
+static float cls_rollout_one(const madn_cfg *c, const cls_env *e0, const uint32_t key_in[2]) {
+  cls_env e = *e0;
+  uint32_t key[2] = {key_in[0], key_in[1]};
+  for (int steps = 0; !e.done && steps < 300; ++steps) {
+    uint32_t nk[2], sub[2];
+    orc_split_i(key, 0, nk); orc_split_i(key, 1, sub);
+    key[0] = nk[0]; key[1] = nk[1];
+    orc_madn_cls_throw_die_one(c, e.board, e.cur, e.pins, e.key, &e.die);  /* env = throw_die(env): the ENV's key chain */
+    uint8_t mask[4];
+    orc_madn_cls_valid_action_one(c, e.board, e.cur, e.pins, e.die, mask);
+    if (!(mask[0] | mask[1] | mask[2] | mask[3])) { e.cur = (int8_t)fmod_(e.cur + 1, c->n); continue; }  /* no_step (:353-365) */
+    float lg[4];
+    cls_policy_one(c, &e, lg);
+    int best = 0; float bv = 0.f;
+    for (int a = 0; a < 4; ++a) {
+      float u = orc_uniform_i(sub, (uint32_t)a, 1.17549435e-38f, 1.0f);
+      float v = -f_log_d(-f_log_d(u)) + lg[a];
+      if (a == 0 || v > bv) { bv = v; best = a; }
+    }
+    orc_madn_cls_step_one(c, e.board, &e.cur, e.pins, &e.reward, &e.done, e.die, best);
+  }
+  int winner[4];
+  get_winner(c, e.board, winner);
+  return winner[gidx(e0->cur, 4)] ? 1.0f : -1.0f;
+}
+
+static void cls_to_emb(const madn_cfg *c, const cls_env *e, float *f) {
+  int k = 0;
+  for (int i = 0; i < c->total; ++i) f[k++] = e->board[i];
+  f[k++] = e->cur;
+  for (int i = 0; i < c->n * 4; ++i) f[k++] = e->pins[i];
+  f[k++] = e->reward; f[k++] = e->done; f[k++] = e->die;
+  f[k++] = (float)(e->key[0] & 0xFFFFu); f[k++] = (float)(e->key[0] >> 16);
+  f[k++] = (float)(e->key[1] & 0xFFFFu); f[k++] = (float)(e->key[1] >> 16);
+}
+static void cls_from_emb(const madn_cfg *c, cls_env *e, const float *f) {
+  int k = 0;
+  memset(e, 0, sizeof(*e));
+  for (int i = 0; i < c->total; ++i) e->board[i] = (int8_t)f[k++];
+  e->cur = (int8_t)f[k++];
+  for (int i = 0; i < c->n * 4; ++i) e->pins[i] = (int8_t)f[k++];
+  e->reward = (int8_t)f[k++]; e->done = (uint8_t)f[k++]; e->die = (int8_t)f[k++];
+  e->key[0] = (uint32_t)f[k] | ((uint32_t)f[k + 1] << 16);
+  e->key[1] = (uint32_t)f[k + 2] | ((uint32_t)f[k + 3] << 16);
+}
+static void cls_ld(const madn_cfg *c, cls_env *e, int64_t g, const int8_t *board, const int8_t *cur, const int8_t *pins,
+                   const int8_t *reward, const uint8_t *done, const int8_t *die, const uint32_t *key) {
+  memset(e, 0, sizeof(*e));
+  memcpy(e->board, board + g * c->total, c->total);
+  e->cur = cur[g]; e->reward = reward[g]; e->done = done[g]; e->die = die[g];
+  memcpy(e->pins, pins + g * c->n * 4, c->n * 4);
+  e->key[0] = key[2 * g]; e->key[1] = key[2 * g + 1];
+}
+
+int orc_madn_cls_embed_dim(CFG_ARGS) { MAKE_CFG; return cfg.total > 64 ? -1 : cfg.total + 4 * cfg.n + 8; }
+
+#define CLS_LEAVES const int8_t *board, const int8_t *current_player, const int8_t *pins, const int8_t *reward, const uint8_t *done, \
+                   const int8_t *die, const uint32_t *key
+
+/* policy_function (:571-583) -> f32 [n, 4] */
+int orc_madn_cls_policy_function(CFG_ARGS, int64_t n, CLS_LEAVES, float *logits) {
+  MAKE_CFG;
+  if (cfg.total > 64) return -1;
+  for (int64_t g = 0; g < n; ++g) {
+    cls_env e; cls_ld(&cfg, &e, g, board, current_player, pins, reward, done, die, key);
+    cls_policy_one(&cfg, &e, logits + 4 * g);
+  }
+  return 0;
+}
+
+/* root_fn (:690-714) */
+int orc_madn_cls_root_fn(CFG_ARGS, int64_t n, CLS_LEAVES, const uint32_t *keys, float *prior, float *value, float *emb) {
+  MAKE_CFG;
+  if (cfg.total > 64) return -1;
+  const int E = cfg.total + 4 * cfg.n + 8;
+  for (int64_t g = 0; g < n; ++g) {
+    cls_env e; cls_ld(&cfg, &e, g, board, current_player, pins, reward, done, die, key);
+    cls_policy_one(&cfg, &e, prior + 4 * g);
+    value[g] = cls_rollout_one(&cfg, &e, keys + 2 * g);
+    cls_to_emb(&cfg, &e, emb + (int64_t)E * g);
+  }
+  return 0;
+}
+
+/* recurrent_fn (:657-688), the decision node: no_step if nothing is legal, else env_step(action); chance_logits = log(1/6) x 6,
+ * afterstate_value = rollout(afterstate) */
+int orc_madn_cls_decision_recurrent_fn(CFG_ARGS, int64_t n, const uint32_t *keys, const int32_t *action, const float *emb_in,
+                                       float *chance_logits, float *afterstate_value, float *emb_out) {
+  MAKE_CFG;
+  if (cfg.total > 64) return -1;
+  const int E = cfg.total + 4 * cfg.n + 8;
+  const float l6 = f_log_d((float)(1.0 / 6.0));
+  for (int64_t g = 0; g < n; ++g) {
+    cls_env e; cls_from_emb(&cfg, &e, emb_in + (int64_t)E * g);
+    uint8_t mask[4];
+    orc_madn_cls_valid_action_one(&cfg, e.board, e.cur, e.pins, e.die, mask);
+    if (!(mask[0] | mask[1] | mask[2] | mask[3])) e.cur = (int8_t)fmod_(e.cur + 1, cfg.n);
+    else orc_madn_cls_step_one(&cfg, e.board, &e.cur, e.pins, &e.reward, &e.done, e.die, action[g]);
+    for (int k = 0; k < 6; ++k) chance_logits[6 * g + k] = l6;
+    afterstate_value[g] = cls_rollout_one(&cfg, &e, keys + 2 * g);
+    cls_to_emb(&cfg, &e, emb_out + (int64_t)E * g);
+  }
+  return 0;
+}
+
+/* recurrent_chance_fn (:624-655): set_die(afterstate, outcome + 1); action_logits = valid_action as 0 / 1, value = rollout,
+ * reward = env.reward, discount = done ? 0 : 1 */
+int orc_madn_cls_chance_recurrent_fn(CFG_ARGS, int64_t n, const uint32_t *keys, const int32_t *outcome, const float *emb_in,
+                                     float *action_logits, float *value, float *reward, float *discount, float *emb_out) {
+  MAKE_CFG;
+  if (cfg.total > 64) return -1;
+  const int E = cfg.total + 4 * cfg.n + 8;
+  for (int64_t g = 0; g < n; ++g) {
+    cls_env e; cls_from_emb(&cfg, &e, emb_in + (int64_t)E * g);
+    e.die = (int8_t)(outcome[g] + 1);
+    uint8_t mask[4];
+    orc_madn_cls_valid_action_one(&cfg, e.board, e.cur, e.pins, e.die, mask);
+    for (int a = 0; a < 4; ++a) action_logits[4 * g + a] = mask[a] ? 1.0f : 0.0f;
+    value[g] = cls_rollout_one(&cfg, &e, keys + 2 * g);
+    reward[g] = (float)e.reward;
+    discount[g] = e.done ? 0.0f : 1.0f;
+    cls_to_emb(&cfg, &e, emb_out + (int64_t)E * g);
+  }
+  return 0;
+}

@@ -23,7 +23,7 @@ def test_generated_files_are_up_to_date_and_cover_the_header():
     with_stream = [n for n, params in protos if any(p == ("void*", "stream") for p in params)]
     assert sorted(h["name"] for h in handlers) == sorted(with_stream) and len(handlers) >= 50
     host_only = sorted(set(n for n, _ in protos) - set(with_stream))
-    assert host_only == ["dogstep_dog_num_actions", "dogstep_dog_obs_planes", "dogstep_host_key_chain", "dogstep_host_split", "dogstep_madn_det_embed_dim",
+    assert host_only == ["dogstep_dog_num_actions", "dogstep_dog_obs_planes", "dogstep_host_key_chain", "dogstep_host_split", "dogstep_madn_cls_embed_dim", "dogstep_madn_det_embed_dim",
                          "dogstep_mcts_is_sparse", "dogstep_version"]
 
 
@@ -124,5 +124,5 @@ def test_plugin_table_matches_the_ctypes_mirror():
             if f.endswith(".py") and f != "jax_plugin.py":
                 used |= set(re.findall(r"\.(dogstep_[a-z0-9_]+)\b", open(os.path.join(dirpath, f)).read()))
     used -= {"dogstep_last_error", "dogstep_host_split", "dogstep_host_key_chain", "dogstep_mcts_is_sparse", "dogstep_dog_num_actions", "dogstep_dog_obs_planes",
-             "dogstep_madn_det_embed_dim"}
+             "dogstep_madn_det_embed_dim", "dogstep_madn_cls_embed_dim"}
     assert used and used <= set(jax_plugin.TABLE), sorted(used - set(jax_plugin.TABLE))
