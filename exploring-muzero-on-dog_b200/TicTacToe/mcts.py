@@ -93,7 +93,9 @@ def play_mcts_games(n, rng_key, num_simulations=50, limit=30, variant=1, device=
     key = rng_key
     for step in range(limit):
         live = ~env.raw("done")
-        if not bool(live.any()):
+        # the termination test is a host round trip: every fourth ply (a ply on a finished batch changes nothing — finished
+        # games are not stepped and not counted)
+        if step % 4 == 0 and not bool(live.any()):
             break
         key, sub = jaxrand.split_host(key)                            # rng_key, action_key = split(rng_key)
         kw = {"fused": fused} if fused is not None else ({} if graph_cache is None else {"graph_cache": graph_cache})
