@@ -2,7 +2,9 @@
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from exploring_muzero_on_dog_b200 import jaxrand, mcts
+from exploring_muzero_on_dog_b200 import jaxrand, mcts, _lib
+if os.environ.get("DOGSTEP_LIB"):
+    _lib.LIB_PATH = os.environ["DOGSTEP_LIB"]  # a variant build (scripts/microbench)
 shape = sys.argv[1] if len(sys.argv) > 1 else "cfg3"
 dev = torch.device("cuda")
 g = torch.Generator(device=dev).manual_seed(0)
