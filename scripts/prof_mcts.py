@@ -47,3 +47,10 @@ for rep in range(3):
     torch.cuda.synchronize()
     tot = ev[0].elapsed_time(ev[-1])
     print(f"{shape} n={n} S={S} A'={A+Cn} fused={int(fused)}: total {tot:.2f} ms -> {n*S/tot/1e3:.2f} M sims/s (tree kernels only)")
+if os.environ.get("DOGSTEP_LIB") and hasattr(_lib.lib(), "dogstep_trace_wide_decided"):
+    import ctypes
+    c3 = (ctypes.c_ulonglong * 3)()
+    _lib.lib().dogstep_trace_wide_decided(c3)
+    tot = max(1, sum(c3))
+    print(f"wide interior levels: decided from bounds {c3[1] / tot:.3f}, exact evaluation {c3[0] / tot:.3f}, two near-maximal children {c3[2] / tot:.3f} (of {tot})")
+
