@@ -27,6 +27,7 @@ ChanceRecurrentFnOutput = namedtuple("ChanceRecurrentFnOutput", ["action_logits"
 SearchSummary = namedtuple("SearchSummary", ["visit_counts", "visit_probs", "value", "qvalues"])
 
 MUZERO, GUMBEL, STOCHASTIC = 0, 1, 2
+AUX_WORDS = 52  # words per node of dogstep_mcts_tree.select_aux (include/dogstep.h)
 
 
 class _QT:
@@ -77,7 +78,7 @@ class Tree:
         self.search_key, self.policy_key = e((n, 2), dtype=torch.uint32), e((n, 2), dtype=torch.uint32)
         self.path = torch.zeros((n, 65), dtype=i32, device=device)  # descent scratch for the parallel backup
         # per-node select cache of the wide Gumbel path (DOG's 806 actions): 144 B per node
-        self.select_aux = (torch.zeros((n, N + 1, 36), dtype=torch.uint32, device=device)
+        self.select_aux = (torch.zeros((n, N + 1, AUX_WORDS), dtype=torch.uint32, device=device)
                            if policy == GUMBEL and num_chance == 0 and 32 < A <= 832 else None)
         # stochastic: the two action indices the callbacks are evaluated with, written by select (no clamp launches per simulation)
         self.select_action_decision = e((n,), dtype=i32) if policy == STOCHASTIC else None

@@ -299,10 +299,12 @@ typedef struct {
   int32_t* path;                  /* [n, 65] optional scratch (NULL allowed): select records the descent (edge count, then
                                    * (node, action) for the first 32 edges) and expand uses it to fetch every level of the
                                    * backup at once instead of walking parent pointers; results are identical */
-  uint32_t* select_aux;           /* [n, N + 1, 36] optional scratch (NULL allowed): per-node select cache for wide Gumbel trees
+  uint32_t* select_aux;           /* [n, N + 1, 52] optional scratch (NULL allowed): per-node select cache for wide Gumbel trees
                                    * (32 < A' <= 832, completed_by_mix_value; DOG's 806 actions) — bitmap of the children with
-                                   * visits, their visit sum / maximum, and the node's prior softmax statistics — so that a
-                                   * level reads the prior row plus the few visited children instead of five dense rows.
+                                   * visits, their visit sum / maximum, the node's prior softmax statistics and its eight
+                                   * largest prior logits with their indices — so that a level reads the few visited children
+                                   * (and the prior row only when its decision cannot be proven without it) instead of five
+                                   * dense rows.
                                    * Written by init / expand, read by select; results are identical with and without it.
                                    * If given, every call on this tree (init, select, expand, expand_select) must get it. */
   int32_t* select_action_decision; /* [n] optional output of select (stochastic): min(action, A - 1), the index the

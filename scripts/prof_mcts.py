@@ -49,8 +49,9 @@ for rep in range(3):
     print(f"{shape} n={n} S={S} A'={A+Cn} fused={int(fused)}: total {tot:.2f} ms -> {n*S/tot/1e3:.2f} M sims/s (tree kernels only)")
 if os.environ.get("DOGSTEP_LIB") and hasattr(_lib.lib(), "dogstep_trace_wide_decided"):
     import ctypes
-    c3 = (ctypes.c_ulonglong * 3)()
+    c3 = (ctypes.c_ulonglong * 5)()
     _lib.lib().dogstep_trace_wide_decided(c3)
-    tot = max(1, sum(c3))
-    print(f"wide interior levels: decided from bounds {c3[1] / tot:.3f}, exact evaluation {c3[0] / tot:.3f}, two near-maximal children {c3[2] / tot:.3f} (of {tot})")
+    tot = max(1, c3[3] + c3[4])
+    print(f"wide interior levels: decided without the row {c3[3] / tot:.3f}; with the row: from bounds {c3[1] / tot:.3f}, exact evaluation "
+          f"{c3[0] / tot:.3f}, two near-maximal children {c3[2] / tot:.3f} (of {tot})")
 

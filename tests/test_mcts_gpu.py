@@ -371,7 +371,7 @@ def test_wide_select_cache_is_consistent_at_scale():
         step(sim, rnd(n, A) * 2, torch.tanh(rnd(n)), 0.1 * rnd(n), torch.where(rnd(n) > 0, 1.0, -1.0), rnd(n, E))
     t = srch.tree
     vc = t.children_visits                                            # [n, N, A]
-    aux = t.select_aux.view(torch.int32)                              # [n, N + 1, 36]
+    aux = t.select_aux.view(torch.int32)                              # [n, N + 1, 52]
     N = S + 1
     assert (vc[:, 0].sum(1) == S).all() and (vc[:, 0][invalid] == 0).all()
     assert (t.node_visits[:, 1:] >= 1).all() and (t.node_visits[:, 0] == S + 1).all()
@@ -388,6 +388,17 @@ def test_wide_select_cache_is_consistent_at_scale():
     s1 = aux[:, :N, 33].view(torch.float32)
     assert torch.equal(m1, lg.max(2).values)
     assert torch.allclose(s1, torch.exp(lg.double() - m1.double().unsqueeze(2)).sum(2).float(), rtol=1e-5)
+    # the eight largest prior logits of every expanded node, descending, ties by index; a list may end early (index -1), never lie
+    created = t.node_visits > 0
+    top_v = aux[:, :N, 36:44].view(torch.float32)
+    top_i = aux[:, :N, 44:52].to(torch.int64)
+    srt = torch.sort(lg, dim=2, descending=True, stable=True)
+    known = top_i >= 0
+    assert known[created][:, :2].all()                                    # every lane gives two: the first two are always known
+    assert torch.equal(torch.where(known, top_i, srt.indices[:, :, :8])[created], srt.indices[:, :, :8][created])
+    assert torch.equal(torch.where(known, top_v, srt.values[:, :, :8])[created], srt.values[:, :, :8][created])
+    assert (known[:, :, :-1] | ~known[:, :, 1:])[created].all()           # unknown entries only at the tail
+    assert known[created].float().mean() > 0.8
     # root_invalid bitmap and valid count in the extra slot
     rwords = aux[:, N, :32].to(torch.int64) & 0xFFFFFFFF
     rbit = (rwords[:, a % 32] >> (a // 32)) & 1
