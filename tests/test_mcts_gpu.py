@@ -394,11 +394,11 @@ def test_wide_select_cache_is_consistent_at_scale():
     top_i = aux[:, :N, 44:52].to(torch.int64)
     srt = torch.sort(lg, dim=2, descending=True, stable=True)
     known = top_i >= 0
-    assert known[created][:, :2].all()                                    # every lane gives two: the first two are always known
+    assert known[created][:, :3].all()                                    # every lane ranks three: the first three are always known
     assert torch.equal(torch.where(known, top_i, srt.indices[:, :, :8])[created], srt.indices[:, :, :8][created])
     assert torch.equal(torch.where(known, top_v, srt.values[:, :, :8])[created], srt.values[:, :, :8][created])
     assert (known[:, :, :-1] | ~known[:, :, 1:])[created].all()           # unknown entries only at the tail
-    assert known[created].float().mean() > 0.8
+    assert known[created].float().mean() > 0.95
     # root_invalid bitmap and valid count in the extra slot
     rwords = aux[:, N, :32].to(torch.int64) & 0xFFFFFFFF
     rbit = (rwords[:, a % 32] >> (a // 32)) & 1
