@@ -67,6 +67,10 @@ CASES = [
     (0, 2, 806, 0, 30, 8),
     (1, 2, 806, 0, 100, 50, "ties"),   # quantised priors and values: exact ties everywhere (argmax keeps the FIRST maximum)
     (1, 2, 100, 0, 60, 50, "ties"),
+    (1, 2, 806, 0, 100, 50, "peaked"),  # network-like rows: a few actions hold nearly all of the prior mass (the visited children
+                                        # then carry > 90 % of it: the cancellation guard of the row-free level)
+    (1, 2, 806, 0, 100, 50, "large"),   # logits beyond +-100: the magnitude guards send every level to the exact evaluation
+    (1, 2, 806, 0, 100, 50, "flat"),    # nearly equal logits (1e-4 apart): two near-maximal children at every level
     (1, 2, 33, 0, 40, 50),             # the narrowest wide tree
     (1, 2, 832, 0, 20, 50),            # the widest register-path tree
 ]
@@ -76,7 +80,8 @@ CASES = [
 def test_cuda_search_equals_oracle(case):
     from exploring_muzero_on_dog_b200 import mcts
     policy, qt, A, Cn, S, depth = case[:6]
-    ties = len(case) > 6
+    ties = len(case) > 6 and case[6] == "ties"
+    shape = case[6] if len(case) > 6 else ""
     n, E = 96, 16
     ccfg, ocfg = _mk_cfgs(policy, qt, S, depth, A, Cn, E)
     rng = np.random.default_rng(1000 * policy + A)
@@ -91,6 +96,22 @@ def test_cuda_search_equals_oracle(case):
     invalid[:4] = 0
     noise = rng.dirichlet(np.full(A, 0.3), n).astype(np.float32)
     net = Net(A, Cn, E, 7, quantize=ties)
+    if shape in ("peaked", "large", "flat"):  # reshape every prior row the search sees, the root's and the network's
+        def reshape_np(p, r):
+            if shape == "peaked":
+                p = p * 3.0
+                p[np.arange(p.shape[0])[:, None], r.integers(0, A, (p.shape[0], 3))] += 22.0
+                return p.astype(np.float32)
+            if shape == "large":
+                return (p * 70.0).astype(np.float32)
+            return (np.round(p * 4) * 1e-4 + 3.0).astype(np.float32)
+        prior = reshape_np(prior, rng)
+        base_net = net
+
+        def net(action, pemb, _r=np.random.default_rng(77)):
+            o = base_net(action, pemb)
+            o["prior"] = torch.as_tensor(reshape_np(o["prior"].float().cpu().numpy(), _r), device="cuda")
+            return o
 
     s = mcts.Search(ccfg, n)
     dev = lambda x: torch.as_tensor(x, device="cuda")
