@@ -51,3 +51,43 @@ def test_choice6_distribution():
     for _ in range(6000):
         cnt[O.choice6(rng.integers(0, 2**32, 2, dtype=np.uint64).astype(np.uint32), p)] += 1
     assert cnt.min() > 800
+
+
+def test_reference_notebook_known_answers():
+    """Known answers recorded by the reference itself: MADN/jupyter_code/test_functions.ipynb cell 1 prints, for step(env, s)
+    with s = 1, 2, 3 on states whose dice_probabilities are uniform, "Die throw: 4 / 1 / 6" and, for s = 3 with four valid
+    actions, "Chosen action: 2".  step (MADN/simulate_classicMADN.py:112-141) draws
+        rng_key, sub = split(PRNGKey(s));  die = choice(sub, [1..6], p)          (classic_madn.py:238-242)
+        rng_key, sub = split(rng_key);     idx = randint(sub, (), 0, N)           (:136-137)
+    so these four values pin split + choice(p) + randint of the restatement (and of the shim the goldens were made on)
+    to real jax.random output."""
+    p = np.full(6, 1 / 6, np.float32)
+    recorded = {1: 4, 2: 1, 3: 6}
+    for s, die in recorded.items():
+        k1, sub = O.split(O.prng_key(s))
+        assert O.choice6(sub, p) + 1 == die
+        _, sub2 = O.split(k1)
+        assert int(O.randint(sub2, 1, 0, 1)[0]) == 0  # N = 1 rows of the same printout
+    _, sub2 = O.split(O.split(O.prng_key(3))[0])
+    assert int(O.randint(sub2, 1, 0, 4)[0]) == 2
+
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "oracle", "jaxshim"))
+    try:
+        for m in [m for m in sys.modules if m == "jax" or m.startswith("jax.")]:
+            del sys.modules[m]
+        import jax
+        import jax.numpy as jnp
+
+        faces = jnp.array([1, 2, 3, 4, 5, 6], dtype=jnp.int8)
+        for s, die in recorded.items():
+            k1, sub = jax.random.split(jax.random.PRNGKey(s))
+            assert int(jax.random.choice(sub, faces, p=jnp.ones(6) / 6)) == die
+        _, sub2 = jax.random.split(jax.random.split(jax.random.PRNGKey(3))[0])
+        assert int(jax.random.randint(sub2, (), 0, 4)) == 2
+    finally:
+        sys.path.pop(0)
+        for m in [m for m in sys.modules if m == "jax" or m.startswith("jax.")]:
+            del sys.modules[m]
