@@ -5,10 +5,12 @@ lockstep iteration and live game, the seat to move is played by its agent type (
 2 rule based :780-878, else tree search — supplied by the caller), no legal action -> no_step, winners accumulate
 manual_get_winner (:16-45) when a game ends.
 
-PARITY STATUS: the env functions underneath are pinned (madn_oracle.c).  do_rule_based is restated array expression by
-array expression (float32, same association); jax.random.categorical's float Gumbel uses -log(-log(u)) with each log
-rounded once from libm's double log, which is this repo's float contract and is NOT pinned against XLA's float32 log
-("parity unpinned": no reference test exercises this function, and JAX is not installable here).
+PARITY STATUS: pinned since round 2 by the reference's own play_eval_loop_jitted run on oracle/jaxshim
+(tests/golden/loops_reference.npz, tests/test_golden_loops.py: winners and every final leaf of random and rule-based seats,
+20 games per run to termination); the env functions underneath are pinned by madn_oracle.c's goldens.  do_rule_based is
+restated array expression by array expression (float32, same association).  One caveat: jax.random.categorical's float
+Gumbel uses -log(-log(u)) with each log rounded once from a double log — this repo's float contract, the same on
+the shim, here and on the GPU; XLA's own float32 log may differ by 1 ulp, which matters only on an exact near-tie.
 
 Note for maintainers: do_rule_based builds its candidate cells from `actions = jnp.arange(6)` (distances 0..5) while action
 (pin, k) plays move k + 1 (map_action), so every bonus is evaluated one cell short.  Restated literally — the code is the

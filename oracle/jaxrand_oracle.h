@@ -9,9 +9,12 @@
  * this image (uv.lock pins jax 0.8.1); this follows its published algorithm
  * (Random123 Threefry-2x32-20 + jax/_src/prng.py, jax/_src/random.py).
  *
- * PARITY STATUS: threefry2x32 is pinned by the three Random123 known-answer vectors
- * (tests/test_oracle_threefry.py).  split/uniform/randint/choice/gumbel follow the
- * published jax source from memory: "parity unpinned" versus a live jax 0.8.1.
+ * PARITY STATUS (tests/test_oracle_threefry.py): threefry2x32 is pinned by the three Random123 known-answer vectors;
+ * split / uniform by the values printed in JAX's documentation for PRNGKey(0) and PRNGKey(42); split + choice(p) + randint by
+ * outputs the reference itself recorded (MADN/jupyter_code/test_functions.ipynb cell 1: die throws 4, 1, 6 for
+ * split(PRNGKey(1|2|3))[1] under the uniform distribution, and randint(…, 0, 4) == 2 on the next split of PRNGKey(3)).
+ * gumbel / categorical follow the published jax source (argmax of logits - log(-log(uniform))) and have no recorded
+ * output to compare with: "parity unpinned" for those two versus a live jax 0.8.1.
  */
 #ifndef JAXRAND_ORACLE_H
 #define JAXRAND_ORACLE_H

@@ -5,8 +5,10 @@ MuZero_Classic_MADN/game_agent_stochastic.py:52-218) on top of the C env oracle:
 encode / mask / (search result supplied by the caller) / env_step or no_step / reward+discount class targets / the
 trajectory row.  The search itself is an input (`search_fn`), exactly as in the CUDA mirror.
 
-PARITY STATUS: the env functions underneath are pinned (see madn_oracle.c); the loop bookkeeping itself is pinned by no
-reference test ("parity unpinned"), it is a line-by-line restatement of the cited lines.
+PARITY STATUS: pinned since round 2 by the reference's own play_batch_of_games_jitted (both game agents) run on
+oracle/jaxshim with the search replaced by a deterministic stand-in (tests/golden/loops_reference.npz,
+tests/test_golden_loops.py: every trajectory buffer of 2 x 2 runs, incl. games that end inside the recording); the env
+functions underneath are pinned by madn_oracle.c's goldens.
 """
 import numpy as np
 
