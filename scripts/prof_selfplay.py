@@ -42,6 +42,14 @@ def main():
     print(f"{which}: {iters} iterations, {total / 1e3 / iters:.3f} ms of kernel time per iteration, libdogstep kernels {100 * own / total:.1f} %")
     for name, us in tot.most_common(25):
         print(f"{us / iters:10.1f} us/iter  {cnt[name] / iters:7.1f} launches/iter  {name[:110]}")
+    from exploring_muzero_on_dog_b200 import _lib
+    if os.environ.get("DOGSTEP_LIB") and hasattr(_lib.lib(), "dogstep_trace_wide_decided"):  # instrumented build only
+        import ctypes
+        c = (ctypes.c_ulonglong * 5)()
+        _lib.lib().dogstep_trace_wide_decided(c)
+        tot_l = max(1, c[3] + c[4])
+        print(f"wide interior levels since start: decided without the row {c[3] / tot_l:.3f}; with the row: from bounds {c[1] / tot_l:.3f}, "
+              f"exact evaluation {c[0] / tot_l:.3f}, two near-maximal children {c[2] / tot_l:.3f} (of {tot_l})")
 
 
 if __name__ == "__main__":

@@ -166,11 +166,15 @@ def test_run_mcts_search_on_the_true_env():
 @pytest.mark.gpu
 def test_throw_die_matches_the_die_values_the_reference_printed():
     """MADN/jupyter_code/test_functions.ipynb cell 1 (output committed with the reference): choice(split(PRNGKey(s))[1],
-    [1..6], p = uniform) is 4, 1, 6 for s = 1, 2, 3 — the same draw throw_die (classic_madn.py:230-242) makes from a freshly
-    reset env whose key is PRNGKey(seed) (see tests/test_oracle_threefry.py for the CPU side of this known answer)."""
+    [1..6], p = uniform) is 4, 1, 6 for s = 1, 2, 3 — the draw throw_die (classic_madn.py:230-242) makes from an env whose key
+    is PRNGKey(s) (see tests/test_oracle_threefry.py for the CPU side of this known answer)."""
+    from exploring_muzero_on_dog_b200 import jaxrand
     from exploring_muzero_on_dog_b200.MADN import classic_madn as cm
+    keys = np.stack([np.asarray(jaxrand.PRNGKey(s), np.uint32) for s in (1, 2, 3)])
     for players in (2, 3, 4):
         env = cm.env_reset(0, num_players=players, distance=10, seed=np.array([1, 2, 3], np.int32), enable_dice_rethrow=True,
                            enable_initial_free_pin=True)
+        env = env.replace(key=keys)
         env = cm.throw_die(env)
         assert env.die.cpu().tolist() == [4, 1, 6]
+        assert np.array_equal(env.numpy()["key"], np.stack([jaxrand.split_host(k)[0] for k in keys]))
