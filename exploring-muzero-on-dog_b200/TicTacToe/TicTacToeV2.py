@@ -55,6 +55,18 @@ def env_step(env, action, inplace=False):
     return env, (reward if env.batched else reward[0]), (done if env.batched else done[0])
 
 
+def play_move(env, action_weights, plies=None):
+    """One ply of the reference's match loops, in place (TicTacToe/eval.py:97-125, :151-176): every game that is not done plays
+    get_mcts_action (:28-34) = argmax(where(board == 0, action_weights, -inf)) through env_step; finished games are left
+    untouched.  Returns the moves (int8 [n], -1 for a finished game); `plies` (int32 [n]) counts the games that moved."""
+    w = to_dev(action_weights, torch.float32, env.device).reshape(env.n, 9)
+    action = torch.empty(env.n, dtype=torch.int8, device=env.device)
+    st = env.cstate()
+    _lib.check(_lib.lib().dogstep_ttt_play_move(C.byref(st), C.c_int64(env.n), _v(env), _lib.ptr(w), _lib.ptr(action),
+                                               None if plies is None else _lib.ptr(plies), _lib.stream()), "ttt_play_move")
+    return action
+
+
 def valid_action_mask(env):
     """valid_action_mask (:81-82) -> bool [n,3,3]"""
     m = torch.empty((env.n, 9), dtype=torch.uint8, device=env.device)

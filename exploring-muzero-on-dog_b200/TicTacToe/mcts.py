@@ -85,24 +85,54 @@ def run_gumbel(rng_key, env, num_simulations, graph_cache=None, fused=None):
                                       qtransform=_QT, graph_cache=graph_cache)
 
 
-def play_mcts_games(n, rng_key, num_simulations=50, limit=30, variant=1, device="cuda", search=run_mcts, graph_cache=None, fused=None):
-    """BASELINE config 1: n lockstep games, both sides pick run_mcts(...).action every ply, until all are done or `limit`
-    plies (TicTacToe/eval.py:97-125 with get_mcts_action on both seats).  Returns (env, plies played per game)."""
+def play_mcts_games(n, rng_key, num_simulations=50, limit=30, variant=1, device="cuda", search=run_mcts, graph_cache=None, fused=None,
+                    move="weights"):
+    """BASELINE config 1: n lockstep games, both seats searched every ply, until all are done or `limit` plies — the
+    reference's play_mcts_match (TicTacToe/eval.py:151-176).  move = "weights": the reference's get_mcts_action (:28-34),
+    the largest action weight among the empty cells; "sample": PolicyOutput.action.  Returns (env, plies played per game)."""
     env = game.env_reset(0, n=n, device=device, variant=variant)
     plies = torch.zeros(n, dtype=torch.int32, device=device)
     key = rng_key
     for step in range(limit):
-        live = ~env.raw("done")
         # the termination test is a host round trip: every fourth ply (a ply on a finished batch changes nothing — finished
         # games are not stepped and not counted)
-        if step % 4 == 0 and not bool(live.any()):
+        if step % 4 == 0 and bool(env.raw("done").all()):
             break
         key, sub = jaxrand.split_host(key)                            # rng_key, action_key = split(rng_key)
         kw = {"fused": fused} if fused is not None else ({} if graph_cache is None else {"graph_cache": graph_cache})
         out = search(jaxrand.split(sub, n, device=device), env, num_simulations, **kw)
+        if move == "weights":
+            game.play_move(env, out.action_weights, plies)           # one launch: pick + env_step of the live games, in place
+            continue
+        live = ~env.raw("done")
         stepped, _, _ = game.env_step(env, out.action.to(torch.int8))
         merged = {k: torch.where(live.reshape((-1,) + (1,) * (stepped.raw(k).ndim - 1)), stepped.raw(k), env.raw(k))
                   for k in ("board", "current_player", "reward", "done", "memory")}
         env = env.replace(**merged)
         plies += live.to(torch.int32)
     return env, plies
+
+
+def play_match(n, rng_key, num_simulations, bot_player=1, limit=30, variant=1, device="cuda", search=run_mcts, fused=None):
+    """n lockstep games of the search bot (seat `bot_player`, +1 moves first) against the random bot — the reference's test /
+    play_match with a search player (TicTacToe/eval.py:97-125, :252-275; get_random_action :51-55 = categorical over the
+    empty cells with the ply's action key).  Returns (env, result per game: +1 the bot won, -1 it lost, 0 draw or limit)."""
+    env = game.env_reset(0, n=n, device=device, variant=variant)
+    key = rng_key
+    for step in range(limit):
+        if step % 4 == 0 and bool(env.raw("done").all()):
+            break
+        key, sub = jaxrand.split_host(key)
+        if (1 if step % 2 == 0 else -1) == bot_player:                # seats alternate every ply in both variants
+            weights = search(jaxrand.split(sub, n, device=device), env, num_simulations,
+                             **({"fused": fused} if fused is not None else {})).action_weights
+        else:
+            # categorical(key, where(empty, 0, -inf)) over the batch: the empty cell with the largest Gumbel draw, i.e. with
+            # the largest of the uniform draws behind it
+            weights = jaxrand.uniform(sub, 9 * n, device=device).reshape(n, 9)
+        game.play_move(env, weights)
+    board = env.raw("board").reshape(n, 9).to(torch.int32)
+    lines = torch.tensor([[0, 1, 2], [3, 4, 5], [6, 7, 8], [0, 3, 6], [1, 4, 7], [2, 5, 8], [0, 4, 8], [2, 4, 6]], device=board.device)
+    sums = board[:, lines].sum(2)
+    winner = (sums == 3).any(1).to(torch.int32) - (sums == -3).any(1).to(torch.int32)   # get_winner
+    return env, torch.where(env.raw("done"), winner * bot_player, torch.zeros_like(winner))

@@ -97,6 +97,30 @@ static int ttt_ptrs(const dogstep_ttt_state* s, TttPtrs* p) {
   return DOGSTEP_OK;
 }
 static inline unsigned tb(int64_t n) { return (unsigned)((n + 127) / 128); }
+// One ply of the reference's match loops (TicTacToe/eval.py:97-125 play_match, :151-176 play_mcts_match): a game that is not
+// done plays get_mcts_action (:28-34) — the first largest action weight among the empty cells, argmax(where(board == 0,
+// action_weights, -inf)) — through env_step; a finished game is left alone (the reference's `while not env.done`).
+__global__ void k_ttt_play_move(TttPtrs p, int64_t n, int variant, const float* __restrict__ weights, int8_t* __restrict__ action,
+                                int32_t* __restrict__ plies) {
+  int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  Ttt e;
+  ttt_load(p, g, e);
+  if (e.done) {
+    if (action) action[g] = -1;
+    return;
+  }
+  int a = 0;
+  float best = -INFINITY;
+  for (int c = 0; c < 9; ++c) {
+    const float x = e.board[c] == 0 ? weights[9 * g + c] : -INFINITY;
+    if (x > best) { best = x; a = c; }
+  }
+  ttt_step(variant, e, (int8_t)a);
+  ttt_store(p, g, e);
+  if (action) action[g] = (int8_t)a;
+  if (plies) plies[g] += 1;
+}
 static inline unsigned tb16(int64_t n) { return (unsigned)((16 * n + 127) / 128); }  // 16 lanes per game
 
 }  // namespace dogstep
@@ -120,6 +144,15 @@ int dogstep_ttt_step(const dogstep_ttt_state* s, int64_t n, int32_t variant, con
   if (int rc = ttt_ptrs(s, &p)) return rc;
   if (n == 0) return DOGSTEP_OK;
   k_ttt_step<<<tb(n), 128, 0, (cudaStream_t)stream>>>(p, n, variant, action, reward, done);
+  return check_launch();
+}
+int dogstep_ttt_play_move(const dogstep_ttt_state* s, int64_t n, int32_t variant, const float* action_weights, int8_t* action,
+                          int32_t* plies, void* stream) {
+  TttPtrs p;
+  if (n < 0 || !action_weights || variant < 0 || variant > 1) return DOGSTEP_ERR_INVALID_ARG;
+  if (int rc = ttt_ptrs(s, &p)) return rc;
+  if (n == 0) return DOGSTEP_OK;
+  k_ttt_play_move<<<tb(n), 128, 0, (cudaStream_t)stream>>>(p, n, variant, action_weights, action, plies);
   return check_launch();
 }
 int dogstep_ttt_policy_function(const dogstep_ttt_state* s, int64_t n, int32_t variant, float* logits, uint8_t* valid_mask,

@@ -493,6 +493,12 @@ int dogstep_ttt_reset(const dogstep_ttt_state* s, int64_t n, void* stream);
 /* env_step — TicTacToe.py:42-59 / TicTacToeV2.py:46-79.  action int8 [n] */
 int dogstep_ttt_step(const dogstep_ttt_state* s, int64_t n, int32_t variant, const int8_t* action, int8_t* reward, uint8_t* done,
                      void* stream);
+/* One ply of play_match / play_mcts_match — TicTacToe/eval.py:97-125, :151-176 with get_mcts_action :28-34: every game that
+ * is not done plays argmax(where(board == 0, action_weights, -inf)) (first maximum) through env_step, in place; finished
+ * games are left untouched.  action_weights f32 [n,9] (PolicyOutput.action_weights); action i8 [n] or NULL receives the move
+ * (-1 for a finished game); plies i32 [n] or NULL is incremented for every game that moved */
+int dogstep_ttt_play_move(const dogstep_ttt_state* s, int64_t n, int32_t variant, const float* action_weights, int8_t* action,
+                          int32_t* plies, void* stream);
 /* policy_function (:96-102) -> logits f32 [n,9] and/or valid_action_mask (:81-82) -> u8 [n,9]; either may be NULL */
 int dogstep_ttt_policy_function(const dogstep_ttt_state* s, int64_t n, int32_t variant, float* logits, uint8_t* valid_mask,
                                 void* stream);

@@ -11,9 +11,14 @@
  * muzero_action_selection (PUCT + 1e-7 uniform tie-break), gumbel root (sequential halving) / interior
  * selection, stochastic decision/chance wrapper, the three qtransforms, and the policy epilogues.
  *
- * PARITY STATUS: **parity unpinned** — the reference holds no test or golden vector for any MCTS result and
+ * PARITY STATUS: **bit-level parity unpinned** — the reference holds no test or golden vector for any MCTS result and
  * mctx cannot be run here.  This file is an independent scalar statement of the same algorithm that the CUDA
  * kernels are compared against bit-for-bit (visit counts exact, values bit-equal) on identical network outputs.
+ * STATISTICALLY pinned by what the reference measured with mctx itself (TicTacToe/results.md:12-15, :53-68): with the
+ * true-env callbacks of ttt_oracle.c, muzero_policy and gumbel_muzero_policy here reproduce the recorded win / loss / tie
+ * rates against a random bot (5 / 10 / 30 / 100 simulations) and the recorded first-player / second-player / draw shares of
+ * search-vs-search play (e.g. 100 simulations: 64.1 / 20.3 / 15.6 % recorded, 65.6 / 20.9 / 13.5 % here, 1,000 games each)
+ * within sampling error — tests/test_ttt.py.
  *
  * Float contract shared with the kernels: no FMA contraction (-ffp-contract=off), exp/log rounded from double,
  * sums in the fixed order  partial[l] = x[l] + x[l+32] + ... ; then butterfly over l^16, l^8, l^4, l^2, l^1.

@@ -279,34 +279,92 @@ def test_oracle_mcts_bot_plays_as_strongly_as_the_reference_measured(policy, sim
 @pytest.mark.gpu
 @pytest.mark.parametrize("search_name", ["run_mcts", "run_gumbel"])
 def test_cuda_mcts_bot_plays_as_strongly_as_the_reference_measured(search_name):
-    """the same match on the GPU: the fused one-launch search (dogstep_ttt_search) on the bot's seat, 1,000 lockstep games"""
-    import torch
+    """the same match on the GPU (TicTacToe.mcts.play_match): the fused one-launch search on the bot's seat, 1,000 lockstep games"""
     from exploring_muzero_on_dog_b200 import jaxrand
-    from exploring_muzero_on_dog_b200.TicTacToe import TicTacToeV2 as g
     from exploring_muzero_on_dog_b200.TicTacToe import mcts as tm
     search, fused = getattr(tm, search_name), {}
-    gen = torch.Generator(device="cuda").manual_seed(11)
     for S in (5, 10, 30, 100):
         w = l = 0
-        key = jaxrand.PRNGKey(S)
         for seat in (1, -1):
-            n = 500
-            env = g.env_reset(0, n=n, variant=1)
-            for step in range(30):
-                live = ~env.raw("done")
-                if not bool(live.any()):
-                    break
-                key, sub = jaxrand.split_host(key)
-                empty = env.raw("board").reshape(n, 9) == 0
-                if int(env.raw("current_player")[live][0]) == seat:   # lockstep: every live game is at the same ply
-                    weights = search(jaxrand.split(sub, n), env, S, fused=fused).action_weights
-                    action = torch.where(empty, weights, torch.full_like(weights, -float("inf"))).argmax(1)   # eval.py:31-34
-                else:
-                    action = torch.where(empty, torch.rand((n, 9), device="cuda", generator=gen), torch.full((n, 9), -1.0, device="cuda")).argmax(1)
-                stepped, _, _ = g.env_step(env, action.to(torch.int8))
-                env = env.replace(**{k: torch.where(live.reshape((-1,) + (1,) * (stepped.raw(k).ndim - 1)), stepped.raw(k), env.raw(k))
-                                     for k in ("board", "current_player", "reward", "done", "memory")})
-            res = _winner(env.raw("board").cpu().numpy(), env.raw("done").cpu().numpy()) * seat
+            env, res = tm.play_match(500, jaxrand.PRNGKey(10 * S + seat + 1), S, bot_player=seat, search=search, fused=fused)
+            res = res.cpu().numpy()
+            assert np.array_equal(res, _winner(env.raw("board").cpu().numpy(), env.raw("done").cpu().numpy()) * seat)
             w += int((res == 1).sum())
             l += int((res == -1).sum())
         _close_to_reference(S, w / 10, l / 10, (1000 - w - l) / 10)
+
+
+# "TicTacToeV2 results (1000 games mcts vs mcts)" (TicTacToe/results.md:53-68; eval.py:151-176 play_mcts_match): share of games
+# won by the first player, by the second player, drawn — muzero_policy and gumbel_muzero_policy, by number of simulations.
+# Both samples have 1,000 games: one standard deviation of the difference of two such shares is 2.2 points at 50 %, 1.6 at 15 %.
+REF_SELFPLAY = {("run_mcts", 5): (0.48, 0.472, 0.048), ("run_mcts", 10): (0.504, 0.464, 0.032), ("run_mcts", 30): (0.581, 0.407, 0.012),
+                ("run_mcts", 100): (0.641, 0.203, 0.156), ("run_gumbel", 5): (0.52, 0.405, 0.075), ("run_gumbel", 10): (0.547, 0.403, 0.05),
+                ("run_gumbel", 30): (0.522, 0.467, 0.011), ("run_gumbel", 100): (0.577, 0.415, 0.008)}
+
+
+def _close_to_reference_selfplay(name, S, win):
+    ref = REF_SELFPLAY[(name, S)]
+    got = ((win == 1).mean(), (win == -1).mean(), (win == 0).mean())
+    assert abs(got[0] - ref[0]) <= 0.06 and abs(got[1] - ref[1]) <= 0.06 and abs(got[2] - ref[2]) <= 0.045, (name, S, got, ref)
+
+
+@pytest.mark.parametrize("name,S", [("run_mcts", 100), ("run_mcts", 5), ("run_gumbel", 30)])
+def test_oracle_mcts_selfplay_reproduces_the_reference_outcome_shares(name, S):
+    """oracle search on both seats, the move = the largest action weight among the empty cells (eval.py:28-34).  The 100-simulation
+    row is the distinctive one (64 % / 20 % / 16 %): sampling PolicyOutput.action instead gives 60 / 38 / 3."""
+    rng = np.random.default_rng(100 + S)
+    s = O.TttState(500 if S == 100 else 1000, 1)   # the CPU suite's time budget; the GPU test below plays 1,000 of every row
+    for _ in range(30):
+        live = np.flatnonzero(s.done == 0)
+        if live.size == 0:
+            break
+        sub = O.TttState(live.size, 1)
+        for k in s.FIELDS:
+            setattr(sub, k, np.ascontiguousarray(getattr(s, k)[live]))
+        O.ttt_step(sub, _oracle_search_actions(sub, S, 0 if name == "run_mcts" else 1, rng))
+        for k in s.FIELDS:
+            getattr(s, k)[live] = getattr(sub, k)
+    _close_to_reference_selfplay(name, S, _winner(s.board, np.ones(s.n)))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["run_mcts", "run_gumbel"])
+def test_cuda_mcts_selfplay_reproduces_the_reference_outcome_shares(name):
+    """config 1's own loop (play_mcts_games, fused search, 1,000 lockstep games) against every row of the reference's table"""
+    from exploring_muzero_on_dog_b200 import jaxrand
+    from exploring_muzero_on_dog_b200.TicTacToe import mcts as tm
+    fused = {}
+    for S in (5, 10, 30, 100):
+        env, _ = tm.play_mcts_games(1000, jaxrand.PRNGKey(S), num_simulations=S, limit=30, variant=1, search=getattr(tm, name), fused=fused)
+        _close_to_reference_selfplay(name, S, _winner(env.raw("board").cpu().numpy(), np.ones(1000)))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", [0, 1])
+def test_cuda_play_move_equals_masked_argmax_then_step(variant):
+    """dogstep_ttt_play_move == argmax(where(board == 0, w, -inf)) + the oracle's env_step on live games, nothing on finished ones"""
+    import torch
+    from exploring_muzero_on_dog_b200.TicTacToe import TicTacToeV2 as g
+    n = 4096
+    rng = np.random.default_rng(5 + variant)
+    s = O.TttState(n, variant)
+    env = g.env_reset(0, n=n, variant=variant)
+    plies = torch.zeros(n, dtype=torch.int32, device="cuda")
+    expect_plies = np.zeros(n, np.int32)
+    for t in range(12):
+        w = rng.random((n, 9)).astype(np.float32)
+        w[rng.random((n, 9)) < 0.3] = 0.0   # ties: the first maximum wins
+        live = s.done == 0
+        a = np.argmax(np.where(s.board.reshape(n, 9) == 0, w, -np.inf), axis=1)
+        before = s.copy()
+        O.ttt_step(s, a)
+        for k in s.FIELDS:
+            getattr(s, k)[~live] = getattr(before, k)[~live]
+        expect_plies += live
+        got = g.play_move(env, torch.from_numpy(w).cuda(), plies).cpu().numpy()
+        assert np.array_equal(got, np.where(live, a, -1))
+        st = env.numpy()
+        for k in ("board", "current_player", "reward", "memory"):
+            assert np.array_equal(st[k].reshape(getattr(s, k).shape), getattr(s, k)), (t, k)
+        assert np.array_equal(st["done"].astype(np.uint8), s.done)
+    assert np.array_equal(plies.cpu().numpy(), expect_plies) and (s.done != 0).any()
