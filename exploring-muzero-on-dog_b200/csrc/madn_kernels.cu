@@ -287,13 +287,28 @@ __global__ void __launch_bounds__(256) k_madn_encode_board(const __grid_constant
 
 // categorical(key, where(mask, 0, -1e9)) == first valid action with the largest 23-bit uniform
 // mantissa (gumbel = -log(-log(u)) is strictly increasing in u; see DESIGN.md "random policy").
+// Four legal actions per pass: the four Threefry evaluations are independent instruction streams, so a thread that owns a whole
+// game (the per-call kernels: 14 warps per SM, bound by the latency of the longest chain of any warp) waits for ceil(legal / 4)
+// evaluations instead of `legal` of them.  Actions are visited in ascending order, a later one wins only with a strictly larger
+// mantissa: the first maximum, as jnp.argmax.
 __device__ __forceinline__ int categorical_masked(Key2 key, uint32_t mask) {
   int best = -1;
   uint32_t bm = 0;
-  for (uint32_t m = mask; m; m &= m - 1) {
-    int a = __ffs(m) - 1;
-    uint32_t mant = bits_i(key, (uint32_t)a) >> 9;
-    if (best < 0 || mant > bm) { best = a; bm = mant; }
+  for (uint32_t m = mask; m;) {
+    int a[4];
+    bool v[4];
+    uint32_t mant[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      v[k] = m != 0u;
+      a[k] = v[k] ? __ffs(m) - 1 : 0;
+      m &= m - 1;  // 0 stays 0
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) mant[k] = bits_i(key, (uint32_t)a[k]) >> 9;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (v[k] && (best < 0 || mant[k] > bm)) { best = a[k]; bm = mant[k]; }
   }
   return best;
 }
