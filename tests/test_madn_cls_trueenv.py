@@ -178,3 +178,17 @@ def test_throw_die_matches_the_die_values_the_reference_printed():
         env = cm.throw_die(env)
         assert env.die.cpu().tolist() == [4, 1, 6]
         assert np.array_equal(env.numpy()["key"], np.stack([jaxrand.split_host(k)[0] for k in keys]))
+
+
+@pytest.mark.gpu
+def test_dice_probabilities_match_the_reference_notebook():
+    """the distributions the reference printed for soft-locked / free players (tests/test_oracle_madn.py), on the device"""
+    from test_oracle_madn import _NOTEBOOK_BASE, notebook_dice_states
+    from exploring_muzero_on_dog_b200.MADN import classic_madn as cm
+    for flags, s, exp in notebook_dice_states():
+        env = cm.env_reset(0, num_players=2, distance=10, layout=[True, False, True, False], seed=np.array([0], np.int32),
+                           **dict(_NOTEBOOK_BASE, **flags))
+        env = env.replace(pins=s.pins, board=s.board)
+        got = cm.dice_probabilities(env).cpu().numpy().reshape(6)
+        assert np.array_equal(got, O.madn_cls_dice_probabilities(s)[0])
+        assert np.array_equal(np.round(got.astype(np.float64), 8), np.round(exp.astype(np.float64), 8))

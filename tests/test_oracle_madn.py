@@ -84,3 +84,29 @@ def test_random_play_terminates_with_plausible_length():
     s2 = O.madn_reset(cfg, seeds, 0)
     glen2, _, _ = O.madn_det_play_random(s2, key, 2000, float_gumbel=True, nthreads=4)
     assert np.array_equal(glen, glen2) and np.array_equal(s.pins, s2.pins)
+
+
+# Printed by the reference itself (MADN/jupyter_code/test_functions.ipynb cells 3-4, "Dice probabilities: ..."): a player whose
+# pins are all at home or parked at the end of the goal lane is soft-locked and throws up to three times when
+# enable_dice_rethrow is set — 1 - (5/6)^3 for the six, or (1 - (4/6)^3) / 2 each for one and six with enable_start_on_1.
+# The notebook's 2-player board (20 ring cells, goal 20..23) is the current layout's 40-cell ring with goal 40..43.
+NOTEBOOK_DICE = {(False, False): [0.16666667] * 6, (False, True): [0.16666667] * 6,
+                 (True, False): [0.11574074] * 5 + [0.4212963], (True, True): [0.35185185] + [0.07407407] * 4 + [0.35185185]}
+_NOTEBOOK_BASE = dict(enable_teams=False, enable_initial_free_pin=False, enable_circular_board=True, enable_start_blocking=False,
+                      enable_jump_in_goal_area=True, enable_friendly_fire=False, enable_bonus_turn_on_6=True, must_traverse_start=False)
+
+
+def notebook_dice_states():
+    from exploring_muzero_on_dog_b200 import rules as R
+    for (rethrow, on1), expect in NOTEBOOK_DICE.items():
+        cfg = O.MadnCfg(2, 0b0101, 10, R.to_mask(dict(_NOTEBOOK_BASE, enable_dice_rethrow=rethrow, enable_start_on_1=on1)))
+        for pins, exp in (([[-1, -1, 43, 42], [5, 6, 7, 8]], expect), ([[1, 2, 3, 4], [5, 6, 7, 8]], [0.16666667] * 6)):
+            s = O.madn_reset(cfg, np.array([0], np.int32), 0, det=False)
+            s.pins[0] = np.array(pins, np.int8)
+            s.board[...] = O.madn_set_pins_on_board(cfg, s.pins)
+            yield dict(enable_dice_rethrow=rethrow, enable_start_on_1=on1), s, np.array(exp, np.float32)
+
+
+def test_dice_probabilities_match_the_reference_notebook():
+    for _, s, exp in notebook_dice_states():
+        assert np.array_equal(np.round(O.madn_cls_dice_probabilities(s)[0].astype(np.float64), 8), np.round(exp.astype(np.float64), 8))
