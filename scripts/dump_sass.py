@@ -19,6 +19,8 @@ HOT = {  # file tag -> substring of the mangled name
     "k_mcts_expand_select_8_2": "k_mcts_expand_selectILi8ELi2EE",
     "k_mcts_expand_select_10_1": "k_mcts_expand_selectILi10ELi1EE",
     "k_replay_save": "k_replay_saveE",
+    "k_ttt_search": "k_ttt_searchILb1EE",
+    "k_madn_det_random_step": "k_madn_det_random_stepE",
 }
 
 
