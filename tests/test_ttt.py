@@ -204,6 +204,10 @@ def test_config1_fused_plays_the_same_games():
         assert torch.equal(pa, pb)
         for k, v in a.numpy().items():
             assert np.array_equal(v, b.numpy()[k]), k
+    # PolicyOutput.action as the move (the reference's eval.py takes the largest action weight instead: the default above)
+    a, pa = tm.play_mcts_games(256, jaxrand.PRNGKey(4), num_simulations=30, limit=30, variant=1, move="sample")
+    b, pb = tm.play_mcts_games(256, jaxrand.PRNGKey(4), num_simulations=30, limit=30, variant=1, move="sample", fused={})
+    assert torch.equal(pa, pb) and all(np.array_equal(v, b.numpy()[k]) for k, v in a.numpy().items())
 
 
 # ---- the reference's recorded playing strength (TicTacToe/results.md:12-15) ---------------------------------------------------
