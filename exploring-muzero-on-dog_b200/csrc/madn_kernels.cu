@@ -332,21 +332,71 @@ __device__ __forceinline__ void store_det_all(const MadnGeom& g, const MadnPtrs&
   p.done[i] = (uint8_t)s.done;
 }
 
+// One lockstep iteration per launch.  A thread owns a game (load, legal mask, move, store); the Threefry draws — one per legal
+// action, 40 % of the call's instructions when every lane draws for its own game, because a warp then runs as many passes as its
+// busiest lane has legal actions — are pooled per warp: the (game, action) pairs go to a shared list and are dealt out evenly to
+// the 32 lanes, the winner of a game is a shared-memory atomicMax on (mantissa << 5 | 23 - action): largest 23-bit mantissa, lowest
+// action on ties (jax.random.categorical's choice, as in the persistent kernel).
 __global__ void __launch_bounds__(kThreads) k_madn_det_random_step(const __grid_constant__ MadnGeom g, MadnPtrs p, int64_t n,
                                                                    Key2 rng, int64_t game_offset,
                                                                    unsigned long long* __restrict__ active_count) {
-  int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-  int active = 0;
-  if (i < n && p.done[i] == 0) {
-    MadnRegs s;
+  __shared__ uint16_t s_items[kThreads / 32][32 * 24];
+  __shared__ uint32_t s_best[kThreads / 32][32];
+  const uint32_t FULL = 0xFFFFFFFFu;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  const bool alive = i < n && p.done[i] == 0;
+  MadnRegs s;
+  Key2 key{0u, 0u};
+  uint32_t m = 0u;
+  int cp = 0;
+  bool fast = false;
+  const RuleSet<kRulesRuntime> R{g.rules};
+  if (alive) {
     load_state<true>(g, p, i, s);
-    madn_det_random_turn(g, s, split_i(rng, (uint32_t)(game_offset + i + 1)));
+    key = split_i(rng, (uint32_t)(game_offset + i + 1));
+    // 4 players, distance 10, board consistent with the pins: the branch-free bit rows of madn_fast.cuh (same results as the
+    // generic rules on every such state, tests/test_madn_fast_core.py)
+    fast = g.n == 4 && g.d == 10 && is_canonical4(s, s.occ);
+    m = fast ? det_valid_mask4(R, g, s, cp) : madn_det_valid_mask(g, s);
+  }
+  s_best[warp][lane] = 0u;
+  const int cnt = __popc(m);
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(FULL, incl, o);
+    if (lane >= o) incl += v;
+  }
+  const int total = __shfl_sync(FULL, incl, 31);
+  int off = incl - cnt;
+  for (uint32_t mm = m; mm; mm &= mm - 1) s_items[warp][off++] = (uint16_t)((lane << 8) | (__ffs(mm) - 1));
+  __syncwarp();
+  for (int base = 0; base < total; base += 64) {  // two independent Threefry chains per lane and pass
+    const int j0 = base + lane, j1 = j0 + 32;
+    const int it0 = (j0 < total) ? (int)s_items[warp][j0] : 0, it1 = (j1 < total) ? (int)s_items[warp][j1] : 0;
+    const Key2 k0{__shfl_sync(FULL, key.a, it0 >> 8), __shfl_sync(FULL, key.b, it0 >> 8)};
+    const Key2 k1{__shfl_sync(FULL, key.a, it1 >> 8), __shfl_sync(FULL, key.b, it1 >> 8)};
+    const uint32_t v0 = bits_i(k0, (uint32_t)(it0 & 0xFF)) >> 9, v1 = bits_i(k1, (uint32_t)(it1 & 0xFF)) >> 9;
+    if (j0 < total) atomicMax(&s_best[warp][it0 >> 8], (v0 << 5) | (uint32_t)(23 - (it0 & 0xFF)));
+    if (j1 < total) atomicMax(&s_best[warp][it1 >> 8], (v1 << 5) | (uint32_t)(23 - (it1 & 0xFF)));
+  }
+  __syncwarp();
+  if (alive) {
+    if (m) {
+      const int a = 23 - (int)(s_best[warp][lane] & 31u);
+      if (fast) det_step4(R, s, cp, a);
+      else madn_det_step(g, s, a / 6, a % 6 + 1, m);  // map_action (deterministic_madn.py:469-479)
+    } else if (fast) {
+      det_no_step4(s);
+    } else {
+      madn_det_no_step(g, s);
+    }
     store_det_all(g, p, i, s);
-    active = 1;
   }
   if (active_count) {
-    unsigned b = __ballot_sync(0xFFFFFFFFu, active);
-    if ((threadIdx.x & 31) == 0 && b) atomicAdd(active_count, (unsigned long long)__popc(b));
+    const unsigned b = __ballot_sync(FULL, alive);
+    if (lane == 0 && b) atomicAdd(active_count, (unsigned long long)__popc(b));
   }
 }
 
