@@ -429,8 +429,12 @@ __device__ int madn_rule_based_action(const MadnGeom& g, const MadnRegs& s, uint
   }
   float best = 0.0f;
   int best_a = -1;
+  // Only the legal actions are scored: an illegal one has logit -inf, so its gumbel + logit is -inf and it can only be the
+  // argmax if nothing is legal — and the caller comes here with m != 0.  (A Threefry pass and two double-precision logs per
+  // action: the loop is the latency of the evaluation step.)
 #pragma unroll 1
-  for (int a = 0; a < 24; ++a) {
+  for (uint32_t mm = m; mm; mm &= mm - 1) {
+    const int a = __ffs(mm) - 1;
     const int p = a / 6, k = a - 6 * p;
     const int cur_pos = byte_s(pw, p);
     const int moved = cur_pos + k, fitted = floormod(moved, g.bs);
@@ -453,7 +457,7 @@ __device__ int madn_rule_based_action(const MadnGeom& g, const MadnRegs& s, uint
     score = __fadd_rn(score, into_goal ? 5.0f : 0.0f);
     score = __fadd_rn(score, leaves_home ? out_w : 0.0f);
     score = __fadd_rn(score, hits ? 2.0f : 0.0f);
-    const float logit = ((m >> a) & 1u) ? __fdiv_rn(score, 0.25f) : __int_as_float(0xFF800000);
+    const float logit = __fdiv_rn(score, 0.25f);
     const float u = uniform_i(key, (uint32_t)a, 1.17549435e-38f, 1.0f);
     const float v = __fadd_rn(-eval_log_f(-eval_log_f(u)), logit);  // jax.random.categorical: argmax(gumbel + logits)
     if (best_a < 0 || v > best) { best = v; best_a = a; }
