@@ -53,26 +53,26 @@ def play_eval_loop(envs, params_tuple, rng_key, num_envs, search_fn=None, max_st
         raise ValueError("a seat plays by tree search: search_fn is required")
     dev = envs.device
     winners = torch.zeros((num_envs, 4), dtype=torch.int32, device=dev)
-    key = np.asarray(rng_key, dtype=np.uint32)
+    # rng_key, *step_keys = split(rng_key, num_envs + 1): element 0 does not depend on the count and is advanced in place on the host
+    key = jaxrand.KeyChain(rng_key.numpy() if isinstance(rng_key, jaxrand.KeyChain) else np.asarray(rng_key, dtype=np.uint32))
+    classic = not isinstance(envs, dm.deterministic_MADN)
     step = 0
     while step < max_steps:
         if step % poll_every == 0 and bool(envs.raw("done").all()):
             break
-        nxt = jaxrand.split_host(key)[0]  # rng_key, *step_keys = split(rng_key, num_envs + 1): element 0 does not depend on the count
         action = None
-        classic = not isinstance(envs, dm.deterministic_MADN)
         if classic:  # throw_die comes before encode_board / valid_action / the search (evaluate_agent_stochastic.py:757-760)
             cfg, st = envs.cfg(), envs.cstate()
             _lib.check(_lib.lib().dogstep_madn_cls_throw_die_active(C.byref(st), C.c_int64(envs.n), C.byref(cfg), _lib.stream()),
                        "throw_die_active")
         if needs_search:
             mod = cm if classic else dm
-            step_keys = jaxrand.split(key, num_envs + 1, device=dev)[1:].contiguous()
+            step_keys = jaxrand.split(key.numpy(), num_envs + 1, device=dev)[1:].contiguous()
             obs = mod.encode_board(envs)
             valid = mod.valid_action(envs).reshape(num_envs, -1)
             action = search_fn(params_tuple, step_keys, obs, ~valid, envs.raw("current_player")).to(torch.int32).contiguous()
         eval_step(envs, types, key, action, winners, game_offset, throw=False)
-        key = nxt
+        key.advance()
         step += 1
     return envs, winners
 
